@@ -1,0 +1,26 @@
+"""Shared pytest fixtures.  `-m gpu` tests need a B200; everything else runs on CPU."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def kitti_state():
+    from oracle import sgpr_oracle
+    return sgpr_oracle.load_state_npz(os.path.join(GOLDEN, "model_kitti.npz"))

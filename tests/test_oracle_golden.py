@@ -1,0 +1,96 @@
+"""The oracle (oracle/sgpr_oracle.py) against what the reference itself produced (tests/golden/, written by
+oracle/make_golden.py from /root/reference).  This is the pin SURVEY.md §8(c) asks for."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sgpr_oracle as orc
+
+SCORE_TOL = 2e-6      # same ATen kernels as the reference ⇒ normally bit-identical; slack for a different host ISA
+
+FIXTURE_PAIRS = [("0", "250"), ("0", "3"), ("3", "0"), ("0", "0"), ("250", "0"), ("3", "250")]
+SURVEY_TABLE = {  # SURVEY.md §4 golden table
+    (10, 100, "0", "250"): 1.34899221e-06, (10, 100, "0", "3"): 0.997977436, (10, 100, "3", "0"): 0.981845498,
+    (10, 100, "0", "0"): 0.9993492, (10, 100, "250", "0"): 2.891822e-05, (10, 100, "3", "250"): 1.4711701e-06,
+    (20, 64, "0", "250"): 0.862866104, (20, 64, "0", "3"): 0.985754967, (20, 64, "3", "0"): 0.984555066,
+}
+
+
+@pytest.fixture(scope="module")
+def fixture_pairs(golden_dir):
+    with np.load(os.path.join(golden_dir, "ref_fixture_pairs.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_golden_matches_survey_table(fixture_pairs):
+    for (K, N, a, b), want in SURVEY_TABLE.items():
+        got = float(fixture_pairs[f"K{K}_N{N}_{a}_{b}_score"][0])
+        assert abs(got - want) <= 1e-6 * max(1.0, abs(want)) + 1e-12, (K, N, a, b, got, want)
+
+
+@pytest.mark.parametrize("K,N", [(10, 100), (20, 64)])
+def test_oracle_reproduces_fixture_pairs(fixture_pairs, kitti_state, K, N):
+    for a, b in FIXTURE_PAIRS:
+        p = f"K{K}_N{N}_{a}_{b}_"
+        f1 = torch.from_numpy(fixture_pairs[p + "features_1"])
+        f2 = torch.from_numpy(fixture_pairs[p + "features_2"])
+        out = orc.forward_pairs(f1, f2, K, kitti_state, want_trace=True)
+        assert np.abs(out["score"].numpy() - fixture_pairs[p + "score"]).max() <= SCORE_TOL
+        assert np.abs(out["att_1"].numpy() - fixture_pairs[p + "att_1"]).max() <= SCORE_TOL
+        assert np.abs(out["att_2"].numpy() - fixture_pairs[p + "att_2"]).max() <= SCORE_TOL
+        assert np.abs(out["emb_1"].numpy() - fixture_pairs[p + "emb_1"]).max() <= 1e-5
+        for side in (1, 2):
+            for layer in range(6):
+                ref_idx = torch.from_numpy(fixture_pairs[p + f"knn_idx_{side}_{layer}"].astype(np.int64))
+                ok = orc.knn_sets_equivalent(out[f"knn_pd_{side}"][layer], out[f"knn_idx_{side}"][layer], ref_idx)
+                assert bool(ok.all()), (K, N, a, b, side, layer)
+                np.testing.assert_allclose(out[f"layer_out_{side}"][layer].numpy(),
+                                           fixture_pairs[p + f"layer_out_{side}_{layer}"], atol=1e-5, rtol=0)
+
+
+@pytest.mark.parametrize("tag", ["n64_k20", "n100_k10", "n32_k10", "n128_k20", "n16_k10", "n64_k20_dense"])
+def test_oracle_reproduces_synthetic(golden_dir, kitti_state, tag):
+    with np.load(os.path.join(golden_dir, f"ref_synth_{tag}.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    K = int(g["K"])
+    out = orc.forward_pairs(torch.from_numpy(g["features_1"]), torch.from_numpy(g["features_2"]), K, kitti_state,
+                            want_trace=True)
+    assert np.abs(out["score"].numpy() - g["score"]).max() <= SCORE_TOL
+    assert np.abs(out["att_1"].numpy() - g["att_1"]).max() <= SCORE_TOL
+    assert np.abs(out["emb_2"].numpy() - g["emb_2"]).max() <= 1e-5
+    for side in (1, 2):
+        for layer in range(6):
+            ref_idx = torch.from_numpy(g[f"knn_idx_{side}_{layer}"].astype(np.int64))
+            # same topk kernel as the reference ⇒ identical index tensors, not just equivalent sets
+            assert torch.equal(out[f"knn_idx_{side}"][layer], ref_idx), (tag, side, layer)
+
+
+def test_synthetic_inputs_are_reproducible(golden_dir):
+    """The seeded generator must give the bytes the golden vectors were made from."""
+    from sg_pr_b200 import synth
+    with np.load(os.path.join(golden_dir, "ref_synth_n64_k20.npz")) as z:
+        f1, f2 = synth.make_pair_batch(z["features_1"].shape[0], int(z["N"]), int(z["K"]), seed=int(z["seed"]))
+        assert np.array_equal(f1.numpy(), z["features_1"]) and np.array_equal(f2.numpy(), z["features_2"])
+
+
+@pytest.mark.parametrize("tag", ["3_20_08", "10_20_05"])
+def test_oracle_other_checkpoints(golden_dir, tag):
+    sd = orc.load_state_npz(os.path.join(golden_dir, f"model_{tag}.npz"))
+    with np.load(os.path.join(golden_dir, "ref_ckpt_scores.npz")) as z:
+        out = orc.forward_pairs(torch.from_numpy(z["features_1"]), torch.from_numpy(z["features_2"]), 20, sd)
+        assert np.abs(out["score"].numpy() - z[f"score_{tag}"]).max() <= SCORE_TOL
+        assert np.abs(out["att_1"].numpy() - z[f"att_1_{tag}"]).max() <= SCORE_TOL
+
+
+def test_score_matrix_matches_pairwise(kitti_state):
+    from sg_pr_b200 import synth
+    g = synth.make_graphs(6, 64, 20, seed=5)
+    emb = orc.embed_graphs(g, 20, kitti_state)
+    pooled = emb["pooled"].squeeze(-1)
+    mat = orc.score_matrix(pooled[:3], pooled, kitti_state)
+    for i in range(3):
+        for j in range(6):
+            s = orc.forward_pairs(g[i:i + 1], g[j:j + 1], 20, kitti_state)["score"][0]
+            assert abs(float(mat[i, j]) - float(s)) <= 1e-6
