@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — graph-pairs/sec of the SG_PR hot path (BASELINE.json: batch 128, 64-node graphs, k=20) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path (oracle port) on host cores
+
+A step = one `SG.forward` over one batch of 128 graph pairs drawn from a synthetic 1000-graph sequence
+(BASELINE.json configs[1]).  `value`: inputs already in HBM, one fused kernel launch per step, device-timed.
+`e2e`: the same step through the drop-in module call `model(data)` with pinned HOST tensors and the score read
+back with `.cpu()` — what eval_batch.py does per batch (sg_net.py:517-523).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from sg_pr_b200 import synth  # noqa: E402
+
+BATCH, NODES, K_NN, SEQ_GRAPHS = 128, 64, 20, 1000
+ALG_BYTES_PER_PAIR = 128 * NODES + 4          # 2x15xNx4 read + (2N+1)x4 written = 8,196 B at N=64
+ALG_FLOP_PER_PAIR = 12.9e6                    # SURVEY §8(d), exact refactored form
+L2_BYTES = 126 * 1024 * 1024
+METRIC = "graph-pairs/sec @ batch 128, 64-node graphs, k=20"
+WORKLOAD = "eval_batch synthetic sequence of 1000 graphs, 64 nodes x 12 feat, k=20, batch 128 (BASELINE configs[1])"
+
+
+def load_state():
+    import numpy as np
+    with np.load(os.path.join(ROOT, "tests", "golden", "model_kitti.npz")) as z:
+        return {k: torch.from_numpy(z[k].copy()) for k in z.files}
+
+
+def build_batches(num_batches: int, seed: int):
+    """Pair batches gathered from one synthetic sequence: two [num_batches, 128, 15, 64] fp32 CPU tensors."""
+    graphs = synth.make_graphs(SEQ_GRAPHS, NODES, K_NN, seed=seed)
+    pairs = synth.make_sequence_pairs(SEQ_GRAPHS, num_batches * BATCH, seed=seed)
+    f1 = graphs[pairs[:, 0]].view(num_batches, BATCH, synth.NUM_CHANNELS, NODES).contiguous()
+    f2 = graphs[pairs[:, 1]].view(num_batches, BATCH, synth.NUM_CHANNELS, NODES).contiguous()
+    return f1, f2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def time_cpu_oracle(state, f1, f2, budget_s: float, max_batches: int):
+    """Oracle port of the reference's CPU SG.forward on all host threads: returns (pairs/s, pairs timed, seconds)."""
+    from oracle import sgpr_oracle as orc
+    orc.forward_pairs(f1[0][:16], f2[0][:16], K_NN, state)            # warm-up (thread pool, oneDNN primitives)
+    done, t0 = 0, time.perf_counter()
+    for i in range(max_batches):
+        orc.forward_pairs(f1[i % f1.shape[0]], f2[i % f1.shape[0]], K_NN, state)
+        done += BATCH
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def run_reference_arm(args, rank: int):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is Python/PyTorch and
+    /root/reference does not exist on the GPU box, so this times the oracle port (same ATen CPU kernels, reference
+    arithmetic form) — cpu_baseline.kind = "port"."""
+    if rank != 0:
+        return
+    from oracle import sgpr_oracle as orc
+    state = load_state()
+    f1, f2 = build_batches(4, seed=0)
+    threads = torch.get_num_threads()
+    # size one step so that warmup+steps fit in ~2.5 minutes
+    t0 = time.perf_counter()
+    orc.forward_pairs(f1[0], f2[0], K_NN, state)
+    t128 = time.perf_counter() - t0
+    per_step_budget = 150.0 / max(1, args.steps + args.warmup)
+    pairs_per_step = int(max(8, min(BATCH, BATCH * per_step_budget / max(t128, 1e-6))))
+    sl = slice(0, pairs_per_step)
+    for i in range(args.warmup):
+        orc.forward_pairs(f1[i % 4][sl], f2[i % 4][sl], K_NN, state)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        orc.forward_pairs(f1[i % 4][sl], f2[i % 4][sl], K_NN, state)
+    dt = time.perf_counter() - t0
+    value = args.steps * pairs_per_step / dt
+    sample = f"{args.steps} steps x {pairs_per_step} pairs of the batch-128 workload, oracle port (torch CPU ops), {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "graph-pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": BATCH, "node_num": NODES, "k": K_NN, "graphs": SEQ_GRAPHS,
+                   "pairs_per_step": pairs_per_step},
+        "cpu_baseline": {"value": value, "unit": "graph-pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "graph-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3 if args.impl == "ours" else 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SG
+
+    state = load_state()
+    margs = sgpr_args()
+    margs.K, margs.node_num, margs.gpu, margs.cuda = K_NN, NODES, local_rank, str(local_rank)
+    model = SG(margs, synth.NUM_LABELS)
+    model.load_state_dict(state)
+    model.cuda(local_rank).eval()
+    eng = model.engine()
+
+    # rotating input set larger than L2 so every step reads cold inputs
+    per_batch = 2 * BATCH * synth.NUM_CHANNELS * NODES * 4
+    num_batches = L2_BYTES // per_batch + 24
+    f1_cpu, f2_cpu = build_batches(num_batches, seed=100 + rank)
+    f1_dev, f2_dev = f1_cpu.to(dev), f2_cpu.to(dev)
+    f1_pin, f2_pin = f1_cpu.pin_memory(), f2_cpu.pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        j = i % num_batches
+        return eng.forward_pairs(f1_dev[j], f2_dev[j], K_NN, want_att=True)
+
+    def step_e2e(i):
+        j = i % num_batches
+        with torch.no_grad():
+            prediction, _, _ = model({"features_1": f1_pin[j], "features_2": f2_pin[j]})
+        return prediction.cpu()
+
+    # ---------------- value: device-resident inputs ----------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    # stretch the clock sample over a long enough window to catch samples: keep the GPU busy ~1.5 s more (untimed)
+    if sampler is not None:
+        t_end = time.perf_counter() + 1.5
+        i = 0
+        while time.perf_counter() < t_end:
+            step_device(i)
+            i += 1
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    else:
+        clocks = None
+
+    # ---------------- e2e: host tensors through the drop-in module ----------------
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    # ---------------- same through the raw C-ABI host entry point (extra, informative) ----------------
+    out = (torch.empty(BATCH).pin_memory(), None, None)
+    for i in range(args.warmup):
+        eng.forward_pairs_host(f1_pin[i % num_batches], f2_pin[i % num_batches], K_NN, want_att=False, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        j = (args.warmup + i) % num_batches
+        eng.forward_pairs_host(f1_pin[j], f2_pin[j], K_NN, want_att=False, out=out)
+    barrier()
+    cabi_ms = (time.perf_counter() - t0) * 1e3
+
+    times = torch.tensor([dev_ms, e2e_ms, cabi_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, cabi_ms = (float(x) for x in times.tolist())
+
+    if rank == 0:
+        total_pairs = world * BATCH * args.steps
+        value = total_pairs / (dev_ms * 1e-3)
+        kernel_s = dev_ms * 1e-3 / args.steps            # the timed region is exactly `steps` launches of the fused kernel
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = BATCH * ALG_BYTES_PER_PAIR / kernel_s / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "embed_kernel_ncu_summary.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "graph-pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch": BATCH, "node_num": NODES, "k": K_NN, "graphs": SEQ_GRAPHS,
+                       "weights": "model/model.pth of the reference (tests/golden/model_kitti.npz)",
+                       "parallelism": f"{world} independent replicas (pair batches sharded, no data-path collective)",
+                       "l2": f"rotating set of {num_batches} input batches = {num_batches * per_batch / 2**20:.0f} MiB > 126 MiB L2"},
+            "e2e": {"value": total_pairs / (e2e_ms * 1e-3), "unit": "graph-pairs/s",
+                    "h2d_bytes_per_step": per_batch, "d2h_bytes_per_step": BATCH * 4,
+                    "api": "sg_pr_b200.sg_net.SG.forward(data) with pinned CPU tensors + prediction.cpu()",
+                    "ms_per_step": e2e_ms / args.steps,
+                    "c_abi_host_call": {"value": total_pairs / (cabi_ms * 1e-3), "ms_per_step": cabi_ms / args.steps}},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "kernel": "sgpr_embed_kernel<2> (fused EdgeConv x6 + attention + NTN head)",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "algorithmic_bytes_per_launch": BATCH * ALG_BYTES_PER_PAIR,
+                         "avg_kernel_us": kernel_s * 1e6,
+                         "note": "path is issue/latency-bound (~1570 flop/B, SURVEY §8d); see compute_roofline"},
+            "compute_roofline": {"bound": "fp32-fma", "achieved_tflops": BATCH * ALG_FLOP_PER_PAIR / kernel_s / 1e12,
+                                 "peak_tflops_nominal": 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12,
+                                 "flop_per_pair": ALG_FLOP_PER_PAIR},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, n, dt = time_cpu_oracle(state, f1_cpu, f2_cpu, budget_s=15.0, max_batches=16)
+            line["cpu_baseline"] = {"value": v, "unit": "graph-pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{n} pairs ({n // BATCH} batches of 128) of the same workload in {dt:.1f} s, "
+                                              f"oracle port of the reference CPU path (torch {torch.__version__})"}
+        print(json.dumps(line), flush=True)
+
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,7 @@ def edgeconv(x: torch.Tensor, k: int, sd, layer: str, trace: dict | None = None)
     if trace is not None:
         trace.setdefault("knn_idx", []).append(idx)
         trace.setdefault("knn_pd", []).append(pd)
+        trace.setdefault("layer_in", []).append(x)
         trace.setdefault("layer_out", []).append(out)
     return out
 
@@ -146,7 +147,7 @@ def forward_pairs(f1: torch.Tensor, f2: torch.Tensor, k: int, sd, want_trace: bo
            "pooled_1": g1["pooled"], "pooled_2": g2["pooled"], "emb_1": g1["emb"], "emb_2": g2["emb"]}
     if want_trace:
         for side, g in (("1", g1), ("2", g2)):
-            for key in ("knn_idx", "knn_pd", "layer_out"):
+            for key in ("knn_idx", "knn_pd", "layer_in", "layer_out"):
                 out[f"{key}_{side}"] = g[key]
     return out
 
@@ -162,12 +163,26 @@ def score_matrix(pooled_rows: torch.Tensor, pooled_cols: torch.Tensor, sd) -> to
     return score_head(ntn_vector(e1, e2, sd), sd).view(r, m)
 
 
-def knn_sets_equivalent(pd_ref: torch.Tensor, idx_ref: torch.Tensor, idx_test: torch.Tensor) -> torch.Tensor:
-    """Per-row verdict that two k-NN index sets select the same multiset of reference distances
-    (swaps among exact ties are not errors — SURVEY §7 hard part 2).  Returns bool [B, N]."""
+def knn_sets_equivalent(pd_ref: torch.Tensor, idx_ref: torch.Tensor, idx_test: torch.Tensor,
+                        x_in: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-row verdict that two k-NN index sets are the same selection up to exact ties (SURVEY §7 hard parts 1-2).
+    Two rows agree when either
+      (a) they pick the same multiset of reference distances, or
+      (b) (needs the layer input `x_in` [B, C, N]) they pick the same multiset of NODE VECTORS — indices are mapped
+          to the first node with a bit-identical feature vector; zero pads and same-label nodes are such
+          duplicates, and the reference itself chooses among them by sgemm rounding noise.
+    Returns bool [B, N]."""
     a = torch.gather(pd_ref, -1, idx_ref.long()).sort(dim=-1)[0]
     b = torch.gather(pd_ref, -1, idx_test.long()).sort(dim=-1)[0]
-    return (a == b).all(dim=-1)
+    same = (a == b).all(dim=-1)
+    if x_in is not None:
+        rows = x_in.transpose(2, 1)
+        dup = (rows[:, :, None, :] == rows[:, None, :, :]).all(dim=-1)
+        canon = dup.to(torch.uint8).argmax(dim=-1)                       # first identical node
+        ca = torch.gather(canon[:, None, :].expand(-1, idx_ref.shape[1], -1), -1, idx_ref.long()).sort(dim=-1)[0]
+        cb = torch.gather(canon[:, None, :].expand(-1, idx_test.shape[1], -1), -1, idx_test.long()).sort(dim=-1)[0]
+        same = same | (ca == cb).all(dim=-1)
+    return same
 
 
 def load_state_npz(path: str) -> Dict[str, torch.Tensor]:

@@ -1,0 +1,359 @@
+// C-ABI implementation (include/sgpr_b200.h): context, weight packing/upload, kernel launches.
+// No torch types, links only cudart.  There is deliberately no CPU path: every entry point needs the device.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/sgpr_b200.h"
+#include "common.cuh"
+#include "embed_kernel.cuh"
+#include "head_kernels.cuh"
+#include "pack.hpp"
+
+using namespace sgpr;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess) return fail(SGPR_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int ensure(T*& ptr, size_t& cap, size_t need) {
+    if (need <= cap) return SGPR_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T));
+    if (e != cudaSuccess) return fail(SGPR_E_CUDA, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+    cap = want;
+    return SGPR_OK;
+}
+
+}  // namespace
+
+struct sgpr_ctx {
+    int device = 0;
+    int sm_count = 0;
+    bool has_weights = false;
+    float* d_blob = nullptr;
+    PackOffsets off{};
+    PackedWeights pw{};
+    HeadParams hp{};
+    int* d_counters = nullptr;   size_t counters_cap = 0;
+    float* d_pooled = nullptr;   size_t pooled_cap = 0;
+    float* d_in = nullptr;       size_t in_cap = 0;      // host-path staging: f1 | f2
+    float* d_out = nullptr;      size_t out_cap = 0;     // host-path staging: score | att1 | att2
+    float* d_proj = nullptr;     size_t proj_cap = 0;
+    float* d_blk = nullptr;      size_t blk_cap = 0;     // rowblk | colblk
+    cudaStream_t stream = nullptr;                      // host-path stream
+    long long launches = 0;
+};
+
+extern "C" {
+
+int sgpr_abi_version(void) { return SGPR_ABI_VERSION; }
+
+const char* sgpr_last_error(void) { return g_err; }
+
+int sgpr_create(sgpr_ctx** out, int device) {
+    if (!out) return fail(SGPR_E_INVALID, "sgpr_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SGPR_E_CUDA, "sgpr_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(SGPR_E_INVALID, "sgpr_create: device %d out of range [0,%d)", device, count);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(SGPR_E_CUDA, "sgpr_create: cudaSetDevice(%d) failed", device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SGPR_E_CUDA, "sgpr_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    sgpr_ctx* ctx = new (std::nothrow) sgpr_ctx();
+    if (!ctx) return fail(SGPR_E_CUDA, "sgpr_create: out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->off = make_offsets();
+    const int max_smem = static_cast<int>(prop.sharedMemPerBlockOptin);
+    e = cudaFuncSetAttribute(sgpr_embed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_embed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_embed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_score_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_blob), ctx->off.total * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        int rc = fail(SGPR_E_CUDA, "sgpr_create: %s", cudaGetErrorString(e));
+        sgpr_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return SGPR_OK;
+}
+
+int sgpr_destroy(sgpr_ctx* ctx) {
+    if (!ctx) return SGPR_OK;
+    DeviceGuard guard(ctx->device);
+    cudaFree(ctx->d_blob);
+    cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_pooled);
+    cudaFree(ctx->d_in);
+    cudaFree(ctx->d_out);
+    cudaFree(ctx->d_proj);
+    cudaFree(ctx->d_blk);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SGPR_OK;
+}
+
+int sgpr_set_weights(sgpr_ctx* ctx, const sgpr_weights* w) {
+    if (!ctx || !w) return fail(SGPR_E_INVALID, "sgpr_set_weights: NULL argument");
+    if (w->filters[0] != SGPR_FILTERS_1 || w->filters[1] != SGPR_FILTERS_2 || w->filters[2] != SGPR_FILTERS_3 ||
+        w->tensor_neurons != SGPR_TENSOR_NEURONS || w->bottleneck != SGPR_BOTTLENECK)
+        return fail(SGPR_E_ARCH,
+                    "sgpr_set_weights: kernels are built for filters 64/64/32, tensor_neurons 16, bottle_neck 16 "
+                    "(got %d/%d/%d, %d, %d)",
+                    w->filters[0], w->filters[1], w->filters[2], w->tensor_neurons, w->bottleneck);
+    const void* must[] = {w->s_conv_w[0], w->s_conv_w[1], w->s_conv_w[2], w->f_conv_w[0], w->f_conv_w[1], w->f_conv_w[2],
+                          w->end_conv_w, w->att_w, w->ntn_w, w->ntn_v, w->ntn_b, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b,
+                          w->end_bn.weight, w->end_bn.bias, w->end_bn.running_mean, w->end_bn.running_var};
+    for (const void* p : must)
+        if (!p) return fail(SGPR_E_INVALID, "sgpr_set_weights: a weight pointer is NULL");
+    for (int l = 0; l < 3; ++l) {
+        const sgpr_bn* bns[2] = {&w->s_bn[l], &w->f_bn[l]};
+        for (const sgpr_bn* b : bns)
+            if (!b->weight || !b->bias || !b->running_mean || !b->running_var)
+                return fail(SGPR_E_INVALID, "sgpr_set_weights: a BatchNorm pointer is NULL");
+    }
+    DeviceGuard guard(ctx->device);
+    std::vector<float> blob;
+    pack_weights(*w, blob, ctx->hp, ctx->off);
+    // synchronous copy: the host vector dies at return, and weights must be visible to every stream afterwards
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(ctx->d_blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const float* b = ctx->d_blob;
+    const PackOffsets& o = ctx->off;
+    ctx->pw = PackedWeights{b + o.s1,    b + o.w_s2,  b + o.w_s3,  b + o.w_f1,  b + o.w_f2,  b + o.w_f3,
+                            b + o.w_end, b + o.ab_s2, b + o.ab_s3, b + o.ab_f1, b + o.ab_f2, b + o.ab_f3,
+                            b + o.ab_end, b + o.att_w, b + o.ntn_w, b + o.ntn_v, b + o.ntn_b};
+    ctx->has_weights = true;
+    return SGPR_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int check_shape(const char* who, int count, int N, int k) {
+    if (count < 0) return fail(SGPR_E_INVALID, "%s: negative batch %d", who, count);
+    if (N < 1 || N > SGPR_MAX_NODES) return fail(SGPR_E_INVALID, "%s: node_num %d outside [1,%d]", who, N, SGPR_MAX_NODES);
+    if (k < 1 || k > N)
+        return fail(SGPR_E_INVALID, "%s: k=%d must satisfy 1 <= k <= node_num=%d (topk raises in the reference, dgcnn.py:19)",
+                    who, k, N);
+    return SGPR_OK;
+}
+
+int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
+    const int N = a.N;
+    a.KS = (a.k + 3) & ~3;
+    const int npl = (N <= 32) ? 1 : (N <= 64) ? 2 : 4;
+    const SmemLayout L = make_layout(32 * npl, a.KS);
+    const int per_sm = (npl <= 2) ? 2 : 1;
+    int grid = a.G < ctx->sm_count * per_sm ? a.G : ctx->sm_count * per_sm;
+    if (grid < 1) return SGPR_OK;
+    switch (npl) {
+        case 1: sgpr_embed_kernel<1><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
+        case 2: sgpr_embed_kernel<2><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
+        default: sgpr_embed_kernel<4><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
+    }
+    ctx->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SGPR_E_CUDA, "embed kernel launch failed: %s", cudaGetErrorString(e));
+    return SGPR_OK;
+}
+
+int forward_pairs_impl(sgpr_ctx* ctx, const float* f1, const float* f2, int B, int N, int k, float* score, float* att1,
+                       float* att2, cudaStream_t st) {
+    int rc = ensure(ctx->d_pooled, ctx->pooled_cap, static_cast<size_t>(2) * B * kF3);
+    if (rc) return rc;
+    if (static_cast<size_t>(B) > ctx->counters_cap) {
+        rc = ensure(ctx->d_counters, ctx->counters_cap, static_cast<size_t>(B));
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_cap * sizeof(int), st));
+    }
+    EmbedArgs a{};
+    a.g0 = f1; a.g1 = f2; a.G = 2 * B; a.N = N; a.k = k; a.pairs = 1;
+    a.pooled = ctx->d_pooled; a.att0 = att1; a.att1 = att2; a.emb = nullptr;
+    a.score = score; a.counters = ctx->d_counters; a.trace_knn = nullptr; a.trace_layers = nullptr;
+    return launch_embed(ctx, a, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgpr_forward_pairs(sgpr_ctx* ctx, const float* f1_dev, const float* f2_dev, int B, int N, int k, float* score_dev,
+                       float* att1_dev, float* att2_dev, void* stream) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_forward_pairs: ctx is NULL");
+    if (!ctx->has_weights) return fail(SGPR_E_NOWEIGHTS, "sgpr_forward_pairs: call sgpr_set_weights first");
+    int rc = check_shape("sgpr_forward_pairs", B, N, k);
+    if (rc) return rc;
+    if (B == 0) return SGPR_OK;
+    if (!f1_dev || !f2_dev || !score_dev) return fail(SGPR_E_INVALID, "sgpr_forward_pairs: NULL feature/score pointer");
+    DeviceGuard guard(ctx->device);
+    return forward_pairs_impl(ctx, f1_dev, f2_dev, B, N, k, score_dev, att1_dev, att2_dev, static_cast<cudaStream_t>(stream));
+}
+
+int sgpr_forward_pairs_host(sgpr_ctx* ctx, const float* f1_host, const float* f2_host, int B, int N, int k,
+                            float* score_host, float* att1_host, float* att2_host) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_forward_pairs_host: ctx is NULL");
+    if (!ctx->has_weights) return fail(SGPR_E_NOWEIGHTS, "sgpr_forward_pairs_host: call sgpr_set_weights first");
+    int rc = check_shape("sgpr_forward_pairs_host", B, N, k);
+    if (rc) return rc;
+    if (B == 0) return SGPR_OK;
+    if (!f1_host || !f2_host || !score_host) return fail(SGPR_E_INVALID, "sgpr_forward_pairs_host: NULL feature/score pointer");
+    DeviceGuard guard(ctx->device);
+    const size_t side = static_cast<size_t>(B) * kInCh * N;
+    const size_t att = static_cast<size_t>(B) * N;
+    rc = ensure(ctx->d_in, ctx->in_cap, 2 * side);
+    if (rc) return rc;
+    rc = ensure(ctx->d_out, ctx->out_cap, static_cast<size_t>(B) + 2 * att);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_in, f1_host, side * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_in + side, f2_host, side * sizeof(float), cudaMemcpyHostToDevice, st));
+    float* d_score = ctx->d_out;
+    float* d_att1 = ctx->d_out + B;
+    float* d_att2 = d_att1 + att;
+    rc = forward_pairs_impl(ctx, ctx->d_in, ctx->d_in + side, B, N, k, d_score, att1_host ? d_att1 : nullptr,
+                            att2_host ? d_att2 : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(score_host, d_score, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (att1_host) CUDA_TRY(cudaMemcpyAsync(att1_host, d_att1, att * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (att2_host) CUDA_TRY(cudaMemcpyAsync(att2_host, d_att2, att * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return SGPR_OK;
+}
+
+int sgpr_embed_trace(sgpr_ctx* ctx, const float* graphs_dev, int M, int N, int k, float* pooled_dev, float* att_dev,
+                     float* emb_dev, uint8_t* knn_dev, float* layer_out_dev, void* stream) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_embed: ctx is NULL");
+    if (!ctx->has_weights) return fail(SGPR_E_NOWEIGHTS, "sgpr_embed: call sgpr_set_weights first");
+    int rc = check_shape("sgpr_embed", M, N, k);
+    if (rc) return rc;
+    if (M == 0) return SGPR_OK;
+    if (!graphs_dev || !pooled_dev) return fail(SGPR_E_INVALID, "sgpr_embed: NULL graphs/pooled pointer");
+    DeviceGuard guard(ctx->device);
+    EmbedArgs a{};
+    a.g0 = graphs_dev; a.g1 = nullptr; a.G = M; a.N = N; a.k = k; a.pairs = 0;
+    a.pooled = pooled_dev; a.att0 = att_dev; a.att1 = nullptr; a.emb = emb_dev;
+    a.score = nullptr; a.counters = nullptr; a.trace_knn = knn_dev; a.trace_layers = layer_out_dev;
+    return launch_embed(ctx, a, static_cast<cudaStream_t>(stream));
+}
+
+int sgpr_embed(sgpr_ctx* ctx, const float* graphs_dev, int M, int N, int k, float* pooled_dev, float* att_dev,
+               float* emb_dev, void* stream) {
+    return sgpr_embed_trace(ctx, graphs_dev, M, N, k, pooled_dev, att_dev, emb_dev, nullptr, nullptr, stream);
+}
+
+int sgpr_score_pairs(sgpr_ctx* ctx, const float* pooled_dev, const int32_t* pair_idx_dev, int P, float* score_dev,
+                     void* stream) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_score_pairs: ctx is NULL");
+    if (!ctx->has_weights) return fail(SGPR_E_NOWEIGHTS, "sgpr_score_pairs: call sgpr_set_weights first");
+    if (P < 0) return fail(SGPR_E_INVALID, "sgpr_score_pairs: negative pair count");
+    if (P == 0) return SGPR_OK;
+    if (!pooled_dev || !pair_idx_dev || !score_dev) return fail(SGPR_E_INVALID, "sgpr_score_pairs: NULL pointer");
+    DeviceGuard guard(ctx->device);
+    const int grid = P < ctx->sm_count * 8 ? P : ctx->sm_count * 8;
+    sgpr_score_pairs_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(pooled_dev, pair_idx_dev, P, score_dev,
+                                                                                      ctx->pw, ctx->hp);
+    ctx->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return SGPR_OK;
+}
+
+int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const float* pooled_cols_dev, int M,
+                      float* scores_dev, int64_t ld_scores, void* stream) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_score_matrix: ctx is NULL");
+    if (!ctx->has_weights) return fail(SGPR_E_NOWEIGHTS, "sgpr_score_matrix: call sgpr_set_weights first");
+    if (R < 0 || M < 0) return fail(SGPR_E_INVALID, "sgpr_score_matrix: negative size");
+    if (R == 0 || M == 0) return SGPR_OK;
+    if (ld_scores < M) return fail(SGPR_E_INVALID, "sgpr_score_matrix: ld_scores %lld < M %d", (long long)ld_scores, M);
+    if (!pooled_rows_dev || !pooled_cols_dev || !scores_dev) return fail(SGPR_E_INVALID, "sgpr_score_matrix: NULL pointer");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = ensure(ctx->d_proj, ctx->proj_cap, static_cast<size_t>(R) * 512);
+    if (rc) return rc;
+    rc = ensure(ctx->d_blk, ctx->blk_cap, (static_cast<size_t>(R) + M) * kT);
+    if (rc) return rc;
+    float* rowblk = ctx->d_blk;
+    float* colblk = ctx->d_blk + static_cast<size_t>(R) * kT;
+    const int cap = ctx->sm_count * 8;
+    sgpr_ntn_prep_kernel<<<R < cap ? R : cap, kThreads, 0, st>>>(pooled_rows_dev, R, ctx->d_proj, rowblk, nullptr, ctx->pw);
+    sgpr_ntn_prep_kernel<<<M < cap ? M : cap, kThreads, 0, st>>>(pooled_cols_dev, M, nullptr, nullptr, colblk, ctx->pw);
+    const dim3 grid((M + kSmTJ - 1) / kSmTJ, (R + kSmTI - 1) / kSmTI);
+    const size_t smem = (kSmTI * 512 + kSmTI * kT) * sizeof(float);
+    sgpr_score_matrix_kernel<<<grid, kThreads, smem, st>>>(ctx->d_proj, rowblk, pooled_cols_dev, colblk, R, M, scores_dev,
+                                                           static_cast<long long>(ld_scores), ctx->pw.ntn_b, ctx->hp);
+    ctx->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return SGPR_OK;
+}
+
+int64_t sgpr_launch_count(const sgpr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+size_t sgpr_packed_size(void) { return make_offsets().total; }
+
+int sgpr_pack_weights_host(const sgpr_weights* w, float* blob, float* head289, size_t* offsets17) {
+    if (!w || !blob || !head289 || !offsets17) return fail(SGPR_E_INVALID, "sgpr_pack_weights_host: NULL argument");
+    if (w->filters[0] != SGPR_FILTERS_1 || w->filters[1] != SGPR_FILTERS_2 || w->filters[2] != SGPR_FILTERS_3 ||
+        w->tensor_neurons != SGPR_TENSOR_NEURONS || w->bottleneck != SGPR_BOTTLENECK)
+        return fail(SGPR_E_ARCH, "sgpr_pack_weights_host: unsupported layer sizes");
+    const PackOffsets o = make_offsets();
+    std::vector<float> tmp;
+    HeadParams hp;
+    pack_weights(*w, tmp, hp, o);
+    std::memcpy(blob, tmp.data(), tmp.size() * sizeof(float));
+    std::memcpy(head289, hp.fc1_w, 256 * sizeof(float));
+    std::memcpy(head289 + 256, hp.fc1_b, 16 * sizeof(float));
+    std::memcpy(head289 + 272, hp.fc2_w, 16 * sizeof(float));
+    head289[288] = hp.fc2_b;
+    const size_t offs[17] = {o.s1, o.w_s2, o.w_s3, o.w_f1, o.w_f2, o.w_f3, o.w_end, o.ab_s2, o.ab_s3, o.ab_f1,
+                             o.ab_f2, o.ab_f3, o.ab_end, o.att_w, o.ntn_w, o.ntn_v, o.ntn_b};
+    std::memcpy(offsets17, offs, sizeof(offs));
+    return SGPR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Shared definitions for the sm_100a SG_PR kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgpr {
+
+constexpr int kThreads = 256;          // one CTA = 8 warps works on one graph
+constexpr int kWarps   = kThreads / 32;
+
+constexpr int kLabels  = 12;           // sg_net.py:200-202
+constexpr int kInCh    = 3 + kLabels;  // [15][N] channel-major input block, sg_net.py:296-299
+constexpr int kF1 = 64, kF2 = 64, kF3 = 32;      // config.yml:11-13
+constexpr int kT  = 16;                // tensor_neurons, config.yml:14
+constexpr int kBn = 16;                // bottle_neck_neurons, config.yml:15
+
+constexpr int XS = 68;    // row stride (floats) of node-major feature tiles: 64 + 4 keeps LDS.128 conflict-free
+constexpr int YS = 132;   // row stride of the per-node GEMM output tile A|B: 128 + 4
+
+constexpr float kSlope = 0.2f;         // LeakyReLU(negative_slope=0.2), sg_net.py:53
+
+// Packed eval-mode parameters in device memory (built by pack.cpp, one allocation).
+// EdgeConv l with C_in -> C_out: `w` is [C_in][2*C_out] (k-major, so lanes read consecutive output channels):
+//   columns [0, C_out)        = sign[c] * W[c][ci]          (the (x_j - x_i) half of the 1x1 conv, dgcnn.py:47)
+//   columns [C_out, 2*C_out)  = sign[c] * W[c][C_in + ci]   (the x_i half)
+// `alpha`/`beta` are the BN-eval scale/shift with alpha made non-negative by folding its sign into `w`
+// (max over neighbours then commutes exactly with BN+LeakyReLU, SURVEY §7 hard part 5).
+struct PackedWeights {
+    const float* s1;        // xyz layer 1: [64][8] = {wa0,wa1,wa2, wb0,wb1,wb2, alpha, beta} per output channel
+    const float* w_s2;      // [64][128]
+    const float* w_s3;      // [64][64]
+    const float* w_f1;      // [12][128]
+    const float* w_f2;      // [64][128]
+    const float* w_f3;      // [64][64]
+    const float* w_end;     // [64][32]   plain transpose of dgcnn_conv_end.0.weight
+    const float* ab_s2;     // alpha[64] beta[64]
+    const float* ab_s3;     // alpha[32] beta[32]
+    const float* ab_f1;     // alpha[64] beta[64]
+    const float* ab_f2;     // alpha[64] beta[64]
+    const float* ab_f3;     // alpha[32] beta[32]
+    const float* ab_end;    // alpha[32] beta[32]  (sign NOT folded: no max follows)
+    const float* att_w;     // [32][32]   attention.weight_matrix (row = input feature)
+    const float* ntn_w;     // [32][512]  tensor_network.weight_matrix.view(32, 32*16): col = b*16 + t
+    const float* ntn_v;     // [16][64]
+    const float* ntn_b;     // [16]
+};
+
+// FC head, small enough to travel as a kernel parameter (constant bank, uniform access).
+struct HeadParams {
+    float fc1_w[kBn * kT];  // [16][16] row = output
+    float fc1_b[kBn];
+    float fc2_w[kBn];
+    float fc2_b;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) -------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.0f ? x : x * kSlope; }
+
+}  // namespace sgpr

@@ -1,0 +1,155 @@
+// Pair-head kernels on pooled graph vectors: explicit pair lists and the all-pairs score matrix.
+//
+// Reference math: TenorNetworkModule.forward (/root/reference/layers_batch.py:70-83) followed by
+// relu(fully_connected_first) and sigmoid(scoring_layer) (/root/reference/sg_net.py:131-136).
+// The reference never forms the M x M matrix online (only the offline loop in
+// data_process/gen_sem_kitti_graph_pairs.py:43-52); this is the embed-once / score-matrix split of SURVEY §8(f1).
+#pragma once
+#include "common.cuh"
+#include "embed_kernel.cuh"
+
+namespace sgpr {
+
+// ---- explicit pair list: one CTA per pair ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+sgpr_score_pairs_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ pair_idx, int P,
+                        float* __restrict__ score, const PackedWeights W, const HeadParams H) {
+    __shared__ float e[64];
+    __shared__ float scratch[512 + 64];
+    const int tid = threadIdx.x;
+    for (int p = blockIdx.x; p < P; p += gridDim.x) {
+        if (tid < 64) {
+            const int side = tid >> 5;
+            e[tid] = __ldg(pooled + static_cast<size_t>(pair_idx[2 * p + side]) * kF3 + (tid & 31));
+        }
+        __syncthreads();
+        pair_head_cta(e, e + 32, W, H, scratch, score + p, tid);
+        __syncthreads();
+    }
+}
+
+// ---- score-matrix preparation -----------------------------------------------------------------------------------
+// For graph i:  proj[i][b*16+t] = sum_a e_i[a] W[a][b][t]            (row role, layers_batch.py:78)
+//               rowblk[i][t]    = sum_c V[t][c]    e_i[c]            (first half of V [e1;e2], :80-81)
+//               colblk[i][t]    = sum_c V[t][32+c] e_i[c]            (second half)
+__global__ void __launch_bounds__(kThreads)
+sgpr_ntn_prep_kernel(const float* __restrict__ pooled, int count, float* __restrict__ proj,
+                     float* __restrict__ rowblk, float* __restrict__ colblk, const PackedWeights W) {
+    __shared__ float e[kF3];
+    const int tid = threadIdx.x;
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        if (tid < kF3) e[tid] = __ldg(pooled + static_cast<size_t>(i) * kF3 + tid);
+        __syncthreads();
+        if (proj) {
+            for (int c = tid; c < 512; c += kThreads) {
+                float acc = 0.0f;
+#pragma unroll 8
+                for (int a = 0; a < kF3; ++a) acc = fmaf(e[a], __ldg(W.ntn_w + a * 512 + c), acc);
+                proj[static_cast<size_t>(i) * 512 + c] = acc;
+            }
+        }
+        if (tid < 32) {
+            const int t = tid & 15, half = tid >> 4;
+            float* dst = half ? colblk : rowblk;
+            if (dst) {
+                float acc = 0.0f;
+                for (int c = 0; c < kF3; ++c) acc = fmaf(__ldg(W.ntn_v + t * 64 + half * 32 + c), e[c], acc);
+                dst[static_cast<size_t>(i) * kT + t] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- score matrix tile kernel ------------------------------------------------------------------------------------
+// CTA tile = TI row graphs x TJ column graphs.  Shared: proj of the TI rows ([TI][512], broadcast reads).
+// A thread owns CPT columns (their 32 pooled floats live in registers) and walks the TI rows:
+//   s[t] = sum_b proj[i][b][t] * e_j[b]   (layers_batch.py:79), + V-block + bias, relu, FC1, relu, FC2, sigmoid.
+constexpr int kSmTI = 16;
+constexpr int kSmCPT = 2;
+constexpr int kSmTJ = kThreads * kSmCPT;
+
+__global__ void __launch_bounds__(kThreads)
+sgpr_score_matrix_kernel(const float* __restrict__ proj, const float* __restrict__ rowblk,
+                         const float* __restrict__ pooled_cols, const float* __restrict__ colblk, int R, int M,
+                         float* __restrict__ scores, long long ld, const float* __restrict__ ntn_b,
+                         const HeadParams H) {
+    extern __shared__ __align__(16) float sm[];
+    float* sP = sm;                       // [TI][512]
+    float* sRB = sm + kSmTI * 512;        // [TI][16]  rowblk + bias
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.y * kSmTI;
+    const int j0 = blockIdx.x * kSmTJ;
+    const int ti = min(kSmTI, R - i0);
+
+    for (int e = tid; e < ti * 128; e += kThreads)
+        reinterpret_cast<float4*>(sP)[e] = __ldg(reinterpret_cast<const float4*>(proj + static_cast<size_t>(i0) * 512) + e);
+    for (int e = tid; e < ti * kT; e += kThreads) sRB[e] = __ldg(rowblk + static_cast<size_t>(i0) * kT + e);
+
+    float ej[kSmCPT][kF3];
+    float cb[kSmCPT][kT];
+    int jj[kSmCPT];
+#pragma unroll
+    for (int c = 0; c < kSmCPT; ++c) {
+        jj[c] = j0 + tid + c * kThreads;
+        const int js = min(jj[c], M - 1);
+#pragma unroll
+        for (int b4 = 0; b4 < kF3 / 4; ++b4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(pooled_cols + static_cast<size_t>(js) * kF3) + b4);
+            ej[c][4 * b4] = v.x; ej[c][4 * b4 + 1] = v.y; ej[c][4 * b4 + 2] = v.z; ej[c][4 * b4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int t4 = 0; t4 < kT / 4; ++t4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(colblk + static_cast<size_t>(js) * kT) + t4);
+            cb[c][4 * t4] = v.x; cb[c][4 * t4 + 1] = v.y; cb[c][4 * t4 + 2] = v.z; cb[c][4 * t4 + 3] = v.w;
+        }
+    }
+    float nb[kT];
+#pragma unroll
+    for (int t = 0; t < kT; ++t) nb[t] = __ldg(ntn_b + t);
+    __syncthreads();
+
+    for (int r = 0; r < ti; ++r) {
+        float acc[kSmCPT][kT];
+#pragma unroll
+        for (int c = 0; c < kSmCPT; ++c)
+#pragma unroll
+            for (int t = 0; t < kT; ++t) acc[c][t] = 0.0f;
+        const float4* prow = reinterpret_cast<const float4*>(sP + r * 512);
+#pragma unroll
+        for (int b = 0; b < kF3; ++b) {
+#pragma unroll
+            for (int t4 = 0; t4 < kT / 4; ++t4) {
+                const float4 p = prow[b * 4 + t4];
+#pragma unroll
+                for (int c = 0; c < kSmCPT; ++c) {
+                    acc[c][4 * t4 + 0] = fmaf(p.x, ej[c][b], acc[c][4 * t4 + 0]);
+                    acc[c][4 * t4 + 1] = fmaf(p.y, ej[c][b], acc[c][4 * t4 + 1]);
+                    acc[c][4 * t4 + 2] = fmaf(p.z, ej[c][b], acc[c][4 * t4 + 2]);
+                    acc[c][4 * t4 + 3] = fmaf(p.w, ej[c][b], acc[c][4 * t4 + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kSmCPT; ++c) {
+            float s[kT];
+#pragma unroll
+            for (int t = 0; t < kT; ++t) {
+                const float blk = __fadd_rn(sRB[r * kT + t], cb[c][t]);
+                s[t] = fmaxf(__fadd_rn(__fadd_rn(acc[c][t], blk), nb[t]), 0.0f);
+            }
+            float z = 0.0f;
+#pragma unroll
+            for (int u = 0; u < kBn; ++u) {
+                float h = 0.0f;
+#pragma unroll
+                for (int t = 0; t < kT; ++t) h = fmaf(s[t], H.fc1_w[u * kT + t], h);
+                h = fmaxf(__fadd_rn(h, H.fc1_b[u]), 0.0f);
+                z = fmaf(h, H.fc2_w[u], z);
+            }
+            if (jj[c] < M) scores[static_cast<size_t>(i0 + r) * ld + jj[c]] = sigmoidf_acc(__fadd_rn(z, H.fc2_b));
+        }
+    }
+}
+
+}  // namespace sgpr

@@ -1,0 +1,108 @@
+// Host-side packing of the reference state_dict into the kernel layout (see PackedWeights in common.cuh).
+// Replaces nothing the reference computes per call: nn.BatchNorm in eval mode evaluates
+//   y = x * alpha + beta,  alpha = gamma / sqrt(running_var + eps),  beta = bias - running_mean * alpha
+// on every forward (ATen batch_norm eval path; modules at /root/reference/sg_net.py:50-76); here it is done once.
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+#include <vector>
+
+#include "../../include/sgpr_b200.h"
+#include "common.cuh"
+
+namespace sgpr {
+
+struct PackOffsets {          // offsets in floats into the blob; every section is 16-byte aligned
+    size_t s1, w_s2, w_s3, w_f1, w_f2, w_f3, w_end;
+    size_t ab_s2, ab_s3, ab_f1, ab_f2, ab_f3, ab_end;
+    size_t att_w, ntn_w, ntn_v, ntn_b;
+    size_t total;
+};
+
+inline size_t align4(size_t x) { return (x + 3) & ~static_cast<size_t>(3); }
+
+inline PackOffsets make_offsets() {
+    PackOffsets o{};
+    size_t p = 0;
+    auto take = [&](size_t n) { size_t at = p; p = align4(p + n); return at; };
+    o.s1 = take(64 * 8);
+    o.w_s2 = take(64 * 128);
+    o.w_s3 = take(64 * 64);
+    o.w_f1 = take(12 * 128);
+    o.w_f2 = take(64 * 128);
+    o.w_f3 = take(64 * 64);
+    o.w_end = take(64 * 32);
+    o.ab_s2 = take(128);
+    o.ab_s3 = take(64);
+    o.ab_f1 = take(128);
+    o.ab_f2 = take(128);
+    o.ab_f3 = take(64);
+    o.ab_end = take(64);
+    o.att_w = take(32 * 32);
+    o.ntn_w = take(32 * 512);
+    o.ntn_v = take(16 * 64);
+    o.ntn_b = take(16);
+    o.total = p;
+    return o;
+}
+
+inline void bn_terms(const sgpr_bn& bn, int c, float eps, float& alpha, float& beta) {
+    const float inv_std = 1.0f / std::sqrt(bn.running_var[c] + eps);
+    alpha = inv_std * bn.weight[c];
+    beta = bn.bias[c] - bn.running_mean[c] * alpha;
+}
+
+// EdgeConv layer: conv weight [cout][2*cin] -> k-major [cin][2*cout] with the BN-scale sign folded in.
+inline void pack_edgeconv(const float* w, const sgpr_bn& bn, int cin, int cout, float eps, float* wt, float* ab) {
+    for (int c = 0; c < cout; ++c) {
+        float alpha, beta;
+        bn_terms(bn, c, eps, alpha, beta);
+        const float sign = (alpha < 0.0f) ? -1.0f : 1.0f;
+        ab[c] = sign * alpha;
+        ab[cout + c] = beta;
+        for (int ci = 0; ci < cin; ++ci) {
+            wt[static_cast<size_t>(ci) * 2 * cout + c] = sign * w[static_cast<size_t>(c) * 2 * cin + ci];
+            wt[static_cast<size_t>(ci) * 2 * cout + cout + c] = sign * w[static_cast<size_t>(c) * 2 * cin + cin + ci];
+        }
+    }
+}
+
+inline int pack_weights(const sgpr_weights& hw, std::vector<float>& blob, HeadParams& hp, const PackOffsets& o) {
+    blob.assign(o.total, 0.0f);
+    const float eps = hw.bn_eps;
+    // xyz layer 1: per output channel {wa0,wa1,wa2, wb0,wb1,wb2, alpha, beta}
+    for (int c = 0; c < 64; ++c) {
+        float alpha, beta;
+        bn_terms(hw.s_bn[0], c, eps, alpha, beta);
+        const float sign = (alpha < 0.0f) ? -1.0f : 1.0f;
+        float* dst = blob.data() + o.s1 + c * 8;
+        for (int q = 0; q < 6; ++q) dst[q] = sign * hw.s_conv_w[0][c * 6 + q];
+        dst[6] = sign * alpha;
+        dst[7] = beta;
+    }
+    pack_edgeconv(hw.s_conv_w[1], hw.s_bn[1], 64, 64, eps, blob.data() + o.w_s2, blob.data() + o.ab_s2);
+    pack_edgeconv(hw.s_conv_w[2], hw.s_bn[2], 64, 32, eps, blob.data() + o.w_s3, blob.data() + o.ab_s3);
+    pack_edgeconv(hw.f_conv_w[0], hw.f_bn[0], 12, 64, eps, blob.data() + o.w_f1, blob.data() + o.ab_f1);
+    pack_edgeconv(hw.f_conv_w[1], hw.f_bn[1], 64, 64, eps, blob.data() + o.w_f2, blob.data() + o.ab_f2);
+    pack_edgeconv(hw.f_conv_w[2], hw.f_bn[2], 64, 32, eps, blob.data() + o.w_f3, blob.data() + o.ab_f3);
+    // conv_end [32][64] -> [64][32]; BN sign kept (no max follows)
+    for (int c = 0; c < 32; ++c) {
+        float alpha, beta;
+        bn_terms(hw.end_bn, c, eps, alpha, beta);
+        blob[o.ab_end + c] = alpha;
+        blob[o.ab_end + 32 + c] = beta;
+        for (int ci = 0; ci < 64; ++ci) blob[o.w_end + ci * 32 + c] = hw.end_conv_w[c * 64 + ci];
+    }
+    std::memcpy(blob.data() + o.att_w, hw.att_w, sizeof(float) * 32 * 32);
+    std::memcpy(blob.data() + o.ntn_w, hw.ntn_w, sizeof(float) * 32 * 512);
+    std::memcpy(blob.data() + o.ntn_v, hw.ntn_v, sizeof(float) * 16 * 64);
+    std::memcpy(blob.data() + o.ntn_b, hw.ntn_b, sizeof(float) * 16);
+    std::memcpy(hp.fc1_w, hw.fc1_w, sizeof(float) * 256);
+    std::memcpy(hp.fc1_b, hw.fc1_b, sizeof(float) * 16);
+    std::memcpy(hp.fc2_w, hw.fc2_w, sizeof(float) * 16);
+    hp.fc2_b = hw.fc2_b[0];
+    return 0;
+}
+
+}  // namespace sgpr

@@ -1,0 +1,426 @@
+"""Drop-in `sg_net` module: `SG` and `SGTrainer` with the reference's names, signatures and checkpoint format
+(/root/reference/sg_net.py:18-564), over the B200-native C-ABI engine.
+
+Boundary: `SG.forward(data)` takes the reference's dict of CPU FloatTensors
+`features_1`, `features_2` ([B, 15, N], channel-major) and returns `(score [B], att_1 [B,N,1], att_2 [B,N,1])` as
+device tensors, like the reference (sg_net.py:112-138).  In eval mode the whole forward is ONE launch of the
+fused sm_100a kernel (csrc/embed_kernel.cuh) through `sg_pr_b200.engine.Engine`; there is no CPU or eager-PyTorch
+fallback for it — without the built library or without a CUDA device the call raises.
+
+Train mode (`fit`, BASELINE config 3) needs batch-statistics BatchNorm and a backward pass, which are a "next" row
+of the scope table: it runs the same math as differentiable stock PyTorch ops on the device
+(`SG._forward_autograd`).  It is never used for, or counted in, the measured eval hot path.
+"""
+import os
+import random
+import time
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import dgcnn
+from . import utils as _utils
+from .layers_batch import AttentionModule, TenorNetworkModule
+from .utils import listDir, load_paires, process_pair
+
+try:  # optional in this image
+    from tqdm import tqdm, trange
+except ImportError:  # pragma: no cover
+    def tqdm(it, **kw):
+        return it
+
+    def trange(n, **kw):
+        return range(n)
+
+
+class _NullWriter:
+    """Stand-in when tensorboardX is absent (sg_net.py:155 creates a SummaryWriter unconditionally)."""
+
+    def __init__(self, logdir=None):
+        self.logdir = logdir
+
+    def add_scalar(self, *a, **k):
+        pass
+
+
+def _make_writer(logdir):
+    try:
+        from tensorboardX import SummaryWriter
+        return SummaryWriter(logdir=logdir)
+    except ImportError:
+        return _NullWriter(logdir)
+
+
+def _edge_block(cin, cout):
+    """Conv2d(1x1, no bias) + BatchNorm2d + LeakyReLU(0.2): the EdgeConv MLP of sg_net.py:50-73."""
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=1, bias=False), nn.BatchNorm2d(cout),
+                         nn.LeakyReLU(negative_slope=0.2))
+
+
+class SG(torch.nn.Module):
+    """Semantic-graph similarity network (sg_net.py:18-138).  Sub-module names match the reference so that
+    `load_state_dict(strict=True)` accepts its checkpoints (SURVEY §8b checkpoint contract)."""
+
+    def __init__(self, args, number_of_labels):
+        super().__init__()
+        self.args = args
+        self.number_labels = number_of_labels
+        self.setup_layers()
+        self._engine = None
+        self._packed_version = None
+
+    def calculate_bottleneck_features(self):
+        self.feature_count = self.args.tensor_neurons
+
+    def setup_layers(self):
+        a = self.args
+        self.calculate_bottleneck_features()
+        self.attention = AttentionModule(a)
+        self.tensor_network = TenorNetworkModule(a)
+        self.fully_connected_first = torch.nn.Linear(self.feature_count, a.bottle_neck_neurons)
+        self.scoring_layer = torch.nn.Linear(a.bottle_neck_neurons, 1)
+        self.dgcnn_s_conv1 = _edge_block(3 * 2, a.filters_1)
+        self.dgcnn_f_conv1 = _edge_block(self.number_labels * 2, a.filters_1)
+        self.dgcnn_s_conv2 = _edge_block(a.filters_1 * 2, a.filters_2)
+        self.dgcnn_f_conv2 = _edge_block(a.filters_1 * 2, a.filters_2)
+        self.dgcnn_s_conv3 = _edge_block(a.filters_2 * 2, a.filters_3)
+        self.dgcnn_f_conv3 = _edge_block(a.filters_2 * 2, a.filters_3)
+        self.dgcnn_conv_end = nn.Sequential(nn.Conv1d(a.filters_3 * 2, a.filters_3, kernel_size=1, bias=False),
+                                            nn.BatchNorm1d(a.filters_3), nn.LeakyReLU(negative_slope=0.2))
+
+    # ---- engine plumbing -----------------------------------------------------------------------------------
+    def _device(self):
+        return torch.device("cuda", int(getattr(self.args, "gpu", 0)))
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)         # .cuda()/.to()/.float(): storage may move — forget the pack
+        self._tensors = None
+        self._packed_version = None
+        return out
+
+    def _weights_version(self):
+        if getattr(self, "_tensors", None) is None:
+            self._tensors = list(self.parameters()) + list(self.buffers())
+        return tuple(t._version for t in self._tensors)
+
+    def engine(self):
+        """The device context with this module's CURRENT eval-mode weights packed (re-packed when they change)."""
+        from .engine import Engine
+        if self._engine is None:
+            self._engine = Engine(self._device())
+        version = self._weights_version()
+        if version != self._packed_version:
+            self._engine.set_weights({k: v for k, v in self.state_dict().items()})
+            self._packed_version = version
+        return self._engine
+
+    # ---- differentiable device path, training only (sg_net.py:79-138 as stock PyTorch ops) -------------------
+    def _edge_layer(self, x, block):
+        return block(dgcnn.get_graph_feature(x, k=self.args.K)).max(dim=-1)[0]     # sg_net.py:84-86
+
+    def dgcnn_conv_pass(self, x):
+        xyz, sem = x[:, :3, :], x[:, 3:, :]
+        for block in (self.dgcnn_s_conv1, self.dgcnn_s_conv2, self.dgcnn_s_conv3):
+            xyz = self._edge_layer(xyz, block)
+        for block in (self.dgcnn_f_conv1, self.dgcnn_f_conv2, self.dgcnn_f_conv3):
+            sem = self._edge_layer(sem, block)
+        return self.dgcnn_conv_end(torch.cat((xyz, sem), dim=1)).permute(0, 2, 1)
+
+    def _forward_autograd(self, f1, f2):
+        e1, e2 = self.dgcnn_conv_pass(f1), self.dgcnn_conv_pass(f2)
+        p1, a1 = self.attention(e1)
+        p2, a2 = self.attention(e2)
+        s = self.tensor_network(p1, p2).permute(0, 2, 1)
+        s = torch.nn.functional.relu(self.fully_connected_first(s))
+        return torch.sigmoid(self.scoring_layer(s)).reshape(-1), a1, a2
+
+    # ---- the boundary ----------------------------------------------------------------------------------------
+    def forward(self, data):
+        """sg_net.py:112-138.  data["features_1"/"features_2"]: [B, 3+labels, node_num] float tensors (CPU or device)."""
+        dev = self._device()
+        f1 = data["features_1"].to(dev, dtype=torch.float32, non_blocking=True)
+        f2 = data["features_2"].to(dev, dtype=torch.float32, non_blocking=True)
+        if self.training:
+            return self._forward_autograd(f1, f2)
+        return self.engine().forward_pairs(f1, f2, int(self.args.K), want_att=True)
+
+
+class _DeviceReplica(torch.nn.Module):
+    """What `nn.DataParallel(model, device_ids=[gpu])` amounts to with one device (sg_net.py:175): a wrapper whose
+    only visible effects are `.module` and the `module.` prefix in state_dict keys."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)
+
+
+class SGTrainer(object):
+    """Trainer / evaluator with the reference's public surface (sg_net.py:141-564)."""
+
+    def __init__(self, args, train=True):
+        self.args = args
+        self.model_pth = self.args.model
+        self.initial_label_enumeration(train)
+        self.setup_model(train)
+        self.writer = _make_writer(self.args.logdir)
+
+    # ---- construction ----------------------------------------------------------------------------------------
+    def setup_model(self, train=True):
+        """sg_net.py:158-176: build SG, (eval) load the DataParallel checkpoint, wrap, move to the device."""
+        self.model = SG(self.args, self.number_of_labels)
+        if (not train) and self.model_pth != "":
+            print("loading model: ", self.model_pth)
+            state = torch.load(self.model_pth, map_location="cpu", weights_only=False)
+            clean = OrderedDict((k[7:] if k.startswith("module.") else k, v) for k, v in state.items())
+            self.model.load_state_dict(clean)
+        self.model = _DeviceReplica(self.model)
+        if torch.cuda.is_available():      # host-side logic stays usable on a CPU box; forward() there raises
+            self.model.cuda(self.args.gpu)
+
+    def initial_label_enumeration(self, train=True):
+        """sg_net.py:178-206: (train) read the pair lists; labels are the 12 SemanticKITTI classes 0..11."""
+        print("\nEnumerating unique labels.\n")
+        if train:
+            self.training_graphs, self.testing_graphs, self.evaling_graphs = [], [], []
+            print("Train sequences: ", self.args.train_sequences)
+            print("evaling sequences: ", self.args.eval_sequences)
+            for sq in self.args.train_sequences:
+                self.training_graphs.extend(
+                    load_paires(os.path.join(self.args.pair_list_dir, sq + ".txt"), self.args.graph_pairs_dir))
+            for sq in self.args.eval_sequences:
+                self.evaling_graphs = load_paires(os.path.join(self.args.pair_list_dir, sq + ".txt"),
+                                                  self.args.graph_pairs_dir)
+            self.testing_graphs = self.evaling_graphs
+            assert len(self.evaling_graphs) != 0
+            assert len(self.training_graphs) != 0
+        self.global_labels = {label: index for index, label in enumerate(range(12))}
+        self.number_of_labels = len(self.global_labels)
+        self.keepnode = self.args.keep_node
+        print(self.global_labels)
+        print(self.number_of_labels)
+
+    # ---- host-side data preparation ----------------------------------------------------------------------------
+    def create_batches(self, split="train"):
+        graphs = self.training_graphs if split == "train" else self.evaling_graphs
+        random.shuffle(graphs)
+        step = self.args.batch_size
+        return [graphs[i:i + step] for i in range(0, len(graphs), step)]
+
+    def augment_data(self, batch_xyz_1):
+        """sg_net.py:223-230: rotate, jitter, scale, perturb, shift (flip is applied by the caller)."""
+        for fn in (_utils.rotate_point_cloud, _utils.jitter_point_cloud, _utils.random_scale_point_cloud,
+                   _utils.rotate_perturbation_point_cloud, _utils.shift_point_cloud):
+            batch_xyz_1 = fn(batch_xyz_1)
+        return batch_xyz_1
+
+    def pc_normalize(self, pc):
+        pc = pc - np.mean(pc, axis=0)
+        return pc / np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
+
+    def _fit_node_count(self, nodes, centers):
+        """Subsample (sorted random choice) or pad (label -1, centre 0) a graph to args.node_num — sg_net.py:250-278."""
+        want = self.args.node_num
+        have = len(nodes)
+        nodes = np.asarray(nodes, dtype=np.float64)
+        centers = np.asarray(centers, dtype=np.float64).reshape(have, 3)
+        if have > want:
+            keep = np.random.choice(have, want, replace=False)
+            keep.sort()
+            return nodes[keep], centers[keep]
+        if have < want:
+            return (np.concatenate((nodes, -np.ones(want - have))),
+                    np.concatenate((centers, np.zeros((want - have, 3)))))
+        return nodes, centers
+
+    def _one_hot(self, nodes):
+        out = np.zeros((len(nodes), self.number_of_labels))
+        for row, node in enumerate(nodes):
+            if node != -1:
+                out[row, self.global_labels[int(node)]] = 1.0
+        return out
+
+    def transfer_to_torch(self, data, training=True):
+        """sg_net.py:241-310: pair dict -> {"features_1","features_2": [15, node_num] float64 arrays, "target"}."""
+        nodes_1, centers_1 = self._fit_node_count(data["nodes_1"], data["centers_1"])
+        nodes_2, centers_2 = self._fit_node_count(data["nodes_2"], data["centers_2"])
+        data["nodes_1"], data["centers_1"] = nodes_1.tolist(), centers_1
+        data["nodes_2"], data["centers_2"] = nodes_2.tolist(), centers_2
+        xyz_1, xyz_2 = centers_1[None].copy(), centers_2[None].copy()
+        if training:
+            if random.random() > 0.5:
+                xyz_1[:, :, 0] = -xyz_1[:, :, 0]
+                xyz_2[:, :, 0] = -xyz_2[:, :, 0]
+            xyz_1, xyz_2 = self.augment_data(xyz_1), self.augment_data(xyz_2)
+        new_data = {
+            "features_1": np.squeeze(np.concatenate((xyz_1, self._one_hot(nodes_1)[None]), axis=2).transpose(0, 2, 1)),
+            "features_2": np.squeeze(np.concatenate((xyz_2, self._one_hot(nodes_2)[None]), axis=2).transpose(0, 2, 1)),
+        }
+        if data["distance"] <= self.args.p_thresh:
+            new_data["target"] = 1.0
+        elif data["distance"] >= 20:
+            new_data["target"] = 0.0
+        else:
+            new_data["target"] = -100.0
+            print("distance error: ", data["distance"])
+            exit(-1)
+        return new_data
+
+    @staticmethod
+    def _stack(features_1, features_2, targets):
+        return {"features_1": torch.FloatTensor(np.array(features_1)),
+                "features_2": torch.FloatTensor(np.array(features_2)),
+                "target": torch.FloatTensor(np.array(targets))}
+
+    # ---- training ------------------------------------------------------------------------------------------------
+    def process_batch(self, batch, training=True):
+        """sg_net.py:312-345: every listed pair is fed in both orders; BCE; (training) backward + Adam step."""
+        self.optimizer.zero_grad()
+        f1, f2, targets = [], [], []
+        for graph_pair in batch:
+            data = self.transfer_to_torch(process_pair(graph_pair), training)
+            f1 += [data["features_1"], data["features_2"]]
+            f2 += [data["features_2"], data["features_1"]]
+            targets += [data["target"], data["target"]]
+        data = self._stack(f1, f2, targets)
+        prediction, _, _ = self.model(data)
+        losses = torch.mean(torch.nn.functional.binary_cross_entropy(prediction, data["target"].to(prediction.device)))
+        if training:
+            losses.backward()
+            self.optimizer.step()
+        return (losses.item(), prediction.cpu().detach().numpy().reshape(-1),
+                data["target"].cpu().detach().numpy().reshape(-1))
+
+    def fit(self):
+        """sg_net.py:347-384."""
+        print("\nModel training.\n")
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.args.learning_rate,
+                                          weight_decay=self.args.weight_decay)
+        f1_max_his = 0
+        self.model.train()
+        epochs = trange(self.args.epochs, leave=True, desc="Epoch")
+        for epoch in epochs:
+            batches = self.create_batches()
+            self.model.train()
+            self.loss_sum, main_index = 0, 0
+            for index, batch in tqdm(enumerate(batches), total=len(batches), desc="Batches"):
+                loss_score, _, _ = self.process_batch(batch)
+                main_index += len(batch)
+                self.loss_sum += loss_score * len(batch)
+                loss = self.loss_sum / main_index
+                if hasattr(epochs, "set_description"):
+                    epochs.set_description("Epoch (Loss=%g)" % round(loss, 5))
+                step = int(epoch) * len(batches) * int(self.args.batch_size) + main_index
+                self.writer.add_scalar("Train_sum", loss, step)
+                self.writer.add_scalar("Train loss", loss_score, step)
+            if epoch % 2 == 0:
+                print("\nModel saving.\n")
+                loss, f1_max = self.score("eval")
+                step = int(epoch) * len(batches) * int(self.args.batch_size)
+                self.writer.add_scalar("eval_loss", loss, step)
+                self.writer.add_scalar("f1_max_score", f1_max, step)
+                os.makedirs(self.args.logdir, exist_ok=True)
+                torch.save(self.model.state_dict(), self.args.logdir + "/" + str(epoch) + ".pth")
+                if f1_max_his <= f1_max:
+                    f1_max_his = f1_max
+                    best = self.args.logdir + "/" + str(epoch) + "_best" + ".pth"
+                    torch.save(self.model.state_dict(), best)
+                    print("\n best model saved ", best)
+                print("------------------------------")
+
+    def score(self, split="test"):
+        """sg_net.py:386-422: eval-mode pass over the split, F1max from the precision-recall curve."""
+        from sklearn import metrics
+        print("\n\nModel evaluation.\n")
+        self.model.eval()
+        self.scores, self.ground_truth = [], []
+        if split not in ("test", "eval"):
+            print("Check split: ", split)
+            exit(-1)
+        if not hasattr(self, "optimizer"):     # the reference crashes here unless fit() ran first (sg_net.py:318)
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.args.learning_rate,
+                                              weight_decay=self.args.weight_decay)
+        losses, pred_db, gt_db = 0, [], []
+        batches = self.create_batches(split="eval")
+        for index, batch in tqdm(enumerate(batches), total=len(batches), desc="Eval Batches"):
+            loss_score, pred_b, gt_b = self.process_batch(batch, False)
+            losses += loss_score
+            pred_db.extend(pred_b)
+            gt_db.extend(gt_b)
+        precision, recall, _ = metrics.precision_recall_curve(gt_db, pred_db)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f1 = np.nan_to_num(2 * precision * recall / (precision + recall))
+        f1_max = np.max(f1)
+        print("\nModel " + split + " F1_max_score: " + str(f1_max) + ".")
+        model_loss = losses / len(batches)
+        print("\nModel " + split + " loss: " + str(model_loss) + ".")
+        return model_loss, f1_max
+
+    def print_evaluation(self):
+        mean = np.mean(self.ground_truth)
+        base_error = np.mean([(n - mean) ** 2 for n in self.ground_truth])
+        print("\nBaseline error: " + str(round(base_error, 5)) + ".")
+        print("\nModel test error: " + str(round(np.mean(self.scores), 5)) + ".")
+
+    # ---- evaluation (the callers of the hot path) -------------------------------------------------------------------
+    def _eval_dicts(self, dicts):
+        self.model.eval()
+        f1, f2, targets = [], [], []
+        for pair in dicts:
+            data = self.transfer_to_torch(pair, False)
+            f1.append(data["features_1"])
+            f2.append(data["features_2"])
+            targets.append(data["target"])
+        with torch.no_grad():
+            prediction, att_1, att_2 = self.model(self._stack(f1, f2, targets))
+        return prediction, att_1, att_2, np.array(targets).reshape(-1)
+
+    def eval_pair(self, pair_file):
+        """sg_net.py:434-457: one pair dict -> (prediction[1], att_1[N], att_2[N]) as numpy."""
+        prediction, att_1, att_2, _ = self._eval_dicts([pair_file])
+        return (prediction.cpu().detach().numpy().reshape(-1), att_1.cpu().detach().numpy().reshape(-1),
+                att_2.cpu().detach().numpy().reshape(-1))
+
+    def eval_batch_pair_data(self, batch):
+        """sg_net.py:480-501: batch of pair dicts -> (pred[B], gt[B])."""
+        start = time.time()
+        prediction, _, _, gt = self._eval_dicts(batch)
+        prediction = prediction.cpu().detach().numpy().reshape(-1)
+        print("forward time: ", time.time() - start)
+        return prediction, gt
+
+    def eval_batch_pair(self, batch):
+        """sg_net.py:503-525: batch of [path_a, path_b] -> (pred[B], gt[B]).  The call eval_pair.py / eval_batch.py make."""
+        prediction, _, _, gt = self._eval_dicts([process_pair(graph_pair) for graph_pair in batch])
+        return prediction.cpu().detach().numpy().reshape(-1), gt
+
+    def write_soft_label(self, data_dir, out_dir=None, thresh=0.5):
+        """sg_net.py:528-564: re-label pair files with the model's decision and report precision / recall."""
+        import json
+        files = []
+        listDir(data_dir, files)
+        tp = tn = fp = fn = 0
+        out_dir = out_dir or os.path.join(data_dir, "pred_label")
+        os.makedirs(out_dir, exist_ok=True)
+        for pair_file in files:
+            with open(pair_file) as handle:
+                data = json.load(handle)
+            pred, _, _ = self.eval_pair(dict(data))
+            near = data["distance"] <= 10
+            if pred <= thresh:
+                tn, fn = tn + near, fn + (not near)
+                data["distance"] = 100
+            else:
+                tp, fp = tp + near, fp + (not near)
+                data["distance"] = 0
+            target = os.path.join(out_dir, os.path.basename(pair_file))
+            print("write pred label: ", target)
+            with open(target, "w", encoding="utf-8") as handle:
+                json.dump(data, handle)
+        print("thresh: ", thresh)
+        print("precision: ", tp / max(tp + fp, 1))
+        print("recall:", tp / max(tp + fn, 1))

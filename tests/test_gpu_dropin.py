@@ -1,0 +1,113 @@
+"""GPU tests of the drop-in boundary: the reference's call sequence (eval_pair.py:6-13, eval_batch.py:30-36) against
+our `sg_net` / `parser_sg` / `utils`, on files materialised from the golden fixtures."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import write_fixture_tree
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def tree(golden_dir, tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("sgpr_tree"))
+    return root, write_fixture_tree(golden_dir, root)
+
+
+def test_eval_pair_call_sequence(tree, golden_dir):
+    """eval_pair.py: SGTrainer(args, False); model.eval(); eval_batch_pair([pair_file]) -> Score 1.3489922e-06."""
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SGTrainer
+    root, cfg = tree
+    args = sgpr_args()
+    args.load(cfg)
+    trainer = SGTrainer(args, False)
+    trainer.model.eval()
+    pred, gt = trainer.eval_batch_pair([args.pair_file, ])
+    z = np.load(os.path.join(golden_dir, "ref_fixture_pairs.npz"))
+    assert pred.shape == (1,) and abs(float(pred[0]) - float(z["K10_N100_0_250_score"][0])) <= 1e-5
+    assert abs(float(pred[0]) - 1.34899221e-06) <= 1e-6 and gt[0] == 0.0
+    # eval_pair(): attention weights come back too (sg_net.py:434-457)
+    from sg_pr_b200.utils import process_pair
+    p, a1, a2 = trainer.eval_pair(process_pair([f"{root}/data/0.json", f"{root}/data/3.json"]))
+    assert abs(float(p[0]) - float(z["K10_N100_0_3_score"][0])) <= 1e-5
+    assert np.abs(a1 - z["K10_N100_0_3_att_1"].reshape(-1)).max() <= 1e-5
+    assert np.abs(a2 - z["K10_N100_0_3_att_2"].reshape(-1)).max() <= 1e-5
+
+
+def test_eval_batch_loop_and_repack_on_weight_change(tree, golden_dir):
+    """eval_batch.py's hot loop over batches, and the engine re-packs when the module's weights change."""
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SGTrainer
+    root, cfg = tree
+    args = sgpr_args().load(cfg)
+    args.K, args.node_num, args.batch_size = 20, 64, 4
+    trainer = SGTrainer(args, False)
+    trainer.model.eval()
+    names = ["0", "3", "250"]
+    pairs = [[f"{root}/data/{a}.json", f"{root}/data/{b}.json"] for a in names for b in names
+             if (a, b) in (("0", "250"), ("0", "3"), ("3", "0"), ("0", "0"), ("250", "0"), ("3", "250"))]
+    batches = [pairs[i:i + args.batch_size] for i in range(0, len(pairs), args.batch_size)]
+    pred_db = []
+    for batch in batches:
+        pred, gt = trainer.eval_batch_pair(batch)
+        pred_db.extend(pred)
+    z = np.load(os.path.join(golden_dir, "ref_fixture_pairs.npz"))
+    for pair, got in zip(pairs, pred_db):
+        a, b = (os.path.basename(p)[:-5] for p in pair)
+        assert abs(float(got) - float(z[f"K20_N64_{a}_{b}_score"][0])) <= 1e-5, (a, b)
+    launches = trainer.model.module.engine().launch_count()
+    assert launches == len(batches)                       # ONE fused launch per batch
+    # change a weight in place -> next forward must use it
+    with torch.no_grad():
+        trainer.model.module.scoring_layer.bias.add_(1.0)
+    pred2, _ = trainer.eval_batch_pair(batches[0])
+    assert np.abs(pred2 - np.array(pred_db[:len(pred2)])).max() > 1e-3
+    # swapping in another checkpoint through load_state_dict is picked up as well
+    ck = np.load(os.path.join(golden_dir, "model_3_20_08.npz"))
+    trainer.model.load_state_dict({"module." + k: torch.from_numpy(ck[k].copy()) for k in ck.files})
+    ref = np.load(os.path.join(golden_dir, "ref_ckpt_scores.npz"))
+    data = {"features_1": torch.from_numpy(ref["features_1"]), "features_2": torch.from_numpy(ref["features_2"])}
+    with torch.no_grad():
+        s, _, _ = trainer.model(data)
+    assert np.abs(s.cpu().numpy() - ref["score_3_20_08"]).max() <= 1e-5
+
+
+def test_training_step_runs_on_device(tree):
+    """fit()'s inner step (process_batch: both orders, BCE, backward, Adam) works and the eval kernel sees the update."""
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SGTrainer
+    root, cfg = tree
+    os.makedirs(f"{root}/lists", exist_ok=True)
+    for seq in ("00", "08"):
+        with open(f"{root}/lists/{seq}.txt", "w") as f:
+            f.write("0.json 3.json\n0.json 250.json\n3.json 250.json\n0.json 0.json\n")
+    args = sgpr_args().load(cfg)
+    args.K, args.node_num, args.batch_size = 10, 48, 4
+    trainer = SGTrainer(args, True)
+    trainer.optimizer = torch.optim.Adam(trainer.model.parameters(), lr=1e-3, weight_decay=5e-4)
+    trainer.model.train()
+    loss0, pred, gt = trainer.process_batch(trainer.training_graphs, True)
+    assert pred.shape == (8,) and np.isfinite(loss0)
+    for _ in range(5):
+        loss, _, _ = trainer.process_batch(trainer.training_graphs, True)
+    assert loss < loss0
+    model_loss, f1 = trainer.score("eval")                # eval mode -> fused kernel with the just-trained weights
+    assert np.isfinite(model_loss) and 0.0 <= f1 <= 1.0
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/eval_pair.py"), reason="reference tree not on this box")
+def test_unmodified_reference_script(tree):
+    """The reference's own eval_pair.py, unmodified, with our modules first on sys.path."""
+    root, cfg = tree
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "sg_pr_b200", "dropin"), ROOT]))
+    out = subprocess.run([sys.executable, "/root/reference/eval_pair.py"], cwd=root, env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Score: 1.34" in out.stdout and "e-06" in out.stdout

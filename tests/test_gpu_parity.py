@@ -1,0 +1,195 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box).  Every call goes through the C-ABI (sg_pr_b200.engine →
+libsgpr_b200.so); the checker is the oracle (oracle/sgpr_oracle.py, run live on the host CPU) and the committed
+golden vectors the reference itself produced (tests/golden/).  Tolerance: 1e-5 abs fp32 on scores (BASELINE.json),
+k-NN index sets exact up to exact ties."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sgpr_oracle as orc
+from sg_pr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-5
+FEAT_ATOL, FEAT_RTOL = 2e-5, 1e-5
+
+
+@pytest.fixture(scope="module")
+def eng(kitti_state):
+    from sg_pr_b200.engine import Engine
+    e = Engine(0)
+    e.set_weights(kitti_state)
+    yield e
+    e.close()
+
+
+def _cuda(t):
+    return t.cuda(non_blocking=False)
+
+
+def test_library_is_loaded_native():
+    """The CUDA path is the one that runs: the in-tree .so must be mapped into this process."""
+    from sg_pr_b200 import _lib
+    _lib.load()
+    with open("/proc/self/maps") as f:
+        assert "libsgpr_b200.so" in f.read()
+
+
+FIXTURE_PAIRS = [("0", "250"), ("0", "3"), ("3", "0"), ("0", "0"), ("250", "0"), ("3", "250")]
+
+
+@pytest.mark.parametrize("K,N", [(10, 100), (20, 64)])
+def test_fixture_pairs_match_reference_golden(eng, golden_dir, K, N):
+    with np.load(os.path.join(golden_dir, "ref_fixture_pairs.npz")) as z:
+        for a, b in FIXTURE_PAIRS:
+            p = f"K{K}_N{N}_{a}_{b}_"
+            f1, f2 = torch.from_numpy(z[p + "features_1"]), torch.from_numpy(z[p + "features_2"])
+            score, a1, a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), K)
+            assert abs(float(score[0]) - float(z[p + "score"][0])) <= SCORE_TOL, (K, N, a, b)
+            assert np.abs(a1.cpu().numpy() - z[p + "att_1"]).max() <= SCORE_TOL
+            assert np.abs(a2.cpu().numpy() - z[p + "att_2"]).max() <= SCORE_TOL
+
+
+@pytest.mark.parametrize("tag", ["n64_k20", "n100_k10", "n32_k10", "n128_k20", "n16_k10"])
+def test_synthetic_golden(eng, golden_dir, tag):
+    with np.load(os.path.join(golden_dir, f"ref_synth_{tag}.npz")) as z:
+        K = int(z["K"])
+        f1, f2 = torch.from_numpy(z["features_1"]), torch.from_numpy(z["features_2"])
+        score, a1, a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), K)
+        assert np.abs(score.cpu().numpy() - z["score"]).max() <= SCORE_TOL
+        assert np.abs(a1.cpu().numpy() - z["att_1"]).max() <= SCORE_TOL
+        assert np.abs(a2.cpu().numpy() - z["att_2"]).max() <= SCORE_TOL
+        emb = eng.embed(_cuda(f1), K, want_emb=True)["emb"].cpu().numpy()
+        np.testing.assert_allclose(emb, z["emb_1"], atol=FEAT_ATOL, rtol=FEAT_RTOL)
+
+
+@pytest.mark.parametrize("tag", ["3_20_08", "10_20_05"])
+def test_other_checkpoints(golden_dir, tag):
+    from sg_pr_b200.engine import Engine
+    e = Engine(0)
+    e.set_weights(orc.load_state_npz(os.path.join(golden_dir, f"model_{tag}.npz")))
+    with np.load(os.path.join(golden_dir, "ref_ckpt_scores.npz")) as z:
+        score, a1, _ = e.forward_pairs(_cuda(torch.from_numpy(z["features_1"])), _cuda(torch.from_numpy(z["features_2"])), 20)
+        assert np.abs(score.cpu().numpy() - z[f"score_{tag}"]).max() <= SCORE_TOL
+        assert np.abs(a1.cpu().numpy() - z[f"att_1_{tag}"]).max() <= SCORE_TOL
+    e.close()
+
+
+@pytest.mark.parametrize("n,k", [(64, 20), (100, 10), (128, 20), (32, 10), (30, 7), (16, 10)])
+def test_stage_parity_vs_oracle(eng, kitti_state, n, k):
+    """Per-stage comparison: k-NN sets of all 6 EdgeConv layers, each layer's output, node embeddings, attention."""
+    g = synth.make_graphs(6, n, k, seed=11)
+    want = orc.embed_graphs(g, k, kitti_state, want_trace=True)
+    got = eng.embed(_cuda(g), k, want_att=True, want_emb=True, trace=True)
+    knn = got["knn"].cpu().long()
+    layers = got["layers"].cpu()
+    for layer in range(6):
+        ok = orc.knn_sets_equivalent(want["knn_pd"][layer], want["knn_idx"][layer], knn[:, layer], want["layer_in"][layer])
+        assert bool(ok.all()), f"k-NN set mismatch (not a tie) layer {layer}: rows {(~ok).nonzero()[:5].tolist()}"
+        ref = want["layer_out"][layer].permute(0, 2, 1)                # [M, N, C']
+        np.testing.assert_allclose(layers[:, layer, :, :ref.shape[2]].numpy(), ref.numpy(), atol=FEAT_ATOL, rtol=FEAT_RTOL)
+    np.testing.assert_allclose(got["emb"].cpu().numpy(), want["emb"].numpy(), atol=FEAT_ATOL, rtol=FEAT_RTOL)
+    np.testing.assert_allclose(got["att"].cpu().numpy(), want["att"].numpy(), atol=SCORE_TOL)
+    np.testing.assert_allclose(got["pooled"].cpu().numpy(), want["pooled"].squeeze(-1).numpy(), atol=5e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_headline_batch_scores(eng, kitti_state, seed):
+    """BASELINE config 2 shape: batch 128, 64-node graphs, k=20 — every score within 1e-5 of the oracle."""
+    f1, f2 = synth.make_pair_batch(128, 64, 20, seed=seed)
+    want = orc.forward_pairs(f1, f2, 20, kitti_state)
+    score, a1, a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)
+    err = (score.cpu() - want["score"]).abs()
+    assert float(err.max()) <= SCORE_TOL, f"max |dscore| {float(err.max()):.3g} at pair {int(err.argmax())}"
+    assert float((a1.cpu() - want["att_1"]).abs().max()) <= SCORE_TOL
+    assert float((a2.cpu() - want["att_2"]).abs().max()) <= SCORE_TOL
+
+
+def test_batch_independence_and_launch_determinism(eng):
+    """A graph's embedding does not depend on its batch or position and repeats bit-exactly."""
+    g = _cuda(synth.make_graphs(300, 64, 20, seed=3))
+    full = eng.embed(g, 20)["pooled"]
+    again = eng.embed(g, 20)["pooled"]
+    assert torch.equal(full, again)
+    solo = eng.embed(g[17:18].contiguous(), 20)["pooled"]
+    assert torch.equal(solo[0], full[17])
+    rev = eng.embed(g.flip(0).contiguous(), 20)["pooled"].flip(0)
+    assert torch.equal(rev, full)
+
+
+def test_pairs_equal_embed_plus_head(eng):
+    """forward_pairs == embed + score_pairs == score_matrix entry, bit for bit in the pair head's own arithmetic."""
+    f1, f2 = synth.make_pair_batch(40, 64, 20, seed=5)
+    score, _, _ = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)
+    pooled = eng.embed(_cuda(torch.cat([f1, f2])), 20)["pooled"]
+    idx = torch.stack([torch.arange(40), torch.arange(40) + 40], dim=1).cuda()
+    assert torch.equal(eng.score_pairs(pooled, idx), score)
+    mat = eng.score_matrix(pooled[:40].contiguous(), pooled[40:].contiguous())
+    assert float((mat.diagonal() - score).abs().max()) <= 2e-6
+    # the score is NOT symmetric in its arguments (layers_batch.py:78-81)
+    swapped, _, _ = eng.forward_pairs(_cuda(f2), _cuda(f1), 20)
+    assert float((swapped - score).abs().max()) > 1e-4
+
+
+def test_score_matrix_vs_oracle(eng, kitti_state):
+    g = synth.make_graphs(70, 64, 20, seed=9)
+    pooled = eng.embed(_cuda(g), 20)["pooled"]
+    mat = eng.score_matrix(pooled[:33].contiguous(), pooled).cpu()
+    want = orc.score_matrix(pooled[:33].cpu(), pooled.cpu(), kitti_state)
+    assert float((mat - want).abs().max()) <= SCORE_TOL
+    # ragged tile edges: 1 row, 1 column, and a strided output view
+    one = eng.score_matrix(pooled[5:6].contiguous(), pooled[7:8].contiguous())
+    assert abs(float(one[0, 0]) - float(want[5, 7])) <= SCORE_TOL
+    big = torch.zeros(33, 100, device="cuda")
+    eng.score_matrix(pooled[:33].contiguous(), pooled, out=big[:, 10:80])
+    assert torch.equal(big[:, 10:80].cpu(), mat) and float(big[:, :10].abs().max()) == 0.0
+
+
+def test_host_entry_point_matches_device(eng):
+    f1, f2 = synth.make_pair_batch(64, 64, 20, seed=21)
+    d_score, d_a1, d_a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)
+    h_score, h_a1, h_a2 = eng.forward_pairs_host(f1, f2, 20)
+    assert torch.equal(h_score, d_score.cpu()) and torch.equal(h_a1, d_a1.cpu()) and torch.equal(h_a2, d_a2.cpu())
+    p_score, _, _ = eng.forward_pairs_host(f1.pin_memory(), f2.pin_memory(), 20, want_att=False)
+    assert torch.equal(p_score, h_score)
+
+
+def test_edge_cases(eng, kitti_state):
+    # empty batch
+    s, a1, a2 = eng.forward_pairs(torch.zeros(0, 15, 64, device="cuda"), torch.zeros(0, 15, 64, device="cuda"), 20)
+    assert s.shape == (0,) and a1.shape == (0, 64, 1)
+    # single pair, k == N, k == 1, all-zero graph (every node a pad)
+    for n, k in ((8, 8), (64, 1), (64, 64), (5, 3)):
+        f1, f2 = synth.make_pair_batch(2, n, 1, seed=n)
+        f2[1].zero_()
+        want = orc.forward_pairs(f1, f2, k, kitti_state)
+        score, a1, a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), k)
+        if k in (1, n):      # no selection ambiguity at all when k == N; k == 1 picks self (distance 0)
+            assert float((score.cpu() - want["score"]).abs().max()) <= SCORE_TOL, (n, k)
+        assert bool(torch.isfinite(score).all()) and float(score.min()) >= 0 and float(score.max()) <= 1
+    # dense (tie-dominated) graphs still give well-formed output
+    f1, f2 = synth.make_pair_batch(4, 64, 20, seed=2, dense=True)
+    score, _, _ = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)
+    assert bool(torch.isfinite(score).all())
+
+
+def test_errors_are_loud(eng):
+    from sg_pr_b200._lib import SgprError
+    f = torch.zeros(2, 15, 64, device="cuda")
+    with pytest.raises(SgprError):
+        eng.forward_pairs(f, f, 65)            # k > N: topk raises in the reference (dgcnn.py:19)
+    with pytest.raises(SgprError):
+        eng.forward_pairs(f, f, 0)
+    big = torch.zeros(1, 15, 129, device="cuda")
+    with pytest.raises(SgprError):
+        eng.forward_pairs(big, big, 10)        # beyond the shared-memory tiling
+    with pytest.raises(ValueError):
+        eng.forward_pairs(torch.zeros(2, 14, 64, device="cuda"), torch.zeros(2, 14, 64, device="cuda"), 10)
+    from sg_pr_b200.engine import Engine
+    fresh = Engine(0)
+    with pytest.raises(SgprError):
+        fresh.forward_pairs(f, f, 10)          # no weights yet
+    fresh.close()
