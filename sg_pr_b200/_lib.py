@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libsgpr_b200.so")
+LIB_PATH = os.environ.get("SGPR_B200_LIB") or os.path.join(PKG, "libsgpr_b200.so")
 
 SGPR_OK = 0
 c_float_p = C.POINTER(C.c_float)

@@ -107,11 +107,18 @@ int sgpr_create(sgpr_ctx** out, int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->off = make_offsets();
-    const int max_smem = static_cast<int>(prop.sharedMemPerBlockOptin);
-    e = cudaFuncSetAttribute(sgpr_embed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_embed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_embed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_score_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    // opt in to the full shared-memory carve-out; the dynamic limit excludes each kernel's static __shared__ bytes
+    auto opt_in = [&](const void* fn) -> cudaError_t {
+        cudaFuncAttributes fa;
+        cudaError_t er = cudaFuncGetAttributes(&fa, fn);
+        if (er != cudaSuccess) return er;
+        const int dyn = static_cast<int>(prop.sharedMemPerBlockOptin) - static_cast<int>(fa.sharedSizeBytes);
+        return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    };
+    e = opt_in(reinterpret_cast<const void*>(&sgpr_embed_kernel<1>));
+    if (e == cudaSuccess) e = opt_in(reinterpret_cast<const void*>(&sgpr_embed_kernel<2>));
+    if (e == cudaSuccess) e = opt_in(reinterpret_cast<const void*>(&sgpr_embed_kernel<4>));
+    if (e == cudaSuccess) e = opt_in(reinterpret_cast<const void*>(&sgpr_score_matrix_kernel));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_blob), ctx->off.total * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {

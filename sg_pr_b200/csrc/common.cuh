@@ -20,19 +20,21 @@ constexpr int YS = 132;   // row stride of the per-node GEMM output tile A|B: 12
 constexpr float kSlope = 0.2f;         // LeakyReLU(negative_slope=0.2), sg_net.py:53
 
 // Packed eval-mode parameters in device memory (built by pack.cpp, one allocation).
-// EdgeConv l with C_in -> C_out: `w` is [C_in][2*C_out] (k-major, so lanes read consecutive output channels):
+// EdgeConv l with C_in -> C_out: `w` is the [C_in][2*C_out] matrix
 //   columns [0, C_out)        = sign[c] * W[c][ci]          (the (x_j - x_i) half of the 1x1 conv, dgcnn.py:47)
 //   columns [C_out, 2*C_out)  = sign[c] * W[c][C_in + ci]   (the x_i half)
+// stored in the channel-PAIR layout of pack.hpp::pair_index (row p = input channels 2p, 2p+1 interleaved per output)
+// so that one FFMA2 advances the even/odd-channel partial sums of an output.
 // `alpha`/`beta` are the BN-eval scale/shift with alpha made non-negative by folding its sign into `w`
 // (max over neighbours then commutes exactly with BN+LeakyReLU, SURVEY §7 hard part 5).
 struct PackedWeights {
     const float* s1;        // xyz layer 1: [64][8] = {wa0,wa1,wa2, wb0,wb1,wb2, alpha, beta} per output channel
-    const float* w_s2;      // [64][128]
-    const float* w_s3;      // [64][64]
-    const float* w_f1;      // [12][128]
-    const float* w_f2;      // [64][128]
-    const float* w_f3;      // [64][64]
-    const float* w_end;     // [64][32]   plain transpose of dgcnn_conv_end.0.weight
+    const float* w_s2;      // 64 in x 128 out (pair layout)
+    const float* w_s3;      // 64 x 64
+    const float* w_f1;      // 12 x 128
+    const float* w_f2;      // 64 x 128
+    const float* w_f3;      // 64 x 64
+    const float* w_end;     // 64 x 32    transpose of dgcnn_conv_end.0.weight (pair layout)
     const float* ab_s2;     // alpha[64] beta[64]
     const float* ab_s3;     // alpha[32] beta[32]
     const float* ab_f1;     // alpha[64] beta[64]

@@ -14,6 +14,11 @@
 // so each layer is: k-NN (Gram tile in registers -> bitonic threshold select) -> per-node GEMM [N x C]x[C x 2C']
 // -> gather-max over the k neighbour rows of A.  Layer 1 of the xyz branch keeps the reference's direct form
 // W_a (x_j - x_i) because metre-scale coordinates would lose ~5 bits to cancellation in A_j - A_i.
+//
+// The five GEMM-form layers run through ONE copy of the phase code (a runtime layer loop): the kernel is
+// issue/latency-bound, so instruction-cache footprint and instruction count matter more than anything else.
+// Dot products use the packed fp32 FMA of sm_100 (fma.rn.f32x2, SASS FFMA2): the two halves of a pair carry the
+// even-channel and odd-channel partial sums, added once at the end.
 #pragma once
 #include "common.cuh"
 
@@ -42,7 +47,7 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout make_layout(int nmax, int ks) {
     SmemLayout L;
     int o = 0;
-    L.w = o;   o += 64 * 128 * 4;              // largest packed layer matrix [64][128]
+    L.w = o;   o += 64 * 128 * 4;              // largest packed layer matrix (64 in x 128 out)
     L.in = o;  o += ((kInCh * nmax * 4 + 15) / 16) * 16;
     L.x = o;   o += nmax * XS * 4;
     L.y = o;   o += nmax * YS * 4;
@@ -55,34 +60,54 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int ks) {
     return L;
 }
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 // ------------------------------------------------------------------------------------------------------------
 // Bitonic sort (ascending) of 32*NPL floats held NPL per lane, element e = q*32 + lane.
+// "Flip" formulation: every merge starts with a mirror exchange (partner e ^ (size-1)) and continues with
+// half-cleaners (partner e ^ d); every exchange is ascending, so the keep-min predicate is one lane bit.
 // ------------------------------------------------------------------------------------------------------------
 template <int NPL>
 __device__ __forceinline__ void bitonic_sort_asc(float (&v)[NPL], int lane) {
 #pragma unroll
     for (int size = 2; size <= 32 * NPL; size <<= 1) {
+        // ---- mirror step ----
+        if (size <= 32) {
+            const bool keep_min = (lane & (size >> 1)) == 0;
 #pragma unroll
-        for (int d = size >> 1; d >= 1; d >>= 1) {
+            for (int q = 0; q < NPL; ++q) {
+                const float p = __shfl_xor_sync(0xffffffffu, v[q], size - 1);
+                v[q] = keep_min ? fminf(v[q], p) : fmaxf(v[q], p);
+            }
+        } else {
+            const int mq = (size >> 5) - 1;          // register mirror mask
+            const int hb = size >> 6;                // q bit that decides lower/upper half of the block
+            float p[NPL];
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) p[q] = __shfl_xor_sync(0xffffffffu, v[q ^ mq], 31);
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) v[q] = ((q & hb) == 0) ? fminf(v[q], p[q]) : fmaxf(v[q], p[q]);
+        }
+        // ---- half-cleaners ----
+#pragma unroll
+        for (int d = size >> 2; d >= 1; d >>= 1) {
             if (d >= 32) {
                 const int dq = d >> 5;
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
                     if ((q & dq) == 0) {
-                        const bool asc = ((q * 32) & size) == 0;
                         const float lo = fminf(v[q], v[q | dq]);
                         const float hi = fmaxf(v[q], v[q | dq]);
-                        v[q] = asc ? lo : hi;
-                        v[q | dq] = asc ? hi : lo;
+                        v[q] = lo;
+                        v[q | dq] = hi;
                     }
                 }
             } else {
-                const bool lower = (lane & d) == 0;
+                const bool keep_min = (lane & d) == 0;
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
                     const float p = __shfl_xor_sync(0xffffffffu, v[q], d);
-                    const bool asc = (((q * 32) | lane) & size) == 0;
-                    v[q] = (lower == asc) ? fminf(v[q], p) : fmaxf(v[q], p);
+                    v[q] = keep_min ? fminf(v[q], p) : fmaxf(v[q], p);
                 }
             }
         }
@@ -90,45 +115,45 @@ __device__ __forceinline__ void bitonic_sort_asc(float (&v)[NPL], int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k-NN of every node over the node-major tile sX[n][4*C4] (dgcnn.py:14-20).
+// k-NN of every node over the node-major tile sX[n][4*c4n] (dgcnn.py:14-20).
 //   pd[i][j] = (2*dot(x_i,x_j) - xx_j) - xx_i     == -xx - inner - xx^T with inner = -2*dot, same rounding order
 //   select the k largest per row; ties at the k-th value go to the lowest indices.  Only the SET matters
 //   downstream (max over neighbours), so the list is written in ascending index order.
 // A warp owns RG rows at a time: Gram tile in registers (RG x NPL per lane), sort a copy, threshold, compact.
 // ------------------------------------------------------------------------------------------------------------
-template <int NPL, int C4>
+template <int NPL>
 __device__ __forceinline__ void knn_phase(const float* __restrict__ sX, const float* __restrict__ sXX,
-                                          uint8_t* __restrict__ sIdx, int N, int k, int KS, int warp, int lane) {
+                                          uint8_t* __restrict__ sIdx, int c4n, int N, int k, int KS, int warp,
+                                          int lane) {
     constexpr int NMAX = 32 * NPL;
     constexpr int RG = (NPL >= 4) ? 2 : 4;
     const int ngroups = (N + RG - 1) / RG;
     const uint32_t lt = (1u << lane) - 1u;
 
+#pragma unroll 1
     for (int g = warp; g < ngroups; g += kWarps) {
         const int i0 = g * RG;
-        float acc[RG][NPL];
+        float2 acc[RG][NPL];
 #pragma unroll
         for (int r = 0; r < RG; ++r)
 #pragma unroll
-            for (int q = 0; q < NPL; ++q) acc[r][q] = 0.0f;
+            for (int q = 0; q < NPL; ++q) acc[r][q] = make_float2(0.0f, 0.0f);
 
-#pragma unroll
-        for (int c = 0; c < C4; ++c) {
+        const float* pa = sX + i0 * XS;
+        const float* pb = sX + lane * XS;
+#pragma unroll 2
+        for (int c = 0; c < c4n; ++c) {
             float4 a[RG], b[NPL];
 #pragma unroll
-            for (int r = 0; r < RG; ++r) a[r] = *reinterpret_cast<const float4*>(sX + (i0 + r) * XS + 4 * c);
+            for (int r = 0; r < RG; ++r) a[r] = *reinterpret_cast<const float4*>(pa + r * XS + 4 * c);
 #pragma unroll
-            for (int q = 0; q < NPL; ++q) b[q] = *reinterpret_cast<const float4*>(sX + (lane + 32 * q) * XS + 4 * c);
+            for (int q = 0; q < NPL; ++q) b[q] = *reinterpret_cast<const float4*>(pb + 32 * q * XS + 4 * c);
 #pragma unroll
             for (int r = 0; r < RG; ++r)
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
-                    float s = acc[r][q];
-                    s = fmaf(a[r].x, b[q].x, s);
-                    s = fmaf(a[r].y, b[q].y, s);
-                    s = fmaf(a[r].z, b[q].z, s);
-                    s = fmaf(a[r].w, b[q].w, s);
-                    acc[r][q] = s;
+                    acc[r][q] = ffma2(make_float2(a[r].x, a[r].y), make_float2(b[q].x, b[q].y), acc[r][q]);
+                    acc[r][q] = ffma2(make_float2(a[r].z, a[r].w), make_float2(b[q].z, b[q].w), acc[r][q]);
                 }
         }
 
@@ -144,7 +169,8 @@ __device__ __forceinline__ void knn_phase(const float* __restrict__ sX, const fl
             float o[NPL], v[NPL];
 #pragma unroll
             for (int q = 0; q < NPL; ++q) {
-                const float t = __fsub_rn(__fmul_rn(2.0f, acc[r][q]), xxj[q]);
+                const float dot = __fadd_rn(acc[r][q].x, acc[r][q].y);
+                const float t = __fsub_rn(__fmul_rn(2.0f, dot), xxj[q]);
                 const float pd = __fsub_rn(t, xxi);
                 o[q] = (lane + 32 * q < N) ? pd : -INFINITY;
                 v[q] = o[q];
@@ -187,48 +213,54 @@ __device__ __forceinline__ void knn_phase(const float* __restrict__ sX, const fl
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Per-node GEMM: out[n][co] = sum_ci X[n][ci] * W[ci][co], co in [0, 32*CPL), sequential FMA over ci ascending.
-// A warp owns NT nodes x all outputs; a lane owns CPL consecutive outputs.  EPI: 0 = store raw,
-// 1 = BN(alpha,beta)+LeakyReLU (conv_end, sg_net.py:74-76,105).
+// Per-node GEMM: out[n][co] = sum_ci X[n][ci] * W[ci][co], co in [0, 32*CPL).
+// A warp owns NT nodes x all outputs; a lane owns CPL consecutive outputs.  W is packed in channel PAIRS
+// (pack.hpp: pack_pairs): row p holds, for every output, (W[2p][co], W[2p+1][co]) so that one FFMA2 advances the
+// even- and odd-channel partial sums of an output.  EPI: 0 = store raw, 1 = BN(alpha,beta)+LeakyReLU (conv_end).
 // ------------------------------------------------------------------------------------------------------------
-template <int CIN4, int CPL, int EPI>
+template <int CPL, int EPI>
 __device__ __forceinline__ void node_gemm(const float* __restrict__ sXin, const float* __restrict__ sW,
                                           float* __restrict__ sOut, int outStride, const float* __restrict__ ab,
-                                          int N, int warp, int lane) {
+                                          int cin4, int N, int warp, int lane) {
     constexpr int NT = 8;
     constexpr int CO = 32 * CPL;
+    constexpr int ROW = 2 * CO;                  // floats per channel-pair row
     const int nchunks = (N + NT - 1) / NT;
+#pragma unroll 1
     for (int ch = warp; ch < nchunks; ch += kWarps) {
         const int n0 = ch * NT;
-        float acc[NT][CPL];
+        float2 acc[NT][CPL];
 #pragma unroll
         for (int n = 0; n < NT; ++n)
 #pragma unroll
-            for (int p = 0; p < CPL; ++p) acc[n][p] = 0.0f;
+            for (int j = 0; j < CPL; ++j) acc[n][j] = make_float2(0.0f, 0.0f);
 
-#pragma unroll 4
-        for (int c4 = 0; c4 < CIN4; ++c4) {
+        const float* px = sXin + n0 * XS;
+#pragma unroll 2
+        for (int c4 = 0; c4 < cin4; ++c4) {
             float4 x[NT];
 #pragma unroll
-            for (int n = 0; n < NT; ++n) x[n] = *reinterpret_cast<const float4*>(sXin + (n0 + n) * XS + 4 * c4);
+            for (int n = 0; n < NT; ++n) x[n] = *reinterpret_cast<const float4*>(px + n * XS + 4 * c4);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float w[CPL];
-                const float* wp = sW + (4 * c4 + q) * CO + lane * CPL;
+            for (int h = 0; h < 2; ++h) {        // channel pair 2*c4 + h
+                float2 w[CPL];
+                const float* wp = sW + (2 * c4 + h) * ROW;
                 if constexpr (CPL == 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(wp);
-                    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+                    const float4 t0 = *reinterpret_cast<const float4*>(wp + lane * 4);
+                    const float4 t1 = *reinterpret_cast<const float4*>(wp + 128 + lane * 4);
+                    w[0] = make_float2(t0.x, t0.y); w[1] = make_float2(t0.z, t0.w);
+                    w[2] = make_float2(t1.x, t1.y); w[3] = make_float2(t1.z, t1.w);
                 } else if constexpr (CPL == 2) {
-                    const float2 t = *reinterpret_cast<const float2*>(wp);
-                    w[0] = t.x; w[1] = t.y;
+                    const float4 t0 = *reinterpret_cast<const float4*>(wp + lane * 4);
+                    w[0] = make_float2(t0.x, t0.y); w[1] = make_float2(t0.z, t0.w);
                 } else {
-                    w[0] = *wp;
+                    w[0] = *reinterpret_cast<const float2*>(wp + lane * 2);
                 }
 #pragma unroll
                 for (int n = 0; n < NT; ++n) {
-                    const float xv = (q == 0) ? x[n].x : (q == 1) ? x[n].y : (q == 2) ? x[n].z : x[n].w;
+                    const float2 xv = h ? make_float2(x[n].z, x[n].w) : make_float2(x[n].x, x[n].y);
 #pragma unroll
-                    for (int p = 0; p < CPL; ++p) acc[n][p] = fmaf(xv, w[p], acc[n][p]);
+                    for (int j = 0; j < CPL; ++j) acc[n][j] = ffma2(xv, w[j], acc[n][j]);
                 }
             }
         }
@@ -236,20 +268,20 @@ __device__ __forceinline__ void node_gemm(const float* __restrict__ sXin, const 
         float al[CPL], be[CPL];
         if constexpr (EPI == 1) {
 #pragma unroll
-            for (int p = 0; p < CPL; ++p) { al[p] = __ldg(ab + lane * CPL + p); be[p] = __ldg(ab + CO + lane * CPL + p); }
+            for (int j = 0; j < CPL; ++j) { al[j] = __ldg(ab + lane * CPL + j); be[j] = __ldg(ab + CO + lane * CPL + j); }
         }
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-            float* op = sOut + (n0 + n) * outStride + lane * CPL;
+            float y[CPL];
 #pragma unroll
-            for (int p = 0; p < CPL; ++p) {
-                float y = acc[n][p];
-                if constexpr (EPI == 1) y = lrelu(fmaf(y, al[p], be[p]));
-                acc[n][p] = y;
+            for (int j = 0; j < CPL; ++j) {
+                y[j] = __fadd_rn(acc[n][j].x, acc[n][j].y);
+                if constexpr (EPI == 1) y[j] = lrelu(fmaf(y[j], al[j], be[j]));
             }
-            if constexpr (CPL == 4) *reinterpret_cast<float4*>(op) = make_float4(acc[n][0], acc[n][1], acc[n][2], acc[n][3]);
-            else if constexpr (CPL == 2) *reinterpret_cast<float2*>(op) = make_float2(acc[n][0], acc[n][1]);
-            else *op = acc[n][0];
+            float* op = sOut + (n0 + n) * outStride + lane * CPL;
+            if constexpr (CPL == 4) *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
+            else if constexpr (CPL == 2) *reinterpret_cast<float2*>(op) = make_float2(y[0], y[1]);
+            else *op = y[0];
         }
     }
 }
@@ -268,30 +300,33 @@ __device__ __forceinline__ void gather_max_bn(const float* __restrict__ sY, cons
 #pragma unroll
     for (int p = 0; p < CPL; ++p) { al[p] = __ldg(ab + lane * CPL + p); be[p] = __ldg(ab + COUT + lane * CPL + p); }
 
+#pragma unroll 1
     for (int i = warp; i < N; i += kWarps) {
         float m[CPL];
 #pragma unroll
         for (int p = 0; p < CPL; ++p) m[p] = -INFINITY;
         const uint8_t* row = sIdx + i * KS;
+        const float* base = sY + lane * CPL;
+#pragma unroll 2
         for (int t = 0; t < KS; t += 4) {
             const uchar4 jj = *reinterpret_cast<const uchar4*>(row + t);
             if constexpr (CPL == 2) {
-                const float2 a0 = *reinterpret_cast<const float2*>(sY + jj.x * YS + 2 * lane);
-                const float2 a1 = *reinterpret_cast<const float2*>(sY + jj.y * YS + 2 * lane);
-                const float2 a2 = *reinterpret_cast<const float2*>(sY + jj.z * YS + 2 * lane);
-                const float2 a3 = *reinterpret_cast<const float2*>(sY + jj.w * YS + 2 * lane);
+                const float2 a0 = *reinterpret_cast<const float2*>(base + jj.x * YS);
+                const float2 a1 = *reinterpret_cast<const float2*>(base + jj.y * YS);
+                const float2 a2 = *reinterpret_cast<const float2*>(base + jj.z * YS);
+                const float2 a3 = *reinterpret_cast<const float2*>(base + jj.w * YS);
                 m[0] = fmaxf(fmaxf(m[0], fmaxf(a0.x, a1.x)), fmaxf(a2.x, a3.x));
                 m[1] = fmaxf(fmaxf(m[1], fmaxf(a0.y, a1.y)), fmaxf(a2.y, a3.y));
             } else {
-                const float a0 = sY[jj.x * YS + lane], a1 = sY[jj.y * YS + lane];
-                const float a2 = sY[jj.z * YS + lane], a3 = sY[jj.w * YS + lane];
+                const float a0 = base[jj.x * YS], a1 = base[jj.y * YS];
+                const float a2 = base[jj.z * YS], a3 = base[jj.w * YS];
                 m[0] = fmaxf(fmaxf(m[0], fmaxf(a0, a1)), fmaxf(a2, a3));
             }
         }
 #pragma unroll
         for (int p = 0; p < CPL; ++p) {
-            const float ai = sY[i * YS + lane * CPL + p];
-            const float bi = sY[i * YS + COUT + lane * CPL + p];
+            const float ai = base[i * YS + p];
+            const float bi = base[i * YS + COUT + p];
             const float y = __fadd_rn(__fsub_rn(m[p], ai), bi);
             const float z = lrelu(fmaf(y, al[p], be[p]));
             sDst[i * dstStride + lane * CPL + p] = z;
@@ -313,11 +348,14 @@ __device__ __forceinline__ void xyz_layer1(const float* __restrict__ sIn, const 
     const float4 p1 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane) * 2 + 1);
     const float4 r0 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane + 1) * 2);
     const float4 r1 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane + 1) * 2 + 1);
-    // p0 = {wa0,wa1,wa2,wb0}, p1 = {wb1,wb2,alpha,beta}
+    // p0 = {wa0,wa1,wa2,wb0}, p1 = {wb1,wb2,alpha,beta} of channel 2*lane; r0/r1 the same for 2*lane+1
+    const float2 wa0 = make_float2(p0.x, r0.x), wa1 = make_float2(p0.y, r0.y), wa2 = make_float2(p0.z, r0.z);
+#pragma unroll 1
     for (int i = warp; i < N; i += kWarps) {
         const float xi0 = sIn[i], xi1 = sIn[N + i], xi2 = sIn[2 * N + i];
         float m0 = -INFINITY, m1 = -INFINITY;
         const uint8_t* row = sIdx + i * KS;
+#pragma unroll 1
         for (int t = 0; t < KS; t += 4) {
             const uchar4 jj = *reinterpret_cast<const uchar4*>(row + t);
             const int js[4] = {jj.x, jj.y, jj.z, jj.w};
@@ -327,10 +365,11 @@ __device__ __forceinline__ void xyz_layer1(const float* __restrict__ sIn, const 
                 const float d0 = __fsub_rn(sIn[j], xi0);
                 const float d1 = __fsub_rn(sIn[N + j], xi1);
                 const float d2 = __fsub_rn(sIn[2 * N + j], xi2);
-                float e0 = __fmul_rn(p0.x, d0); e0 = fmaf(p0.y, d1, e0); e0 = fmaf(p0.z, d2, e0);
-                float e1 = __fmul_rn(r0.x, d0); e1 = fmaf(r0.y, d1, e1); e1 = fmaf(r0.z, d2, e1);
-                m0 = fmaxf(m0, e0);
-                m1 = fmaxf(m1, e1);
+                float2 e = __fmul2_rn(wa0, make_float2(d0, d0));
+                e = ffma2(wa1, make_float2(d1, d1), e);
+                e = ffma2(wa2, make_float2(d2, d2), e);
+                m0 = fmaxf(m0, e.x);
+                m1 = fmaxf(m1, e.y);
             }
         }
         float y0 = fmaf(p0.w, xi0, m0); y0 = fmaf(p1.x, xi1, y0); y0 = fmaf(p1.y, xi2, y0);
@@ -342,14 +381,26 @@ __device__ __forceinline__ void xyz_layer1(const float* __restrict__ sIn, const 
     }
 }
 
-// squared norms per node, sequential over channels: xx = sum_c x_c^2   (dgcnn.py:16, products rounded, then added)
-template <int C>
-__device__ __forceinline__ void sq_norms(const float* __restrict__ sX, float* __restrict__ sXX, int N, int tid) {
-    for (int n = tid; n < N; n += kThreads) {
+// squared norms per node: xx = sum_c x_c^2 (dgcnn.py:16; products rounded, then added).  4 threads per node, each
+// sums a quarter of the channels in order, partials combined pairwise.
+__device__ __forceinline__ void sq_norms(const float* __restrict__ sX, float* __restrict__ sXX, int c4n, int N, int tid) {
+    const int part = tid & 3;
+    const int per = (c4n + 3) >> 2;                     // float4 groups per quarter
+    for (int n0 = 0; n0 < N; n0 += kThreads / 4) {      // warp-uniform trip count
+        const int n = n0 + (tid >> 2);
         float s = 0.0f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) { const float x = sX[n * XS + c]; s = __fadd_rn(s, __fmul_rn(x, x)); }
-        sXX[n] = s;
+        if (n < N) {
+            for (int g = part * per; g < min(c4n, (part + 1) * per); ++g) {
+                const float4 x = *reinterpret_cast<const float4*>(sX + n * XS + 4 * g);
+                s = __fadd_rn(s, __fmul_rn(x.x, x.x));
+                s = __fadd_rn(s, __fmul_rn(x.y, x.y));
+                s = __fadd_rn(s, __fmul_rn(x.z, x.z));
+                s = __fadd_rn(s, __fmul_rn(x.w, x.w));
+            }
+        }
+        s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
+        s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));
+        if (n < N && part == 0) sXX[n] = s;
     }
 }
 
@@ -400,11 +451,24 @@ __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, cons
     }
 }
 
+// One entry of the layer loop (the five GEMM-form EdgeConv layers, sg_net.py:87-102).
+struct LayerDesc {
+    const float* w;        // this layer's packed matrix (already requested into sW by the previous step)
+    const float* ab;       // alpha | beta
+    const float* next_w;   // matrix to prefetch into sW once this layer's GEMM has consumed sW
+    int next_bytes;
+    int cin4;              // input channels / 4
+    int cout;              // 64 or 32
+};
+
 // ------------------------------------------------------------------------------------------------------------
 // The fused kernel.
 // ------------------------------------------------------------------------------------------------------------
+#ifndef SGPR_MINBLOCKS_SMALL
+#define SGPR_MINBLOCKS_SMALL 2
+#endif
 template <int NPL>
-__global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, (NPL <= 2) ? SGPR_MINBLOCKS_SMALL : 1)
 sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) {
     constexpr int NMAX = 32 * NPL;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -429,10 +493,12 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
     if (tid == 0) { mbar_init(barIn, 1); mbar_init(barW, 1); fence_mbar_init(); }
     // zero the feature tiles once so rows >= N never hold junk
     for (int e = tid; e < NMAX * XS; e += kThreads) { sX[e] = 0.0f; sCat[e] = 0.0f; }
+    for (int e = tid; e < NMAX; e += kThreads) sXX[e] = 0.0f;
     __syncthreads();
 
     const uint32_t inBytes = static_cast<uint32_t>(kInCh * N * 4);
 
+#pragma unroll 1
     for (int g = blockIdx.x; g < A.G; g += gridDim.x) {
         const float* gin = A.pairs ? (((g & 1) ? A.g1 : A.g0) + static_cast<size_t>(g >> 1) * kInCh * N)
                                    : (A.g0 + static_cast<size_t>(g) * kInCh * N);
@@ -449,90 +515,56 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         if (bulk_ok) { mbar_wait(barIn, phIn); phIn ^= 1; }
         else { for (int e = tid; e < kInCh * N; e += kThreads) sIn[e] = __ldg(gin + e); __syncthreads(); }
 
-        // ================= xyz branch =================
-        // layer 1 operand: node-major [n][4] = (x, y, z, 0)
+        // ================= xyz layer 1 (direct form) =================
         for (int n = tid; n < N; n += kThreads) {
             const float x = sIn[n], y = sIn[N + n], z = sIn[2 * N + n];
             *reinterpret_cast<float4*>(sX + n * XS) = make_float4(x, y, z, 0.0f);
             sXX[n] = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
         }
         __syncthreads();
-        knn_phase<NPL, 1>(sX, sXX, sIdx, N, k, KS, warp, lane);
+        knn_phase<NPL>(sX, sXX, sIdx, 1, N, k, KS, warp, lane);
         __syncthreads();
         trace_knn_rows(tk, sIdx, N, k, KS, tid);
         xyz_layer1(sIn, sIdx, KS, W.s1, sX, tl, N, warp, lane);
         __syncthreads();
 
-        // layer 2: 64 -> 64
-        sq_norms<64>(sX, sXX, N, tid);
-        __syncthreads();
-        knn_phase<NPL, 16>(sX, sXX, sIdx, N, k, KS, warp, lane);
-        mbar_wait(barW, phW); phW ^= 1;
-        node_gemm<16, 4, 0>(sX, sW, sY, YS, nullptr, N, warp, lane);
-        __syncthreads();
-        if (tid == 0) { mbar_expect_tx(barW, 64 * 64 * 4); bulk_g2s(sW, W.w_s3, 64 * 64 * 4, barW); }
-        trace_knn_rows(tk ? tk + 1 * N * k : nullptr, sIdx, N, k, KS, tid);
-        gather_max_bn<64>(sY, sIdx, KS, W.ab_s2, sX, XS, tl ? tl + 1 * N * 64 : nullptr, N, warp, lane);
-        __syncthreads();
-
-        // layer 3: 64 -> 32, result into sCat[:, 0:32]
-        sq_norms<64>(sX, sXX, N, tid);
-        __syncthreads();
-        knn_phase<NPL, 16>(sX, sXX, sIdx, N, k, KS, warp, lane);
-        mbar_wait(barW, phW); phW ^= 1;
-        node_gemm<16, 2, 0>(sX, sW, sY, YS, nullptr, N, warp, lane);
-        __syncthreads();
-        if (tid == 0) { mbar_expect_tx(barW, 12 * 128 * 4); bulk_g2s(sW, W.w_f1, 12 * 128 * 4, barW); }
-        trace_knn_rows(tk ? tk + 2 * N * k : nullptr, sIdx, N, k, KS, tid);
-        gather_max_bn<32>(sY, sIdx, KS, W.ab_s3, sCat, XS, tl ? tl + 2 * N * 64 : nullptr, N, warp, lane);
-        __syncthreads();
-
-        // ================= semantic branch =================
-        // layer 1 operand: node-major [n][12] from input rows 3..14
-        for (int e = tid; e < N * kLabels; e += kThreads) {
-            const int n = e % N, c = e / N;
-            sX[n * XS + c] = sIn[(3 + c) * N + n];
+        // ================= the five GEMM-form EdgeConv layers: xyz 2,3 then sem 1,2,3 =================
+#pragma unroll 1
+        for (int l = 1; l < 6; ++l) {
+            LayerDesc D;
+            switch (l) {
+                case 1:  D = LayerDesc{W.w_s2, W.ab_s2, W.w_s3, 64 * 64 * 4, 16, 64}; break;
+                case 2:  D = LayerDesc{W.w_s3, W.ab_s3, W.w_f1, 12 * 128 * 4, 16, 32}; break;
+                case 3:  D = LayerDesc{W.w_f1, W.ab_f1, W.w_f2, 64 * 128 * 4, 3, 64}; break;
+                case 4:  D = LayerDesc{W.w_f2, W.ab_f2, W.w_f3, 64 * 64 * 4, 16, 64}; break;
+                default: D = LayerDesc{W.w_f3, W.ab_f3, W.w_end, 64 * 32 * 4, 16, 32}; break;
+            }
+            if (l == 3) {   // semantic branch input: node-major [n][12] from input rows 3..14 (sg_net.py:82,94)
+                for (int e = tid; e < N * kLabels; e += kThreads) {
+                    const int n = e % N, c = e / N;
+                    sX[n * XS + c] = sIn[(3 + c) * N + n];
+                }
+                __syncthreads();
+            }
+            sq_norms(sX, sXX, D.cin4, N, tid);
+            __syncthreads();
+            knn_phase<NPL>(sX, sXX, sIdx, D.cin4, N, k, KS, warp, lane);
+            mbar_wait(barW, phW); phW ^= 1;
+            if (D.cout == 64) node_gemm<4, 0>(sX, sW, sY, YS, nullptr, D.cin4, N, warp, lane);
+            else              node_gemm<2, 0>(sX, sW, sY, YS, nullptr, D.cin4, N, warp, lane);
+            __syncthreads();
+            if (tid == 0) { mbar_expect_tx(barW, D.next_bytes); bulk_g2s(sW, D.next_w, D.next_bytes, barW); }
+            trace_knn_rows(tk ? tk + l * N * k : nullptr, sIdx, N, k, KS, tid);
+            float* tr = tl ? tl + l * N * 64 : nullptr;
+            if (D.cout == 64) gather_max_bn<64>(sY, sIdx, KS, D.ab, sX, XS, tr, N, warp, lane);
+            else              gather_max_bn<32>(sY, sIdx, KS, D.ab, (l == 2) ? sCat : sCat + 32, XS, tr, N, warp, lane);
+            __syncthreads();
         }
-        __syncthreads();
-        sq_norms<kLabels>(sX, sXX, N, tid);
-        __syncthreads();
-        knn_phase<NPL, 3>(sX, sXX, sIdx, N, k, KS, warp, lane);
-        mbar_wait(barW, phW); phW ^= 1;
-        node_gemm<3, 4, 0>(sX, sW, sY, YS, nullptr, N, warp, lane);
-        __syncthreads();
-        if (tid == 0) { mbar_expect_tx(barW, 64 * 128 * 4); bulk_g2s(sW, W.w_f2, 64 * 128 * 4, barW); }
-        trace_knn_rows(tk ? tk + 3 * N * k : nullptr, sIdx, N, k, KS, tid);
-        gather_max_bn<64>(sY, sIdx, KS, W.ab_f1, sX, XS, tl ? tl + 3 * N * 64 : nullptr, N, warp, lane);
-        __syncthreads();
-
-        // layer 2
-        sq_norms<64>(sX, sXX, N, tid);
-        __syncthreads();
-        knn_phase<NPL, 16>(sX, sXX, sIdx, N, k, KS, warp, lane);
-        mbar_wait(barW, phW); phW ^= 1;
-        node_gemm<16, 4, 0>(sX, sW, sY, YS, nullptr, N, warp, lane);
-        __syncthreads();
-        if (tid == 0) { mbar_expect_tx(barW, 64 * 64 * 4); bulk_g2s(sW, W.w_f3, 64 * 64 * 4, barW); }
-        trace_knn_rows(tk ? tk + 4 * N * k : nullptr, sIdx, N, k, KS, tid);
-        gather_max_bn<64>(sY, sIdx, KS, W.ab_f2, sX, XS, tl ? tl + 4 * N * 64 : nullptr, N, warp, lane);
-        __syncthreads();
-
-        // layer 3, result into sCat[:, 32:64]
-        sq_norms<64>(sX, sXX, N, tid);
-        __syncthreads();
-        knn_phase<NPL, 16>(sX, sXX, sIdx, N, k, KS, warp, lane);
-        mbar_wait(barW, phW); phW ^= 1;
-        node_gemm<16, 2, 0>(sX, sW, sY, YS, nullptr, N, warp, lane);
-        __syncthreads();
-        if (tid == 0) { mbar_expect_tx(barW, 64 * 32 * 4); bulk_g2s(sW, W.w_end, 64 * 32 * 4, barW); }
-        trace_knn_rows(tk ? tk + 5 * N * k : nullptr, sIdx, N, k, KS, tid);
-        gather_max_bn<32>(sY, sIdx, KS, W.ab_f3, sCat + 32, XS, tl ? tl + 5 * N * 64 : nullptr, N, warp, lane);
-        __syncthreads();
 
         // ================= conv_end (sg_net.py:104-109): cat(xyz3, sem3) [N,64] -> [N,32] =================
         mbar_wait(barW, phW); phW ^= 1;
         float* sE = sX;   // node embeddings, stride XS (first 32 columns)
-        node_gemm<16, 1, 1>(sCat, sW, sE, XS, W.ab_end, N, warp, lane);
+        node_gemm<1, 1>(sCat, sW, sE, XS, W.ab_end, 16, N, warp, lane);
         __syncthreads();
         if (A.emb) {
             float* eo = A.emb + static_cast<size_t>(g) * N * kF3;
@@ -542,19 +574,17 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         // ================= attention pooling (layers_batch.py:28-39) =================
         // ctx[b] = tanh(mean_n sum_a E[n][a] Watt[a][b]): lane = b, warp strides over nodes
         {
-            float wcol[kF3];
-#pragma unroll
-            for (int a = 0; a < kF3; ++a) wcol[a] = __ldg(W.att_w + a * kF3 + lane);
             float colsum = 0.0f;
+#pragma unroll 1
             for (int n = warp; n < N; n += kWarps) {
                 float t = 0.0f;
-#pragma unroll
+#pragma unroll 4
                 for (int a4 = 0; a4 < kF3 / 4; ++a4) {
                     const float4 e = *reinterpret_cast<const float4*>(sE + n * XS + 4 * a4);
-                    t = fmaf(e.x, wcol[4 * a4 + 0], t);
-                    t = fmaf(e.y, wcol[4 * a4 + 1], t);
-                    t = fmaf(e.z, wcol[4 * a4 + 2], t);
-                    t = fmaf(e.w, wcol[4 * a4 + 3], t);
+                    t = fmaf(e.x, __ldg(W.att_w + (4 * a4 + 0) * kF3 + lane), t);
+                    t = fmaf(e.y, __ldg(W.att_w + (4 * a4 + 1) * kF3 + lane), t);
+                    t = fmaf(e.z, __ldg(W.att_w + (4 * a4 + 2) * kF3 + lane), t);
+                    t = fmaf(e.w, __ldg(W.att_w + (4 * a4 + 3) * kF3 + lane), t);
                 }
                 colsum = __fadd_rn(colsum, t);
             }
@@ -574,7 +604,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         float* sAtt = sXX;
         for (int n = tid; n < N; n += kThreads) {
             float s = 0.0f;
-#pragma unroll
+#pragma unroll 8
             for (int b = 0; b < kF3; ++b) s = fmaf(sE[n * XS + b], sCtx[b], s);
             const float a = sigmoidf_acc(s);
             sAtt[n] = a;

@@ -53,8 +53,20 @@ inline void bn_terms(const sgpr_bn& bn, int c, float eps, float& alpha, float& b
     beta = bn.bias[c] - bn.running_mean[c] * alpha;
 }
 
-// EdgeConv layer: conv weight [cout][2*cin] -> k-major [cin][2*cout] with the BN-scale sign folded in.
+// Index of element (ci, co) of a [cin][CO] matrix in the channel-PAIR layout the kernels read (CO = 32*CPL):
+// row p = ci/2 holds, per output, the pair (W[2p][co], W[2p+1][co]); a lane owns CPL consecutive outputs and reads
+// them as conflict-free 16-byte (CPL>=2) or 8-byte (CPL=1) vectors, outputs 2,3 of a lane in a second 128-float plane.
+inline size_t pair_index(int ci, int co, int CO) {
+    const int cpl = CO / 32;
+    const int p = ci >> 1, r = ci & 1;
+    const int lane = co / cpl, j = co % cpl;
+    return static_cast<size_t>(p) * 2 * CO + (j >> 1) * 128 + lane * (cpl >= 2 ? 4 : 2) + (j & 1) * 2 + r;
+}
+
+// EdgeConv layer: conv weight [cout][2*cin] -> pair layout of the [cin][2*cout] matrix (A half | B half) with the
+// BN-scale sign folded in.
 inline void pack_edgeconv(const float* w, const sgpr_bn& bn, int cin, int cout, float eps, float* wt, float* ab) {
+    const int CO = 2 * cout;
     for (int c = 0; c < cout; ++c) {
         float alpha, beta;
         bn_terms(bn, c, eps, alpha, beta);
@@ -62,8 +74,8 @@ inline void pack_edgeconv(const float* w, const sgpr_bn& bn, int cin, int cout, 
         ab[c] = sign * alpha;
         ab[cout + c] = beta;
         for (int ci = 0; ci < cin; ++ci) {
-            wt[static_cast<size_t>(ci) * 2 * cout + c] = sign * w[static_cast<size_t>(c) * 2 * cin + ci];
-            wt[static_cast<size_t>(ci) * 2 * cout + cout + c] = sign * w[static_cast<size_t>(c) * 2 * cin + cin + ci];
+            wt[pair_index(ci, c, CO)] = sign * w[static_cast<size_t>(c) * 2 * cin + ci];
+            wt[pair_index(ci, cout + c, CO)] = sign * w[static_cast<size_t>(c) * 2 * cin + cin + ci];
         }
     }
 }
@@ -86,13 +98,13 @@ inline int pack_weights(const sgpr_weights& hw, std::vector<float>& blob, HeadPa
     pack_edgeconv(hw.f_conv_w[0], hw.f_bn[0], 12, 64, eps, blob.data() + o.w_f1, blob.data() + o.ab_f1);
     pack_edgeconv(hw.f_conv_w[1], hw.f_bn[1], 64, 64, eps, blob.data() + o.w_f2, blob.data() + o.ab_f2);
     pack_edgeconv(hw.f_conv_w[2], hw.f_bn[2], 64, 32, eps, blob.data() + o.w_f3, blob.data() + o.ab_f3);
-    // conv_end [32][64] -> [64][32]; BN sign kept (no max follows)
+    // conv_end [32][64] -> pair layout of [64][32]; BN sign kept (no max follows)
     for (int c = 0; c < 32; ++c) {
         float alpha, beta;
         bn_terms(hw.end_bn, c, eps, alpha, beta);
         blob[o.ab_end + c] = alpha;
         blob[o.ab_end + 32 + c] = beta;
-        for (int ci = 0; ci < 64; ++ci) blob[o.w_end + ci * 32 + c] = hw.end_conv_w[c * 64 + ci];
+        for (int ci = 0; ci < 64; ++ci) blob[o.w_end + pair_index(ci, c, 32)] = hw.end_conv_w[c * 64 + ci];
     }
     std::memcpy(blob.data() + o.att_w, hw.att_w, sizeof(float) * 32 * 32);
     std::memcpy(blob.data() + o.ntn_w, hw.ntn_w, sizeof(float) * 32 * 512);

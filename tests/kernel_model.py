@@ -24,6 +24,16 @@ def _lrelu(z):
     return np.where(z > 0, z, z * np.float32(0.2)).astype(np.float32)
 
 
+def unpack_pairs(flat, cin, co):
+    """Inverse of csrc/pack.hpp::pair_index: flat pair-layout buffer -> dense [cin, co] matrix."""
+    cpl = co // 32
+    ci = np.arange(cin)[:, None]
+    c = np.arange(co)[None, :]
+    lane, j = c // cpl, c % cpl
+    idx = (ci >> 1) * 2 * co + (j >> 1) * 128 + lane * (4 if cpl >= 2 else 2) + (j & 1) * 2 + (ci & 1)
+    return flat[idx]
+
+
 def embed_graph(feat, k, blob, offs):
     """feat [15, N] -> dict(emb [N,32], att [N], pooled [32], knn [6][N,k], layers [6][N,C'])."""
     f32 = np.float32
@@ -33,7 +43,7 @@ def embed_graph(feat, k, blob, offs):
 
     def edge_layer(x, wname, abname, cin, cout):
         idx = _topk_set_lowest_index(_pd(x), k)
-        w = sec(wname, cin * 2 * cout).reshape(cin, 2 * cout)
+        w = unpack_pairs(sec(wname, cin * 2 * cout), cin, 2 * cout)
         y = (x.astype(f32) @ w).astype(f32)
         a, b = y[:, :cout], y[:, cout:]
         m = a[idx].max(axis=1)
@@ -63,7 +73,7 @@ def embed_graph(feat, k, blob, offs):
 
     cat = np.concatenate([xyz3, sem3], axis=1)
     ab = sec("ab_end", 64)
-    emb = _lrelu((cat @ sec("w_end", 64 * 32).reshape(64, 32)).astype(f32) * ab[:32] + ab[32:])
+    emb = _lrelu((cat @ unpack_pairs(sec("w_end", 64 * 32), 64, 32)).astype(f32) * ab[:32] + ab[32:])
     watt = sec("att_w", 1024).reshape(32, 32)
     ctx = np.tanh((emb @ watt).astype(f32).sum(axis=0, dtype=f32) / f32(n)).astype(f32)
     att = (1.0 / (1.0 + np.exp(-(emb @ ctx).astype(f32)))).astype(f32)

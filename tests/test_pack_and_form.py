@@ -28,7 +28,7 @@ def test_pack_layout_and_sign_fold(kitti_state, packed):
     inv = 1.0 / torch.sqrt(sd["dgcnn_s_conv2.1.running_var"] + 1e-5)
     alpha = (inv * sd["dgcnn_s_conv2.1.weight"]).numpy()
     sign = np.where(alpha < 0, -1.0, 1.0).astype(np.float32)
-    w = blob[offs["w_s2"]:offs["w_s2"] + 64 * 128].reshape(64, 128)
+    w = km.unpack_pairs(blob[offs["w_s2"]:offs["w_s2"] + 64 * 128], 64, 128)
     ref = sd["dgcnn_s_conv2.0.weight"].numpy().reshape(64, 128)
     np.testing.assert_array_equal(w[:, :64], (ref[:, :64] * sign[:, None]).T)
     np.testing.assert_array_equal(w[:, 64:], (ref[:, 64:] * sign[:, None]).T)
