@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -78,6 +79,7 @@ struct sgpr_ctx {
     float* d_blk = nullptr;      size_t blk_cap = 0;     // rowblk | colblk
     cudaStream_t stream = nullptr;                      // host-path stream
     long long launches = 0;
+    int dedup = 1;               // collapse trailing all-zero nodes (exact); SGPR_NO_DEDUP=1 disables it for experiments
 };
 
 extern "C" {
@@ -107,6 +109,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->off = make_offsets();
+    if (const char* nd = getenv("SGPR_NO_DEDUP")) ctx->dedup = (nd[0] == '1') ? 0 : 1;
     // opt in to the full shared-memory carve-out; the dynamic limit excludes each kernel's static __shared__ bytes
     auto opt_in = [&](const void* fn) -> cudaError_t {
         cudaFuncAttributes fa;
@@ -195,6 +198,7 @@ int check_shape(const char* who, int count, int N, int k) {
 int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     const int N = a.N;
     a.KS = (a.k + 3) & ~3;
+    a.dedup = ctx->dedup;
     const int npl = (N <= 32) ? 1 : (N <= 64) ? 2 : 4;
     const SmemLayout L = make_layout(32 * npl, a.KS);
     const int per_sm = (npl <= 2) ? 2 : 1;

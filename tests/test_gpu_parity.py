@@ -148,6 +148,26 @@ def test_batch_independence_and_launch_determinism(eng):
     assert torch.equal(rev, full)
 
 
+def test_pad_collapse_is_bit_exact(eng, kitti_state, monkeypatch):
+    """Collapsing the trailing all-zero pad nodes into one row (csrc/embed_kernel.cuh) must not change a single bit
+    versus processing every node: compare against a context created with SGPR_NO_DEDUP=1."""
+    from sg_pr_b200.engine import Engine
+    monkeypatch.setenv("SGPR_NO_DEDUP", "1")
+    plain = Engine(0)
+    monkeypatch.delenv("SGPR_NO_DEDUP")
+    plain.set_weights(kitti_state)
+    for n, k, dense in ((64, 20, False), (100, 10, False), (32, 10, False), (64, 20, True)):
+        g = synth.make_graphs(40, n, k, seed=31, dense=dense)
+        g[3].zero_()                       # an all-pad graph
+        g[4, :, n // 2:].zero_()           # pads start mid-way
+        g[5, :, 1:].zero_()                # a single real node
+        a = eng.embed(_cuda(g), k, want_att=True, want_emb=True)
+        b = plain.embed(_cuda(g), k, want_att=True, want_emb=True)
+        for key in ("pooled", "att", "emb"):
+            assert torch.equal(a[key], b[key]), (n, k, dense, key)
+    plain.close()
+
+
 def test_pairs_equal_embed_plus_head(eng):
     """forward_pairs == embed + score_pairs == score_matrix entry, bit for bit in the pair head's own arithmetic."""
     f1, f2 = synth.make_pair_batch(40, 64, 20, seed=5)
