@@ -633,7 +633,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
                 uint32_t bits = 0;
 #pragma unroll
                 for (int c = 0; c < kInCh; ++c) bits |= __float_as_uint(sIn[c * N + n]);
-                if (bits != 0u) last = n;
+                if ((bits << 1) != 0u) last = n;          // +0.0 and -0.0 are both "zero": they compare and add alike
             }
             last = __reduce_max_sync(0xffffffffu, last);
             if (lane == 0) sLast[warp] = last;

@@ -44,7 +44,7 @@ def make_graphs(num_graphs: int, node_num: int = 64, k: int = 20, seed: int = 0,
     xyz = (torch.rand(num_graphs, node_num, 3, generator=g) - 0.5) * _EXTENT
     lab = torch.randint(0, NUM_LABELS, (num_graphs, node_num), generator=g)
     live = (torch.arange(node_num)[None, :] < n_real[:, None])
-    out[:, :3, :] = (xyz * live[:, :, None]).permute(0, 2, 1)
+    out[:, :3, :] = (xyz * live[:, :, None] + 0.0).permute(0, 2, 1)      # + 0.0: pads are +0.0 like np.zeros, never -0.0
     onehot = torch.nn.functional.one_hot(lab, NUM_LABELS).to(torch.float32) * live[:, :, None]
     out[:, 3:, :] = onehot.permute(0, 2, 1)
     return out.contiguous()
