@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsgpr_b200.so")
 SOURCES = ["api.cu"]
-DEPS = ["api.cu", "common.cuh", "embed_kernel.cuh", "head_kernels.cuh", "pack.hpp", "sortnet32.inc"]
+DEPS = ["api.cu", "common.cuh", "embed_kernel.cuh", "head_kernels.cuh", "pack.hpp", "sortnet32.inc", "sortnet16.inc", "sortnet8.inc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
