@@ -229,15 +229,16 @@ __device__ __forceinline__ void select_rows(const float* __restrict__ sY, uint8_
     const int P = NMAX - k;
     const float tl = pick_uniform<EPL>(v, P % EPL);
     const float thr = __shfl_sync(0xffffffffu, tl, rl + (P / EPL) * 8);
-    // ---- count pass over the unsorted values ----
-    int gt_all = 0, gt_e = 0, eq_e = 0;
+    // ---- count pass: per-lane bit masks over its EPL columns ----
+    uint32_t mgt = 0, meq = 0;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
-        const bool g = o[j] > thr, e = o[j] == thr, em = (c0 + j) < R;
-        gt_all += g;
-        gt_e += (g && em);
-        eq_e += (e && em);
+        mgt |= (o[j] > thr) ? (1u << j) : 0u;
+        meq |= (o[j] == thr) ? (1u << j) : 0u;
     }
+    const int ne = min(max(R - c0, 0), EPL);          // emittable columns of this lane (c < R)
+    const uint32_t em = (ne >= 32) ? 0xffffffffu : ((1u << ne) - 1u);
+    const int gt_all = __popc(mgt), gt_e = __popc(mgt & em), eq_e = __popc(meq & em);
     int gts[4], eqs[4], gt_tot = 0;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -258,15 +259,18 @@ __device__ __forceinline__ void select_rows(const float* __restrict__ sY, uint8_
     // ---- emit pass ----
     if (live) {
         uint8_t* list = sIdx + row * KS;
-        int pos = base, eq_left = need - eq_before;
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-            const int c = c0 + j;
-            if (c < R) {
-                const bool tk = (o[j] > thr) || (o[j] == thr && eq_left > 0);
-                if (o[j] == thr) --eq_left;
-                if (tk) { list[pos] = static_cast<uint8_t>(c); ++pos; }
-            }
+        uint32_t ties = meq & em, keep = 0;
+        for (int t = min(max(need - eq_before, 0), eq_e); t > 0; --t) {   // lowest t tied columns (t is 0 or 1 but for pads)
+            const uint32_t low = ties & (0u - ties);
+            keep |= low;
+            ties ^= low;
+        }
+        uint32_t taken = (mgt & em) | keep;
+        int pos = base;
+        while (taken) {
+            const int j = __ffs(taken) - 1;
+            list[pos++] = static_cast<uint8_t>(c0 + j);
+            taken &= taken - 1u;
         }
         // the lane that wrote the last entry pads the list to a multiple of 4 (repeats are harmless under max)
         if (pos == total && pos > base) {
@@ -414,21 +418,21 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
 // xyz layer 1 (3 -> 64) in the reference's direct form (sg_net.py:84-86) for own rows: per edge
 //     e = wa0*d0 + wa1*d1 + wa2*d2  (d = x_j - x_i, sequential FMA), max over the edges, then the centre
 //     terms wb.x_i appended in the same sequential order (monotone in e, so they commute with the max).
-// sIn is the channel-major input block [15][N]; a lane owns output channels 2*lane, 2*lane+1.
+// A lane owns output channels 2*lane, 2*lane+1; neighbour coordinates come from the layer-0 node tile.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void xyz_rows(const float* __restrict__ sIn, const uint8_t* __restrict__ sIdx,
+__device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uint8_t* __restrict__ sIdx,
                                          const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ s1,
                                          float* __restrict__ sDst, float* __restrict__ sXX, float* __restrict__ trace,
-                                         int N, int r0, int r1, int lane) {
+                                         int r0, int r1, int lane) {
+    // sT: the (x, y, z, 0) node tile of layer 0 (stride XS).  p0 = {wa0,wa1,wa2,wb0}, p1 = {wb1,wb2,alpha,beta} of
+    // channel 2*lane; q0/q1 the same for channel 2*lane+1
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane) * 2);
     const float4 p1 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane) * 2 + 1);
     const float4 q0 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane + 1) * 2);
     const float4 q1 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane + 1) * 2 + 1);
-    // p0 = {wa0,wa1,wa2,wb0}, p1 = {wb1,wb2,alpha,beta} of channel 2*lane; q0/q1 the same for 2*lane+1
-    const float2 wa0 = make_float2(p0.x, q0.x), wa1 = make_float2(p0.y, q0.y), wa2 = make_float2(p0.z, q0.z);
 #pragma unroll 1
     for (int i = r0; i < r1; ++i) {
-        const float xi0 = sIn[i], xi1 = sIn[N + i], xi2 = sIn[2 * N + i];
+        const float4 xi = *reinterpret_cast<const float4*>(sT + i * XS);
         float m0 = -INFINITY, m1 = -INFINITY;
         const uint8_t* row = sIdx + i * KS;
         const int cnt = sCnt[i];
@@ -436,21 +440,19 @@ __device__ __forceinline__ void xyz_rows(const float* __restrict__ sIn, const ui
         for (int t = 0; t < cnt; t += 4) {
             const uchar4 jj = *reinterpret_cast<const uchar4*>(row + t);
             const int js[4] = {jj.x, jj.y, jj.z, jj.w};
+            float e0[4], e1[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = js[u];
-                const float d0 = __fsub_rn(sIn[j], xi0);
-                const float d1 = __fsub_rn(sIn[N + j], xi1);
-                const float d2 = __fsub_rn(sIn[2 * N + j], xi2);
-                float2 e = __fmul2_rn(wa0, make_float2(d0, d0));
-                e = ffma2(wa1, make_float2(d1, d1), e);
-                e = ffma2(wa2, make_float2(d2, d2), e);
-                m0 = fmaxf(m0, e.x);
-                m1 = fmaxf(m1, e.y);
+                const float4 xj = *reinterpret_cast<const float4*>(sT + js[u] * XS);
+                const float d0 = __fsub_rn(xj.x, xi.x), d1 = __fsub_rn(xj.y, xi.y), d2 = __fsub_rn(xj.z, xi.z);
+                e0[u] = fmaf(p0.z, d2, fmaf(p0.y, d1, __fmul_rn(p0.x, d0)));
+                e1[u] = fmaf(q0.z, d2, fmaf(q0.y, d1, __fmul_rn(q0.x, d0)));
             }
+            m0 = fmaxf(fmaxf(m0, fmaxf(e0[0], e0[1])), fmaxf(e0[2], e0[3]));
+            m1 = fmaxf(fmaxf(m1, fmaxf(e1[0], e1[1])), fmaxf(e1[2], e1[3]));
         }
-        float y0 = fmaf(p0.w, xi0, m0); y0 = fmaf(p1.x, xi1, y0); y0 = fmaf(p1.y, xi2, y0);
-        float y1 = fmaf(q0.w, xi0, m1); y1 = fmaf(q1.x, xi1, y1); y1 = fmaf(q1.y, xi2, y1);
+        float y0 = fmaf(p0.w, xi.x, m0); y0 = fmaf(p1.x, xi.y, y0); y0 = fmaf(p1.y, xi.z, y0);
+        float y1 = fmaf(q0.w, xi.x, m1); y1 = fmaf(q1.x, xi.y, y1); y1 = fmaf(q1.y, xi.z, y1);
         const float z0 = lrelu(fmaf(y0, p1.z, p1.w));
         const float z1 = lrelu(fmaf(y1, q1.z, q1.w));
         *reinterpret_cast<float2*>(sDst + i * XS + 2 * lane) = make_float2(z0, z1);
@@ -660,7 +662,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
 
             if (l == 0) {
                 // xyz layer 1 gathers from the input block itself (read-only): no barrier needed before it
-                xyz_rows(sIn, sIdx, sCnt, KS, W.s1, sX, sXX, tr, N, w0, w1, lane);
+                xyz_rows(sCat, sIdx, sCnt, KS, W.s1, sX, sXX, tr, w0, w1, lane);
             } else {
                 __syncthreads();                               // barrier B: every A|B row is in place, sW is consumed
                 if (tid == 0 && D.next_w) { mbar_expect_tx(barW, D.next_bytes); bulk_g2s(sW, D.next_w, D.next_bytes, barW); }

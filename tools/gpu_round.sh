@@ -6,7 +6,9 @@ python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pyt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 120 ./tools/microbench_ffma > gpurun_out/microbench.json 2>&1
 timeout 600 python bench.py --steps 400 --warmup 20 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 300 python tools/perf_probe.py > gpurun_out/perf_probe.jsonl 2>&1
 timeout 400 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer.log 2>&1; echo "sanitizer rc=$?" >> gpurun_out/sanitizer.log
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgpr_embed -s 5 -c 2 -f -o gpurun_out/prof_embed python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/microbench.json; head -c 1500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err; tail -3 gpurun_out/sanitizer.log
+cat gpurun_out/perf_probe.jsonl
