@@ -345,6 +345,13 @@ int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const 
 
 int64_t sgpr_launch_count(const sgpr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+#ifdef SGPR_TIMELINE
+// debug builds only (not declared in the public header): copy CTA 0's clock stamps, [8 warps][128 slots]
+int sgpr_debug_timeline(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_timeline, sizeof(long long) * kWarps * 128) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 size_t sgpr_packed_size(void) { return make_offsets().total; }
 
 int sgpr_pack_weights_host(const sgpr_weights* w, float* blob, float* head289, size_t* offsets17) {

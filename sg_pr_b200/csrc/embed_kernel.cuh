@@ -38,6 +38,14 @@
 
 namespace sgpr {
 
+// Optional per-phase clock stamps of CTA 0 (debug builds only: -DSGPR_TIMELINE); see tools/timeline.py.
+#ifdef SGPR_TIMELINE
+__device__ long long g_timeline[kWarps * 128];
+#define SGPR_TL(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_timeline[(threadIdx.x >> 5) * 128 + (slot)] = clock64(); } while (0)
+#else
+#define SGPR_TL(slot) do { } while (0)
+#endif
+
 struct EmbedArgs {
     const float* g0;        // graphs of side 0 (or all graphs when !pairs)   [*, 15, N]
     const float* g1;        // graphs of side 1 (pairs mode)
@@ -543,8 +551,10 @@ __device__ __forceinline__ void front_pass(const FrontCtx& F, int r0, int nr, in
                                            bool& waited) {
     SGPR_NR_SWITCH(nr, (gram_rows<NPL, NR>(F.sXt, F.sXX, F.sY, F.c4n, F.R, r0, lane)))
     __syncwarp();
+    SGPR_TL(8 + F.layer * 8 + 1);
     select_rows<NPL>(F.sY, F.sIdx, F.sCnt, F.trace_knn, F.R, F.N, F.k, F.KS, r0, nr, lane);
     __syncwarp();                                      // the distance rows are dead; A|B may overwrite them
+    SGPR_TL(8 + F.layer * 8 + 2);
     if (F.layer != 0) {
         if (!waited) { mbar_wait(barW, phW); phW ^= 1; waited = true; }
         if (F.cout == 64) { SGPR_NR_SWITCH(nr, (gemm_rows<NR, 4, 0>(F.sXt, F.sW, F.sY, YS, nullptr, F.c4n, r0, lane))) }
@@ -605,6 +615,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         uint8_t* tk = A.trace_knn ? A.trace_knn + static_cast<size_t>(g) * 6 * N * k : nullptr;
         float* tl = A.trace_layers ? A.trace_layers + static_cast<size_t>(g) * 6 * N * 64 : nullptr;
 
+        SGPR_TL(0);
         // ---- stage the input block and the first GEMM's weights (TMA bulk copies, mbarrier completion) ----
         if (tid == 0) {
             if (bulk_ok) { mbar_expect_tx(barIn, inBytes); bulk_g2s(sIn, gin, inBytes, barIn); }
@@ -614,6 +625,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         if (bulk_ok) { mbar_wait(barIn, phIn); phIn ^= 1; }
         else { for (int e = tid; e < kInCh * N; e += kThreads) sIn[e] = __ldg(gin + e); __syncthreads(); }
 
+        SGPR_TL(1);
         // ---- layer-0 tile (x, y, z, 0) + squared norms for every node, and the last non-zero node ----
         int last = -1;
         for (int n = tid; n < N; n += kThreads) {
@@ -657,7 +669,9 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             // ---- front: distance rows -> selection -> (GEMM rows) for own rows, no CTA barrier ----
             FrontCtx F{(l == 0) ? sCat : sX, (l == 0) ? sXX0 : sXX, sY, sW, sIdx, sCnt, tkl, D.cin4, D.cout, R, N, k, KS, l};
             bool waited = false;
+            SGPR_TL(8 + l * 8 + 0);
             for (int r0 = w0; r0 < w1; r0 += 8) front_pass<NPL>(F, r0, min(8, w1 - r0), lane, barW, phW, waited);
+            SGPR_TL(8 + l * 8 + 3);
             if (l != 0 && !waited) { mbar_wait(barW, phW); phW ^= 1; }       // warps without rows still track the phase
 
             if (l == 0) {
@@ -665,6 +679,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
                 xyz_rows(sCat, sIdx, sCnt, KS, W.s1, sX, sXX, tr, w0, w1, lane);
             } else {
                 __syncthreads();                               // barrier B: every A|B row is in place, sW is consumed
+                SGPR_TL(8 + l * 8 + 4);
                 if (tid == 0 && D.next_w) { mbar_expect_tx(barW, D.next_bytes); bulk_g2s(sW, D.next_w, D.next_bytes, barW); }
                 // ---- back: gather-max for own rows ----
                 if (D.cout == 64) {
@@ -685,13 +700,16 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
                     }
                 }
             }
+            SGPR_TL(8 + l * 8 + 5);
             __syncthreads();                                   // barrier A: the next layer's input (or sE) is complete
+            SGPR_TL(8 + l * 8 + 6);
             if (tr || tkl) {                                   // debug taps: every trailing pad is a copy of row R-1
                 if (tr) for (int e = tid; e < (N - R) * 64; e += kThreads) tr[(R + e / 64) * 64 + (e & 63)] = tr[(R - 1) * 64 + (e & 63)];
                 if (tkl) for (int e = tid; e < (N - R) * k; e += kThreads) tkl[(R + e / k) * k + (e % k)] = tkl[(R - 1) * k + (e % k)];
             }
         }
 
+        SGPR_TL(58);
         float* sE = sX;   // node embeddings, stride XS (first 32 columns)
         // every trailing pad is a copy of row R-1
         for (int e = tid; e < (N - R) * kF3; e += kThreads) sE[(R + (e >> 5)) * XS + (e & 31)] = sE[(R - 1) * XS + (e & 31)];
@@ -750,6 +768,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             A.pooled[static_cast<size_t>(g) * kF3 + tid] = s;
         }
 
+        SGPR_TL(60);
         // ================= pair head, run by whichever CTA of the pair finishes last =================
         if (A.pairs) {
             __threadfence();
@@ -771,6 +790,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             }
         }
         __syncthreads();
+        SGPR_TL(62);
     }
 }
 

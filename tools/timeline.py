@@ -1,0 +1,31 @@
+"""Per-phase clock stamps of CTA 0 from a -DSGPR_TIMELINE build (tools/variants/lib_timeline.so)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import sgpr_oracle as orc
+from sg_pr_b200 import synth, _lib
+from sg_pr_b200.engine import Engine
+sd = orc.load_state_npz("tests/golden/model_kitti.npz")
+eng = Engine(0); eng.set_weights(sd)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+f1, f2 = synth.make_pair_batch(B, 64, 20, seed=1)
+f1, f2 = f1.cuda(), f2.cuda()
+for _ in range(3): eng.forward_pairs(f1, f2, 20)
+torch.cuda.synchronize()
+lib = _lib.load()
+buf = np.zeros(8 * 128, dtype=np.int64)
+lib.sgpr_debug_timeline.argtypes = [ctypes.c_void_p]
+assert lib.sgpr_debug_timeline(buf.ctypes.data) == 0
+t = buf.reshape(8, 128)
+t0 = t[:, 0].min()
+names = {0: "start", 1: "input landed", 58: "layers done", 60: "attention done", 62: "end"}
+for l in range(6):
+    for j, nm in enumerate(["front start", "gram done", "select done", "front done", "barrier B", "back done", "barrier A"]):
+        names[8 + l * 8 + j] = f"L{l} {nm}"
+print("n_real side0 graph0:", int((f1[0, 3:].sum(0) > 0).sum()))
+print(f"{'slot':18s}" + "".join(f"   w{w}" .rjust(9) for w in range(8)))
+prev = None
+for slot in sorted(names):
+    row = t[:, slot] - t0
+    if (t[:, slot] == 0).all(): continue
+    print(f"{names[slot]:18s}" + "".join(f"{int(v):9d}" for v in row))
