@@ -141,22 +141,34 @@ __device__ __forceinline__ void gram_rows(const float* __restrict__ sXt, const f
         for (int q = 0; q < NPL; ++q) acc[r][q] = make_float2(0.0f, 0.0f);
     const float* pa = sXt + r0 * XS;
     const float* pb = sXt + lane * XS;
+    // software pipeline: the loads of channel group c+1 are in flight while the FFMA2s of group c issue
+    float4 a[NR], b[NPL];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) a[r] = *reinterpret_cast<const float4*>(pa + r * XS);
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) b[q] = (q < nq) ? *reinterpret_cast<const float4*>(pb + 32 * q * XS) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
     for (int c = 0; c < c4n; ++c) {
-        float4 a[NR];
+        float4 an[NR], bn[NPL];
+        const int cn = min(c + 1, c4n - 1);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a[r] = *reinterpret_cast<const float4*>(pa + r * XS + 4 * c);
+        for (int r = 0; r < NR; ++r) an[r] = *reinterpret_cast<const float4*>(pa + r * XS + 4 * cn);
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) bn[q] = (q < nq) ? *reinterpret_cast<const float4*>(pb + 32 * q * XS + 4 * cn) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < NPL; ++q) {
             if (q < nq) {
-                const float4 b = *reinterpret_cast<const float4*>(pb + 32 * q * XS + 4 * c);
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
-                    acc[r][q] = ffma2(make_float2(a[r].x, a[r].y), make_float2(b.x, b.y), acc[r][q]);
-                    acc[r][q] = ffma2(make_float2(a[r].z, a[r].w), make_float2(b.z, b.w), acc[r][q]);
+                    acc[r][q] = ffma2(make_float2(a[r].x, a[r].y), make_float2(b[q].x, b[q].y), acc[r][q]);
+                    acc[r][q] = ffma2(make_float2(a[r].z, a[r].w), make_float2(b[q].z, b[q].w), acc[r][q]);
                 }
             }
         }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a[r] = an[r];
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) b[q] = bn[q];
     }
 #pragma unroll
     for (int q = 0; q < NPL; ++q) {
@@ -317,33 +329,39 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ sXin, const 
 #pragma unroll
         for (int j = 0; j < CPL; ++j) acc[n][j] = make_float2(0.0f, 0.0f);
     const float* px = sXin + r0 * XS;
+    auto load_w = [&](float2 (&w)[CPL], int p) {
+        const float* wp = sW + p * ROW;
+        if constexpr (CPL == 4) {
+            const float4 t0 = *reinterpret_cast<const float4*>(wp + lane * 4);
+            const float4 t1 = *reinterpret_cast<const float4*>(wp + 128 + lane * 4);
+            w[0] = make_float2(t0.x, t0.y); w[1] = make_float2(t0.z, t0.w);
+            w[2] = make_float2(t1.x, t1.y); w[3] = make_float2(t1.z, t1.w);
+        } else if constexpr (CPL == 2) {
+            const float4 t0 = *reinterpret_cast<const float4*>(wp + lane * 4);
+            w[0] = make_float2(t0.x, t0.y); w[1] = make_float2(t0.z, t0.w);
+        } else {
+            w[0] = *reinterpret_cast<const float2*>(wp + lane * 2);
+        }
+    };
+    // software pipeline over channel pairs: the weights of pair p+1 load while the FFMA2s of pair p issue
+    const int npairs = 2 * cin4;
+    float2 w0[CPL], w1[CPL];
+    load_w(w0, 0);
 #pragma unroll 2
     for (int c4 = 0; c4 < cin4; ++c4) {
         float4 x[NR];
 #pragma unroll
         for (int n = 0; n < NR; ++n) x[n] = *reinterpret_cast<const float4*>(px + n * XS + 4 * c4);
+        load_w(w1, 2 * c4 + 1);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {            // channel pair 2*c4 + h
-            float2 w[CPL];
-            const float* wp = sW + (2 * c4 + h) * ROW;
-            if constexpr (CPL == 4) {
-                const float4 t0 = *reinterpret_cast<const float4*>(wp + lane * 4);
-                const float4 t1 = *reinterpret_cast<const float4*>(wp + 128 + lane * 4);
-                w[0] = make_float2(t0.x, t0.y); w[1] = make_float2(t0.z, t0.w);
-                w[2] = make_float2(t1.x, t1.y); w[3] = make_float2(t1.z, t1.w);
-            } else if constexpr (CPL == 2) {
-                const float4 t0 = *reinterpret_cast<const float4*>(wp + lane * 4);
-                w[0] = make_float2(t0.x, t0.y); w[1] = make_float2(t0.z, t0.w);
-            } else {
-                w[0] = *reinterpret_cast<const float2*>(wp + lane * 2);
-            }
+        for (int n = 0; n < NR; ++n)
 #pragma unroll
-            for (int n = 0; n < NR; ++n) {
-                const float2 xv = h ? make_float2(x[n].z, x[n].w) : make_float2(x[n].x, x[n].y);
+            for (int j = 0; j < CPL; ++j) acc[n][j] = ffma2(make_float2(x[n].x, x[n].y), w0[j], acc[n][j]);
+        load_w(w0, min(2 * c4 + 2, npairs - 1));
 #pragma unroll
-                for (int j = 0; j < CPL; ++j) acc[n][j] = ffma2(xv, w[j], acc[n][j]);
-            }
-        }
+        for (int n = 0; n < NR; ++n)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) acc[n][j] = ffma2(make_float2(x[n].z, x[n].w), w1[j], acc[n][j]);
     }
     float al[CPL], be[CPL];
     if constexpr (EPI == 1) {
@@ -365,17 +383,38 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ sXin, const 
     }
 }
 
+// squared norms (dgcnn.py:16 term of the next layer) of up to 8 own rows: 4 lanes per row, each sums a quarter of the
+// channels in order, partials combined pairwise.  Call under __syncwarp after the rows were written by this warp.
+__device__ __forceinline__ void norms_rows(const float* __restrict__ sT, float* __restrict__ sXX, int c4n, int r0, int r1,
+                                           int lane) {
+    const int part = lane >> 3, rl = lane & 7;
+    const int per = (c4n + 3) >> 2;
+    for (int b0 = r0; b0 < r1; b0 += 8) {
+        const int row = min(b0 + rl, r1 - 1);
+        float s = 0.0f;
+        for (int g = part * per; g < min(c4n, (part + 1) * per); ++g) {
+            const float4 x = *reinterpret_cast<const float4*>(sT + row * XS + 4 * g);
+            s = __fadd_rn(s, __fmul_rn(x.x, x.x));
+            s = __fadd_rn(s, __fmul_rn(x.y, x.y));
+            s = __fadd_rn(s, __fmul_rn(x.z, x.z));
+            s = __fadd_rn(s, __fmul_rn(x.w, x.w));
+        }
+        s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 8));
+        s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 16));
+        if (part == 0 && b0 + rl < r1) sXX[b0 + rl] = s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Gather-max + BN + LeakyReLU for own rows (sg_net.py:85-86 etc.): for node i and channel c
 //     out = LReLU(alpha_c * ((max_{j in knn(i)} A[j][c] - A[i][c]) + B[i][c]) + beta_c)
-// sY row = [A(0..COUT) | B(COUT..2COUT)]; a lane owns COUT/32 channels.  With XXOUT the squared norm of the new
-// feature row (the next layer's dgcnn.py:16 term) is reduced across the warp and stored.
+// sY row = [A(0..COUT) | B(COUT..2COUT)]; a lane owns COUT/32 channels.  Neighbour rows are fetched 12 at a time
+// (three packed index words, then twelve independent loads) to keep the shared-memory pipe busy.
 // ------------------------------------------------------------------------------------------------------------
-template <int COUT, bool XXOUT>
+template <int COUT>
 __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const uint8_t* __restrict__ sIdx,
                                             const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ ab,
-                                            float* __restrict__ sDst, float* __restrict__ sXX, float* __restrict__ trace,
-                                            int r0, int r1, int lane) {
+                                            float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane) {
     constexpr int CPL = COUT / 32;
     float al[CPL], be[CPL];
 #pragma unroll
@@ -386,38 +425,41 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
         float m[CPL];
 #pragma unroll
         for (int p = 0; p < CPL; ++p) m[p] = -INFINITY;
-        const uint8_t* row = sIdx + i * KS;
-        const int cnt = sCnt[i];
-#pragma unroll 2
-        for (int t = 0; t < cnt; t += 4) {
-            const uchar4 jj = *reinterpret_cast<const uchar4*>(row + t);
-            if constexpr (CPL == 2) {
-                const float2 a0 = *reinterpret_cast<const float2*>(base + jj.x * YS);
-                const float2 a1 = *reinterpret_cast<const float2*>(base + jj.y * YS);
-                const float2 a2 = *reinterpret_cast<const float2*>(base + jj.z * YS);
-                const float2 a3 = *reinterpret_cast<const float2*>(base + jj.w * YS);
-                m[0] = fmaxf(fmaxf(m[0], fmaxf(a0.x, a1.x)), fmaxf(a2.x, a3.x));
-                m[1] = fmaxf(fmaxf(m[1], fmaxf(a0.y, a1.y)), fmaxf(a2.y, a3.y));
-            } else {
-                const float a0 = base[jj.x * YS], a1 = base[jj.y * YS];
-                const float a2 = base[jj.z * YS], a3 = base[jj.w * YS];
-                m[0] = fmaxf(fmaxf(m[0], fmaxf(a0, a1)), fmaxf(a2, a3));
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(sIdx + i * KS);
+        const int nw = sCnt[i] >> 2;                    // packed index words (4 neighbours each), >= 1
+        float ai[CPL], bi[CPL];
+#pragma unroll
+        for (int p = 0; p < CPL; ++p) { ai[p] = base[i * YS + p]; bi[p] = base[i * YS + COUT + p]; }
+#pragma unroll 1
+        for (int t = 0; t < nw; t += 3) {
+            uint32_t wd[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) wd[q] = row[min(t + q, nw - 1)];       // tail words repeat (harmless under max)
+            float v[12][CPL];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const int j = (wd[e >> 2] >> (8 * (e & 3))) & 0xff;
+                if constexpr (CPL == 2) {
+                    const float2 a = *reinterpret_cast<const float2*>(base + j * YS);
+                    v[e][0] = a.x; v[e][1] = a.y;
+                } else {
+                    v[e][0] = base[j * YS];
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < CPL; ++p) {
+                const float m0 = fmaxf(fmaxf(v[0][p], v[1][p]), fmaxf(v[2][p], v[3][p]));
+                const float m1 = fmaxf(fmaxf(v[4][p], v[5][p]), fmaxf(v[6][p], v[7][p]));
+                const float m2 = fmaxf(fmaxf(v[8][p], v[9][p]), fmaxf(v[10][p], v[11][p]));
+                m[p] = fmaxf(fmaxf(m[p], m0), fmaxf(m1, m2));
             }
         }
-        float ss = 0.0f;
 #pragma unroll
         for (int p = 0; p < CPL; ++p) {
-            const float ai = base[i * YS + p];
-            const float bi = base[i * YS + COUT + p];
-            const float y = __fadd_rn(__fsub_rn(m[p], ai), bi);
+            const float y = __fadd_rn(__fsub_rn(m[p], ai[p]), bi[p]);
             const float z = lrelu(fmaf(y, al[p], be[p]));
             sDst[i * XS + lane * CPL + p] = z;
             if (trace) trace[i * 64 + lane * CPL + p] = z;
-            ss = __fadd_rn(ss, __fmul_rn(z, z));
-        }
-        if constexpr (XXOUT) {
-            ss = warp_sum(ss);
-            if (lane == 0) sXX[i] = ss;
         }
     }
 }
@@ -430,8 +472,7 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uint8_t* __restrict__ sIdx,
                                          const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ s1,
-                                         float* __restrict__ sDst, float* __restrict__ sXX, float* __restrict__ trace,
-                                         int r0, int r1, int lane) {
+                                         float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane) {
     // sT: the (x, y, z, 0) node tile of layer 0 (stride XS).  p0 = {wa0,wa1,wa2,wb0}, p1 = {wb1,wb2,alpha,beta} of
     // channel 2*lane; q0/q1 the same for channel 2*lane+1
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane) * 2);
@@ -465,8 +506,6 @@ __device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uin
         const float z1 = lrelu(fmaf(y1, q1.z, q1.w));
         *reinterpret_cast<float2*>(sDst + i * XS + 2 * lane) = make_float2(z0, z1);
         if (trace) { trace[i * 64 + 2 * lane] = z0; trace[i * 64 + 2 * lane + 1] = z1; }
-        const float ss = warp_sum(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)));
-        if (lane == 0) sXX[i] = ss;
     }
 }
 
@@ -676,23 +715,25 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
 
             if (l == 0) {
                 // xyz layer 1 gathers from the input block itself (read-only): no barrier needed before it
-                xyz_rows(sCat, sIdx, sCnt, KS, W.s1, sX, sXX, tr, w0, w1, lane);
+                xyz_rows(sCat, sIdx, sCnt, KS, W.s1, sX, tr, w0, w1, lane);
+                __syncwarp();
+                norms_rows(sX, sXX, 16, w0, w1, lane);
             } else {
                 __syncthreads();                               // barrier B: every A|B row is in place, sW is consumed
                 SGPR_TL(8 + l * 8 + 4);
                 if (tid == 0 && D.next_w) { mbar_expect_tx(barW, D.next_bytes); bulk_g2s(sW, D.next_w, D.next_bytes, barW); }
                 // ---- back: gather-max for own rows ----
                 if (D.cout == 64) {
-                    gather_rows<64, true>(sY, sIdx, sCnt, KS, D.ab, sX, sXX, tr, w0, w1, lane);
+                    gather_rows<64>(sY, sIdx, sCnt, KS, D.ab, sX, tr, w0, w1, lane);
+                    __syncwarp();
+                    norms_rows(sX, sXX, 16, w0, w1, lane);
                 } else {
-                    gather_rows<32, false>(sY, sIdx, sCnt, KS, D.ab, (l == 2) ? sCat : sCat + 32, nullptr, tr, w0, w1, lane);
+                    gather_rows<32>(sY, sIdx, sCnt, KS, D.ab, (l == 2) ? sCat : sCat + 32, tr, w0, w1, lane);
                     if (l == 2) {   // stage the semantic branch input: rows [n][0..11] from input rows 3..14 (sg_net.py:82,94)
-                        for (int i = w0; i < w1; ++i) {
-                            const float x = (lane < kLabels) ? sIn[(3 + lane) * N + i] : 0.0f;
-                            if (lane < 16) sX[i * XS + lane] = x;
-                            const float ss = warp_sum(__fmul_rn(x, x));
-                            if (lane == 0) sXX[i] = ss;
-                        }
+                        for (int i = w0; i < w1; ++i)
+                            if (lane < 16) sX[i * XS + lane] = (lane < kLabels) ? sIn[(3 + lane) * N + i] : 0.0f;
+                        __syncwarp();
+                        norms_rows(sX, sXX, 3, w0, w1, lane);
                     } else {        // l == 5: conv_end on own rows (sg_net.py:104-109): cat(xyz3, sem3) [.,64] -> [.,32]
                         __syncwarp();
                         for (int r0 = w0; r0 < w1; r0 += 8)
@@ -720,27 +761,30 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         }
 
         // ================= attention pooling over all N nodes (layers_batch.py:28-39) =================
-        // ctx[b] = tanh(mean_n sum_a E[n][a] Watt[a][b]): lane = b, warp strides over nodes
-        {
+        // warp w handles nodes w, w+8, ...; lane = feature index
+        float* sCtx = sRed + kWarps * 32;        // [32]
+        float* sPool = sRed + kWarps * 32 + 32;  // [32]
+        {   // ctx[b] = tanh(mean_n sum_a E[n][a] Watt[a][b])
+            float wcol[kF3];
+#pragma unroll
+            for (int a = 0; a < kF3; ++a) wcol[a] = __ldg(W.att_w + a * kF3 + lane);
             float colsum = 0.0f;
-#pragma unroll 1
+#pragma unroll 2
             for (int n = warp; n < N; n += kWarps) {
                 float t = 0.0f;
-#pragma unroll 4
+#pragma unroll
                 for (int a4 = 0; a4 < kF3 / 4; ++a4) {
                     const float4 e = *reinterpret_cast<const float4*>(sE + n * XS + 4 * a4);
-                    t = fmaf(e.x, __ldg(W.att_w + (4 * a4 + 0) * kF3 + lane), t);
-                    t = fmaf(e.y, __ldg(W.att_w + (4 * a4 + 1) * kF3 + lane), t);
-                    t = fmaf(e.z, __ldg(W.att_w + (4 * a4 + 2) * kF3 + lane), t);
-                    t = fmaf(e.w, __ldg(W.att_w + (4 * a4 + 3) * kF3 + lane), t);
+                    t = fmaf(e.x, wcol[4 * a4 + 0], t);
+                    t = fmaf(e.y, wcol[4 * a4 + 1], t);
+                    t = fmaf(e.z, wcol[4 * a4 + 2], t);
+                    t = fmaf(e.w, wcol[4 * a4 + 3], t);
                 }
                 colsum = __fadd_rn(colsum, t);
             }
             sRed[warp * 32 + lane] = colsum;
         }
         __syncthreads();
-        float* sCtx = sRed + kWarps * 32;        // [32]
-        float* sPool = sRed + kWarps * 32 + 32;  // [32]
         if (tid < kF3) {
             float s = 0.0f;
 #pragma unroll
@@ -748,22 +792,40 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             sCtx[tid] = tanhf(s / static_cast<float>(N));
         }
         __syncthreads();
-        // att[n] = sigmoid(E[n] . ctx)
-        float* sAtt = sXX;
-        for (int n = tid; n < N; n += kThreads) {
-            float s = 0.0f;
-#pragma unroll 8
-            for (int b = 0; b < kF3; ++b) s = fmaf(sE[n * XS + b], sCtx[b], s);
-            const float a = sigmoidf_acc(s);
-            sAtt[n] = a;
+        {   // att[n] = sigmoid(E[n] . ctx); pooled[a] = sum_n E[n][a] att[n]   (per-warp partials, then 8-way sum)
+            const float cb = sCtx[lane];
             float* ao = A.pairs ? ((g & 1) ? A.att1 : A.att0) : A.att0;
-            if (ao) ao[static_cast<size_t>(A.pairs ? (g >> 1) : g) * N + n] = a;
+            if (ao) ao += static_cast<size_t>(A.pairs ? (g >> 1) : g) * N;
+            float pool = 0.0f;
+            for (int n0 = warp; n0 < N; n0 += 8 * kWarps) {          // up to 8 nodes of this warp at a time
+                float e[8], d[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int n = n0 + u * kWarps;
+                    e[u] = (n < N) ? sE[n * XS + lane] : 0.0f;
+                    d[u] = __fmul_rn(e[u], cb);
+                }
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) d[u] = __fadd_rn(d[u], __shfl_xor_sync(0xffffffffu, d[u], sft));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int n = n0 + u * kWarps;
+                    if (n < N) {
+                        const float a = sigmoidf_acc(d[u]);
+                        if (ao && lane == 0) ao[n] = a;
+                        pool = fmaf(e[u], a, pool);
+                    }
+                }
+            }
+            sRed[warp * 32 + lane] = pool;
         }
         __syncthreads();
-        // pooled[a] = sum_n E[n][a] att[n]
         if (tid < kF3) {
             float s = 0.0f;
-            for (int n = 0; n < N; ++n) s = fmaf(sE[n * XS + tid], sAtt[n], s);
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s = __fadd_rn(s, sRed[w * 32 + tid]);
             sPool[tid] = s;
             A.pooled[static_cast<size_t>(g) * kF3 + tid] = s;
         }
