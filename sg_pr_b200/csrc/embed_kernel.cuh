@@ -515,38 +515,59 @@ __device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uin
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_acc(float z) { return 1.0f / (1.0f + expf(-z)); }
 
+__device__ __forceinline__ float group16_sum(float v) {       // sum over the 16 lanes of a half-warp (tree order)
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
 __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, const float* __restrict__ e2,
                                               const PackedWeights& W, const HeadParams& H, float* __restrict__ scratch,
                                               float* __restrict__ score_out, int tid) {
     float* P = scratch;          // [512]  P[b*16+t] = sum_a e1[a] * W[a][b*16+t]   (layers_batch.py:78)
     float* s = scratch + 512;    // [16]
-    float* h = scratch + 528;    // [16]
-    for (int c = tid; c < 512; c += kThreads) {
-        float acc = 0.0f;
-#pragma unroll 8
-        for (int a = 0; a < kF3; ++a) acc = fmaf(e1[a], __ldg(W.ntn_w + a * 512 + c), acc);
-        P[c] = acc;
+    // all 64 weight loads of a thread's two outputs are issued before the first FMA: one L2 round trip, not eight
+    {
+        float w0[kF3], w1[kF3];
+#pragma unroll
+        for (int a = 0; a < kF3; ++a) {
+            w0[a] = __ldg(W.ntn_w + a * 512 + tid);
+            w1[a] = __ldg(W.ntn_w + a * 512 + 256 + tid);
+        }
+        float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+        for (int a = 0; a < kF3; ++a) { acc0 = fmaf(e1[a], w0[a], acc0); acc1 = fmaf(e1[a], w1[a], acc1); }
+        P[tid] = acc0;
+        P[256 + tid] = acc1;
     }
     __syncthreads();
-    if (tid < kT) {
-        float acc = 0.0f;
-        for (int b = 0; b < kF3; ++b) acc = fmaf(P[b * kT + tid], e2[b], acc);      // layers_batch.py:79
-        float blk = 0.0f;
-        for (int c = 0; c < kF3; ++c) blk = fmaf(__ldg(W.ntn_v + tid * 64 + c), e1[c], blk);          // :80-81
-        for (int c = 0; c < kF3; ++c) blk = fmaf(__ldg(W.ntn_v + tid * 64 + 32 + c), e2[c], blk);
-        s[tid] = fmaxf(__fadd_rn(__fadd_rn(acc, blk), __ldg(W.ntn_b + tid)), 0.0f);                 // :82
+    // thread (t, part): t = tid / 16 is the NTN neuron, part = tid % 16 a slice of the contraction
+    const int t = tid >> 4, part = tid & 15;
+    {
+        float bil = fmaf(P[(2 * part + 1) * kT + t], e2[2 * part + 1], __fmul_rn(P[(2 * part) * kT + t], e2[2 * part]));   // :79
+        float blk = 0.0f;                                                                                                 // :80-81
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = part * 4 + q;
+            blk = fmaf(__ldg(W.ntn_v + t * 64 + c), (c < kF3) ? e1[c] : e2[c - kF3], blk);
+        }
+        bil = group16_sum(bil);
+        blk = group16_sum(blk);
+        if (part == 0) s[t] = fmaxf(__fadd_rn(__fadd_rn(bil, blk), __ldg(W.ntn_b + t)), 0.0f);                            // :82
     }
     __syncthreads();
-    if (tid < kBn) {
-        float acc = 0.0f;
-        for (int t = 0; t < kT; ++t) acc = fmaf(s[t], H.fc1_w[tid * kT + t], acc);                   // sg_net.py:134
-        h[tid] = fmaxf(__fadd_rn(acc, H.fc1_b[tid]), 0.0f);
+    {
+        // h[u] = relu(fc1_w[u] . s + fc1_b[u]) with (u, part) = (t, part); then score = sigmoid(fc2_w . h + fc2_b)
+        float h = group16_sum(__fmul_rn(s[part], H.fc1_w[t * kT + part]));                                                // sg_net.py:134
+        h = fmaxf(__fadd_rn(h, H.fc1_b[t]), 0.0f);
+        // one value per half-warp -> collect the 16 h's in warp 0 via shared memory
+        if (part == 0) P[t] = __fmul_rn(h, H.fc2_w[t]);
     }
     __syncthreads();
-    if (tid == 0) {
-        float acc = 0.0f;
-        for (int u = 0; u < kBn; ++u) acc = fmaf(h[u], H.fc2_w[u], acc);                             // sg_net.py:136
-        *score_out = sigmoidf_acc(__fadd_rn(acc, H.fc2_b));
+    if (tid < 32) {
+        float z = (tid < kBn) ? P[tid] : 0.0f;                                                                          // sg_net.py:136
+        z = group16_sum(z);
+        if (tid == 0) *score_out = sigmoidf_acc(__fadd_rn(z, H.fc2_b));
     }
 }
 

@@ -55,3 +55,38 @@ eva_pair:
   pair_file: ["{root}/data/0.json", "{root}/data/250.json"]
 """)
     return cfg
+
+
+NEAR_TIE_REL = 2e-6     # a k-th / (k+1)-th reference distance closer than this (relative) is decided by sgemm rounding
+
+
+def near_tie_flips(eng, state, graphs, k):
+    """k-NN rows where the kernel and the oracle pick different (non-equivalent) sets, with the relative gap of the
+    reference distances at the k-th boundary: [(graph, layer, row, rel_gap)].  SURVEY §7 hard part 2: such a row
+    flips with the last bit of the Gram matrix — in the reference too (MKL vs cuBLAS vs fp64 disagree on them) —
+    and moves the score by up to ~1e-2; it is classified, not hidden."""
+    from oracle import sgpr_oracle as orc
+    want = orc.embed_graphs(graphs, k, state, want_trace=True)
+    got = eng.embed(graphs.cuda(), k, trace=True)
+    knn = got["knn"].cpu().long()
+    out = []
+    for layer in range(6):
+        ok = orc.knn_sets_equivalent(want["knn_pd"][layer], want["knn_idx"][layer], knn[:, layer], want["layer_in"][layer])
+        for b, i in (~ok).nonzero().tolist():
+            srt = want["knn_pd"][layer][b, i].sort(descending=True)[0]
+            out.append((b, layer, i, float((srt[k - 1] - srt[k]).abs() / srt[k - 1].abs().clamp_min(1e-30))))
+    return out
+
+
+def assert_scores_match_or_near_tie(eng, state, f1, f2, k, got, want, tol=1e-5, max_bad=2):
+    """Every score within tol of the oracle, except (at most max_bad) pairs whose deviation is explained row by row by
+    k-NN near-ties (reference gap < NEAR_TIE_REL).  Returns the indices of the explained pairs."""
+    import torch
+    err = (got.detach().cpu() - want).abs()
+    bad = (err > tol).nonzero().flatten().tolist()
+    assert len(bad) <= max_bad, f"{len(bad)} of {len(err)} pairs off by more than {tol}: {bad}"
+    for p in bad:
+        flips = near_tie_flips(eng, state, torch.stack([f1[p], f2[p]]).cpu(), k)
+        assert flips and all(gap < NEAR_TIE_REL for *_, gap in flips), \
+            f"pair {p}: |dscore| {float(err[p]):.3g} not explained by a k-NN near-tie: {flips}"
+    return bad

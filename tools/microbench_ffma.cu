@@ -51,6 +51,20 @@ __global__ void k_shfl(float* out) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+__global__ void k_fmnmx(float* out, float a) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 0.001f + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fminf(fmaxf(acc[i], a), acc[(i + 1) & 15] + 1.0f);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 float time_ms(F f) {
     cudaEvent_t e0, e1;
@@ -71,6 +85,8 @@ int main() {
     float t1 = time_ms([&] { k_ffma<<<blocks, threads>>>(out, 1.0001f, 0.5f); });
     float t2 = time_ms([&] { k_ffma2<<<blocks, threads>>>(out, 1.0001f, 0.5f); });
     float t3 = time_ms([&] { k_shfl<<<blocks, threads>>>(out); });
+    float t4 = time_ms([&] { k_fmnmx<<<blocks, threads>>>(out, 0.5f); });
+    printf("{\"fmnmx_fadd_triplets_per_clk_per_sm\": %.2f}\n", n / t4 / 1e6 / p.multiProcessorCount / (p.clockRate / 1e3) * 1e3 / 1e3);
     printf("{\"device\": \"%s\", \"sms\": %d, \"ffma_tflops\": %.2f, \"ffma2_tflops\": %.2f, \"ffma_ms\": %.4f, \"ffma2_ms\": %.4f, "
            "\"shfl_minmax_gops\": %.1f}\n",
            p.name, p.multiProcessorCount, 2 * n / t1 / 1e9, 2 * n / t2 / 1e9, t1, t2,
