@@ -87,6 +87,15 @@ def assert_scores_match_or_near_tie(eng, state, f1, f2, k, got, want, tol=1e-5, 
     assert len(bad) <= max_bad, f"{len(bad)} of {len(err)} pairs off by more than {tol}: {bad}"
     for p in bad:
         flips = near_tie_flips(eng, state, torch.stack([f1[p], f2[p]]).cpu(), k)
-        assert flips and all(gap < NEAR_TIE_REL for *_, gap in flips), \
+        # only the FIRST divergence of each graph/branch has to be a near-tie: once one neighbour set differs, the
+        # features of the later layers of that branch (xyz = layers 0-2, sem = 3-5) legitimately differ too
+        first = {}
+        for b, layer, row, gap in flips:
+            key = (b, layer // 3)
+            if key not in first or layer < first[key][0]:
+                first[key] = (layer, [])
+            if layer == first[key][0]:
+                first[key][1].append(gap)
+        assert first and all(g < NEAR_TIE_REL for _, gaps in first.values() for g in gaps), \
             f"pair {p}: |dscore| {float(err[p]):.3g} not explained by a k-NN near-tie: {flips}"
     return bad

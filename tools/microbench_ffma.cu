@@ -86,7 +86,7 @@ int main() {
     float t2 = time_ms([&] { k_ffma2<<<blocks, threads>>>(out, 1.0001f, 0.5f); });
     float t3 = time_ms([&] { k_shfl<<<blocks, threads>>>(out); });
     float t4 = time_ms([&] { k_fmnmx<<<blocks, threads>>>(out, 0.5f); });
-    printf("{\"fmnmx_fadd_triplets_per_clk_per_sm\": %.2f}\n", n / t4 / 1e6 / p.multiProcessorCount / (p.clockRate / 1e3) * 1e3 / 1e3);
+    printf("{\"fmnmx_fmnmx_fadd_lane_triplets_per_clk_per_sm\": %.2f}\n", n / (t4 * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3));
     printf("{\"device\": \"%s\", \"sms\": %d, \"ffma_tflops\": %.2f, \"ffma2_tflops\": %.2f, \"ffma_ms\": %.4f, \"ffma2_ms\": %.4f, "
            "\"shfl_minmax_gops\": %.1f}\n",
            p.name, p.multiProcessorCount, 2 * n / t1 / 1e9, 2 * n / t2 / 1e9, t1, t2,
