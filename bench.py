@@ -267,11 +267,14 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = BATCH * ALG_BYTES_PER_PAIR / kernel_s / 1e9
-        traffic = None
+        traffic, traffic_src = None, None       # dram__bytes_read+write per launch from the committed `ncu --set full` summary
         try:
-            with open(os.path.join(ROOT, "profiles", "embed_kernel_ncu_summary.json")) as f:
+            import glob
+            latest = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), key=os.path.getmtime)[-1]
+            with open(latest) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        except (OSError, ValueError):
+            traffic_src = os.path.relpath(latest, ROOT)
+        except (IndexError, OSError, ValueError):
             pass
         line = {
             "metric": METRIC, "value": value, "unit": "graph-pairs/s", "n_gpus": world, "steps": args.steps,
@@ -289,7 +292,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "sgpr_embed_kernel<2> (fused EdgeConv x6 + attention + NTN head)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "algorithmic_bytes_per_launch": BATCH * ALG_BYTES_PER_PAIR,
