@@ -79,6 +79,9 @@ struct sgpr_ctx {
     float* d_blk = nullptr;      size_t blk_cap = 0;     // rowblk | colblk
     cudaStream_t stream = nullptr;                      // host-path stream
     long long launches = 0;
+    int* d_order = nullptr;      size_t order_cap = 0;   // rows[G] | order[G]
+    int* d_ctrs = nullptr;                               // {done counter, work counter}
+    int balance = 1;             // order graphs by active rows before the fused kernel; SGPR_NO_BALANCE=1 disables it
     int dedup = 1;               // collapse trailing all-zero nodes (exact); SGPR_NO_DEDUP=1 disables it for experiments
 };
 
@@ -110,6 +113,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->off = make_offsets();
     if (const char* nd = getenv("SGPR_NO_DEDUP")) ctx->dedup = (nd[0] == '1') ? 0 : 1;
+    if (const char* nb = getenv("SGPR_NO_BALANCE")) ctx->balance = (nb[0] == '1') ? 0 : 1;
     // opt in to the full shared-memory carve-out; the dynamic limit excludes each kernel's static __shared__ bytes
     auto opt_in = [&](const void* fn) -> cudaError_t {
         cudaFuncAttributes fa;
@@ -124,6 +128,8 @@ int sgpr_create(sgpr_ctx** out, int device) {
     if (e == cudaSuccess) e = opt_in(reinterpret_cast<const void*>(&sgpr_score_matrix_kernel));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_blob), ctx->off.total * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_ctrs), 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_ctrs, 0, 2 * sizeof(int));
     if (e != cudaSuccess) {
         int rc = fail(SGPR_E_CUDA, "sgpr_create: %s", cudaGetErrorString(e));
         sgpr_destroy(ctx);
@@ -143,6 +149,8 @@ int sgpr_destroy(sgpr_ctx* ctx) {
     cudaFree(ctx->d_out);
     cudaFree(ctx->d_proj);
     cudaFree(ctx->d_blk);
+    cudaFree(ctx->d_order);
+    cudaFree(ctx->d_ctrs);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SGPR_OK;
@@ -202,8 +210,24 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     const int npl = (N <= 32) ? 1 : (N <= 64) ? 2 : 4;
     const SmemLayout L = make_layout(32 * npl, a.KS);
     const int per_sm = (npl <= 2) ? 2 : 1;
-    int grid = a.G < ctx->sm_count * per_sm ? a.G : ctx->sm_count * per_sm;
+    const int capacity = ctx->sm_count * per_sm;
+    int grid = a.G < capacity ? a.G : capacity;
     if (grid < 1) return SGPR_OK;
+    a.order = nullptr;
+    a.work_ctr = nullptr;
+    // more graphs than SMs: place / pop them by measured size so that co-resident CTAs balance (results unchanged)
+    if (ctx->balance && a.G > ctx->sm_count) {
+        int rc = ensure(ctx->d_order, ctx->order_cap, static_cast<size_t>(2) * a.G);
+        if (rc) return rc;
+        const int resident = (a.G <= capacity) ? 1 : 0;
+        int ogrid = (a.G + kWarps - 1) / kWarps;
+        if (ogrid > 4 * ctx->sm_count) ogrid = 4 * ctx->sm_count;
+        sgpr_order_kernel<<<ogrid, kThreads, 0, st>>>(a.g0, a.g1, a.pairs, a.G, a.N, a.dedup, ctx->sm_count, resident,
+                                                     ctx->d_order, ctx->d_order + a.G, ctx->d_ctrs, ctx->d_ctrs + 1);
+        ctx->launches += 1;
+        a.order = ctx->d_order + a.G;
+        if (!resident) a.work_ctr = ctx->d_ctrs + 1;
+    }
     switch (npl) {
         case 1: sgpr_embed_kernel<1><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
         case 2: sgpr_embed_kernel<2><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;

@@ -61,6 +61,8 @@ struct EmbedArgs {
     int* counters;          // [B]  arrival counters, zero on entry, zero on exit
     uint8_t* trace_knn;     // [G][6][N][k] or null
     float* trace_layers;    // [G][6][N][64] or null
+    const int* order;       // [G] slot -> graph (heavy graphs placed so that co-resident CTAs balance), or null = identity
+    int* work_ctr;          // non-null: CTAs pop slots from this counter (persistent launches, heaviest graph first)
 };
 
 struct SmemLayout {
@@ -667,8 +669,18 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
 
     const uint32_t inBytes = static_cast<uint32_t>(kInCh * N * 4);
 
+    __shared__ int sSlot;
 #pragma unroll 1
-    for (int g = blockIdx.x; g < A.G; g += gridDim.x) {
+    for (int it = blockIdx.x;; it += gridDim.x) {
+        int slot = it;
+        if (A.work_ctr) {                               // dynamic: next heaviest unprocessed graph
+            if (tid == 0) sSlot = atomicAdd(A.work_ctr, 1);
+            __syncthreads();
+            slot = sSlot;
+            __syncthreads();
+        }
+        if (slot >= A.G) break;
+        const int g = A.order ? __ldg(A.order + slot) : slot;
         const float* gin = A.pairs ? (((g & 1) ? A.g1 : A.g0) + static_cast<size_t>(g >> 1) * kInCh * N)
                                    : (A.g0 + static_cast<size_t>(g) * kInCh * N);
         const bool bulk_ok = ((inBytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0);

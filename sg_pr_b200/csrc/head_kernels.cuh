@@ -6,9 +6,70 @@
 // data_process/gen_sem_kitti_graph_pairs.py:43-52); this is the embed-once / score-matrix split of SURVEY §8(f1).
 #pragma once
 #include "common.cuh"
+#include "../../include/sgpr_b200.h"
 #include "embed_kernel.cuh"
 
 namespace sgpr {
+
+// ---- work ordering -------------------------------------------------------------------------------------------
+// Per-graph cost of the fused kernel grows with its active rows R (embed_kernel.cuh: nodes up to the last non-zero
+// one + 1).  This pre-pass measures R for every graph and builds `order[slot] -> graph`:
+//   * resident launches with two CTAs per SM (S < G <= 2S): CTA j and CTA S+j share an SM, CTAs G-S..S-1 have one
+//     to themselves -> the heaviest graphs go to the lone CTAs, the rest are paired heaviest-with-lightest;
+//   * persistent launches (G beyond the resident capacity): descending R, popped through a work counter (LPT).
+// It changes only WHERE each graph runs; results are bit-identical.
+__global__ void __launch_bounds__(kThreads)
+sgpr_order_kernel(const float* __restrict__ g0, const float* __restrict__ g1, int pairs, int G, int N, int dedup, int S,
+                  int resident, int* __restrict__ rows, int* __restrict__ order, int* __restrict__ done_ctr,
+                  int* __restrict__ work_ctr) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int g = blockIdx.x * kWarps + warp; g < G; g += gridDim.x * kWarps) {
+        const float* gin = pairs ? (((g & 1) ? g1 : g0) + static_cast<size_t>(g >> 1) * kInCh * N)
+                                 : (g0 + static_cast<size_t>(g) * kInCh * N);
+        int last = -1;
+        if (dedup) {
+            for (int n = lane; n < N; n += 32) {
+                uint32_t bits = 0;
+#pragma unroll
+                for (int c = 0; c < kInCh; ++c) bits |= __float_as_uint(__ldg(gin + c * N + n));
+                if ((bits << 1) != 0u) last = n;
+            }
+            last = __reduce_max_sync(0xffffffffu, last);
+        }
+        if (lane == 0) rows[g] = dedup ? min(last + 2, N) : N;
+    }
+    __shared__ int sIsLast;
+    __shared__ int hist[SGPR_MAX_NODES + 2];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sIsLast = (atomicAdd(done_ctr, 1) == static_cast<int>(gridDim.x) - 1);
+    __syncthreads();
+    if (!sIsLast) return;
+    __threadfence();
+    // ---- counting sort by R, descending ----
+    for (int b = tid; b < SGPR_MAX_NODES + 2; b += kThreads) hist[b] = 0;
+    __syncthreads();
+    for (int g = tid; g < G; g += kThreads) atomicAdd(&hist[__ldcg(rows + g)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int b = SGPR_MAX_NODES + 1; b >= 0; --b) { const int c = hist[b]; hist[b] = run; run += c; }
+        *done_ctr = 0;
+        *work_ctr = 0;
+    }
+    __syncthreads();
+    const int D = G - S;                                   // SMs holding two CTAs when S < G <= 2S
+    for (int g = tid; g < G; g += kThreads) {
+        const int rank = atomicAdd(&hist[__ldcg(rows + g)], 1);        // 0 = heaviest
+        int slot = rank;
+        if (resident && D > 0 && G <= 2 * S) {
+            if (rank < S - D) slot = D + rank;                          // lone CTAs: the heaviest graphs
+            else if (rank < S) slot = rank - (S - D);                   // first CTA of a shared SM, descending
+            else slot = S + (G - 1 - rank);                             // its partner: lightest with heaviest
+        }
+        order[slot] = g;
+    }
+}
 
 // ---- explicit pair list: one CTA per pair ---------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
