@@ -81,6 +81,7 @@ struct sgpr_ctx {
     long long launches = 0;
     int* d_order = nullptr;      size_t order_cap = 0;   // rows[G] | order[G]
     int* d_ctrs = nullptr;                               // {done counter, work counter}
+    int zerocopy = 1;            // host entry point: read pinned buffers in place; SGPR_NO_ZEROCOPY=1 forces staged copies
     int balance = 1;             // order graphs by active rows before the fused kernel; SGPR_NO_BALANCE=1 disables it
     int dedup = 1;               // collapse trailing all-zero nodes (exact); SGPR_NO_DEDUP=1 disables it for experiments
 };
@@ -113,6 +114,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->off = make_offsets();
     if (const char* nd = getenv("SGPR_NO_DEDUP")) ctx->dedup = (nd[0] == '1') ? 0 : 1;
+    if (const char* nz = getenv("SGPR_NO_ZEROCOPY")) ctx->zerocopy = (nz[0] == '1') ? 0 : 1;
     if (const char* nb = getenv("SGPR_NO_BALANCE")) ctx->balance = (nb[0] == '1') ? 0 : 1;
     // opt in to the full shared-memory carve-out; the dynamic limit excludes each kernel's static __shared__ bytes
     auto opt_in = [&](const void* fn) -> cudaError_t {
@@ -203,6 +205,21 @@ int check_shape(const char* who, int count, int N, int k) {
     return SGPR_OK;
 }
 
+// Pinned (page-locked) host memory is mapped into the device address space under UVA: the kernel can pull each
+// graph's 60*N-byte block straight over PCIe with its bulk-TMA load.  Returns the device-visible alias or nullptr.
+const void* device_alias_of_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    return nullptr;
+}
+
+bool is_device_memory(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
 int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     const int N = a.N;
     a.KS = (a.k + 3) & ~3;
@@ -216,7 +233,8 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     a.order = nullptr;
     a.work_ctr = nullptr;
     // more graphs than SMs: place / pop them by measured size so that co-resident CTAs balance (results unchanged)
-    if (ctx->balance && a.G > ctx->sm_count) {
+    // (skipped when the graphs sit in pinned host memory: the pre-pass would pull them over PCIe a second time)
+    if (ctx->balance && a.G > ctx->sm_count && is_device_memory(a.g0)) {
         int rc = ensure(ctx->d_order, ctx->order_cap, static_cast<size_t>(2) * a.G);
         if (rc) return rc;
         const int resident = (a.G <= capacity) ? 1 : 0;
@@ -282,11 +300,26 @@ int sgpr_forward_pairs_host(sgpr_ctx* ctx, const float* f1_host, const float* f2
     DeviceGuard guard(ctx->device);
     const size_t side = static_cast<size_t>(B) * kInCh * N;
     const size_t att = static_cast<size_t>(B) * N;
+    cudaStream_t st = ctx->stream;
+    // ---- zero-copy: every buffer pinned -> the kernel reads the inputs and writes the results in place ----
+    if (ctx->zerocopy) {
+        const float* d1 = static_cast<const float*>(device_alias_of_pinned(f1_host));
+        const float* d2 = static_cast<const float*>(device_alias_of_pinned(f2_host));
+        float* ds = static_cast<float*>(const_cast<void*>(device_alias_of_pinned(score_host)));
+        float* da1 = att1_host ? static_cast<float*>(const_cast<void*>(device_alias_of_pinned(att1_host))) : nullptr;
+        float* da2 = att2_host ? static_cast<float*>(const_cast<void*>(device_alias_of_pinned(att2_host))) : nullptr;
+        if (d1 && d2 && ds && (!att1_host || da1) && (!att2_host || da2)) {
+            rc = forward_pairs_impl(ctx, d1, d2, B, N, k, ds, da1, da2, st);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(st));
+            return SGPR_OK;
+        }
+    }
+    // ---- staged: H2D copies, kernel, D2H copies ----
     rc = ensure(ctx->d_in, ctx->in_cap, 2 * side);
     if (rc) return rc;
     rc = ensure(ctx->d_out, ctx->out_cap, static_cast<size_t>(B) + 2 * att);
     if (rc) return rc;
-    cudaStream_t st = ctx->stream;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_in, f1_host, side * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_in + side, f2_host, side * sizeof(float), cudaMemcpyHostToDevice, st));
     float* d_score = ctx->d_out;
@@ -373,6 +406,10 @@ int64_t sgpr_launch_count(const sgpr_ctx* ctx) { return ctx ? ctx->launches : 0;
 // debug builds only (not declared in the public header): copy CTA 0's clock stamps, [8 warps][128 slots]
 int sgpr_debug_timeline(long long* out) {
     return cudaMemcpyFromSymbol(out, g_timeline, sizeof(long long) * kWarps * 128) == cudaSuccess ? 0 : -2;
+}
+int sgpr_debug_ctas(int* smid1024, long long* t2048) {
+    if (cudaMemcpyFromSymbol(smid1024, g_smid, sizeof(int) * 1024) != cudaSuccess) return -2;
+    return cudaMemcpyFromSymbol(t2048, g_cta_t, sizeof(long long) * 2048) == cudaSuccess ? 0 : -2;
 }
 #endif
 

@@ -41,6 +41,8 @@ namespace sgpr {
 // Optional per-phase clock stamps of CTA 0 (debug builds only: -DSGPR_TIMELINE); see tools/timeline.py.
 #ifdef SGPR_TIMELINE
 __device__ long long g_timeline[kWarps * 128];
+__device__ int g_smid[1024];
+__device__ long long g_cta_t[2048];
 #define SGPR_TL(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_timeline[(threadIdx.x >> 5) * 128 + (slot)] = clock64(); } while (0)
 #else
 #define SGPR_TL(slot) do { } while (0)
@@ -661,6 +663,14 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
     uint64_t* barW = bars + 1;
     uint32_t phIn = 0, phW = 0;
 
+#ifdef SGPR_TIMELINE
+    if (tid == 0 && blockIdx.x < 1024) {
+        unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g_smid[blockIdx.x] = static_cast<int>(sm);
+        long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_cta_t[2 * blockIdx.x] = t;
+    }
+#endif
     if (tid == 0) { mbar_init(barIn, 1); mbar_init(barW, 1); fence_mbar_init(); }
     // zero the feature tiles once so rows beyond the active ones never hold junk
     for (int e = tid; e < NMAX * XS; e += kThreads) { sX[e] = 0.0f; sCat[e] = 0.0f; }
@@ -887,6 +897,12 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         __syncthreads();
         SGPR_TL(62);
     }
+#ifdef SGPR_TIMELINE
+    if (tid == 0 && blockIdx.x < 1024) {
+        long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_cta_t[2 * blockIdx.x + 1] = t;
+    }
+#endif
 }
 
 }  // namespace sgpr

@@ -140,8 +140,10 @@ class Engine:
     def _stream(self) -> C.c_void_p:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _dev(self, t: torch.Tensor, what: str) -> torch.Tensor:
-        if t.device != self.device:
+    def _dev(self, t: torch.Tensor, what: str, allow_pinned: bool = False) -> torch.Tensor:
+        """A tensor the kernels can address: on the engine's device, or (inputs only) pinned host memory, which UVA
+        maps into the device address space — the fused kernel then pulls each graph block over PCIe by itself."""
+        if t.device != self.device and not (allow_pinned and t.device.type == "cpu" and t.is_pinned()):
             raise ValueError(f"{what} lives on {t.device}, engine on {self.device}")
         return t.contiguous()
 
@@ -151,7 +153,7 @@ class Engine:
         b, n = _check_graphs(f1, "features_1")
         if tuple(f2.shape) != tuple(f1.shape):
             raise ValueError(f"features_2 {tuple(f2.shape)} != features_1 {tuple(f1.shape)}")
-        f1, f2 = self._dev(f1, "features_1"), self._dev(f2, "features_2")
+        f1, f2 = self._dev(f1, "features_1", True), self._dev(f2, "features_2", True)
         score = torch.empty(b, dtype=torch.float32, device=self.device)
         att1 = torch.empty(b, n, 1, dtype=torch.float32, device=self.device) if want_att else None
         att2 = torch.empty(b, n, 1, dtype=torch.float32, device=self.device) if want_att else None

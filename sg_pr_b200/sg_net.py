@@ -140,10 +140,15 @@ class SG(torch.nn.Module):
     def forward(self, data):
         """sg_net.py:112-138.  data["features_1"/"features_2"]: [B, 3+labels, node_num] float tensors (CPU or device)."""
         dev = self._device()
-        f1 = data["features_1"].to(dev, dtype=torch.float32, non_blocking=True)
-        f2 = data["features_2"].to(dev, dtype=torch.float32, non_blocking=True)
+        f1, f2 = data["features_1"], data["features_2"]
         if self.training:
-            return self._forward_autograd(f1, f2)
+            return self._forward_autograd(f1.to(dev, dtype=torch.float32), f2.to(dev, dtype=torch.float32))
+        # pinned fp32 host tensors are read in place by the kernel (zero-copy over PCIe); anything else is moved first
+        zero_copy = all(t.device.type == "cpu" and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous()
+                        for t in (f1, f2))
+        if not zero_copy:
+            f1 = f1.to(dev, dtype=torch.float32, non_blocking=True)
+            f2 = f2.to(dev, dtype=torch.float32, non_blocking=True)
         return self.engine().forward_pairs(f1, f2, int(self.args.K), want_att=True)
 
 

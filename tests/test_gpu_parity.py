@@ -179,8 +179,14 @@ def test_host_entry_point_matches_device(eng):
     d_score, d_a1, d_a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)
     h_score, h_a1, h_a2 = eng.forward_pairs_host(f1, f2, 20)
     assert torch.equal(h_score, d_score.cpu()) and torch.equal(h_a1, d_a1.cpu()) and torch.equal(h_a2, d_a2.cpu())
-    p_score, _, _ = eng.forward_pairs_host(f1.pin_memory(), f2.pin_memory(), 20, want_att=False)
-    assert torch.equal(p_score, h_score)
+    # pinned buffers: the kernel reads the inputs and writes the scores in place (zero-copy) — same bits
+    out = (torch.empty(64).pin_memory(), torch.empty(64, 64, 1).pin_memory(), torch.empty(64, 64, 1).pin_memory())
+    p_score, p_a1, p_a2 = eng.forward_pairs_host(f1.pin_memory(), f2.pin_memory(), 20, out=out)
+    assert torch.equal(p_score, h_score) and torch.equal(p_a1, h_a1) and torch.equal(p_a2, h_a2)
+    z_score, z_a1, _ = eng.forward_pairs(f1.pin_memory(), f2.pin_memory(), 20)      # device outputs, pinned inputs
+    assert torch.equal(z_score.cpu(), h_score) and torch.equal(z_a1.cpu(), h_a1)
+    mixed, _, _ = eng.forward_pairs_host(f1.pin_memory(), f2, 20, want_att=False)     # one pageable side -> staged path
+    assert torch.equal(mixed, h_score)
 
 
 def test_edge_cases(eng, kitti_state):
