@@ -148,15 +148,20 @@ class Engine:
         return t.contiguous()
 
     # ---- the hot path ---------------------------------------------------------------------------------------
-    def forward_pairs(self, f1: torch.Tensor, f2: torch.Tensor, k: int, want_att: bool = True):
-        """Device tensors in, device tensors out: (score [B], att_1 [B,N,1], att_2 [B,N,1]) — sg_net.py:138."""
-        b, n = _check_graphs(f1, "features_1")
-        if tuple(f2.shape) != tuple(f1.shape):
-            raise ValueError(f"features_2 {tuple(f2.shape)} != features_1 {tuple(f1.shape)}")
-        f1, f2 = self._dev(f1, "features_1", True), self._dev(f2, "features_2", True)
-        score = torch.empty(b, dtype=torch.float32, device=self.device)
-        att1 = torch.empty(b, n, 1, dtype=torch.float32, device=self.device) if want_att else None
-        att2 = torch.empty(b, n, 1, dtype=torch.float32, device=self.device) if want_att else None
+    def forward_pairs(self, f1: torch.Tensor, f2: torch.Tensor, k: int, want_att: bool = True, _checked: bool = False):
+        """Device (or pinned-host) tensors in, device tensors out: (score [B], att_1 [B,N,1], att_2 [B,N,1]) — sg_net.py:138.
+        `_checked`: the caller (SG.forward) has already validated placement / dtype / layout."""
+        if not _checked:
+            _check_graphs(f1, "features_1")
+            if tuple(f2.shape) != tuple(f1.shape):
+                raise ValueError(f"features_2 {tuple(f2.shape)} != features_1 {tuple(f1.shape)}")
+            f1, f2 = self._dev(f1, "features_1", True), self._dev(f2, "features_2", True)
+        b, n = int(f1.shape[0]), int(f1.shape[2])
+        # one allocation for the three results (views are returned)
+        buf = torch.empty(b + (2 * b * n if want_att else 0), dtype=torch.float32, device=self.device)
+        score = buf[:b]
+        att1 = buf[b:b + b * n].view(b, n, 1) if want_att else None
+        att2 = buf[b + b * n:].view(b, n, 1) if want_att else None
         check(self._lib.sgpr_forward_pairs(self._ctx, f1.data_ptr(), f2.data_ptr(), b, n, int(k), score.data_ptr(),
                                            att1.data_ptr() if want_att else None,
                                            att2.data_ptr() if want_att else None, self._stream()),

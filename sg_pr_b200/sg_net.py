@@ -144,12 +144,13 @@ class SG(torch.nn.Module):
         if self.training:
             return self._forward_autograd(f1.to(dev, dtype=torch.float32), f2.to(dev, dtype=torch.float32))
         # pinned fp32 host tensors are read in place by the kernel (zero-copy over PCIe); anything else is moved first
-        zero_copy = all(t.device.type == "cpu" and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous()
-                        for t in (f1, f2))
-        if not zero_copy:
+        ok = (f1.dim() == 3 and f1.shape[1] == 15 and f2.shape == f1.shape and f1.dtype == torch.float32
+              and f2.dtype == torch.float32 and f1.is_contiguous() and f2.is_contiguous())
+        if not (ok and f1.device.type == "cpu" and f2.device.type == "cpu" and f1.is_pinned() and f2.is_pinned()):
+            ok = False
             f1 = f1.to(dev, dtype=torch.float32, non_blocking=True)
             f2 = f2.to(dev, dtype=torch.float32, non_blocking=True)
-        return self.engine().forward_pairs(f1, f2, int(self.args.K), want_att=True)
+        return self.engine().forward_pairs(f1, f2, int(self.args.K), want_att=True, _checked=ok)
 
 
 class _DeviceReplica(torch.nn.Module):
