@@ -36,6 +36,17 @@
 #pragma once
 #include "common.cuh"
 
+// tuning switches (defaults are the measured-best variants; see profiles/r01_variants.txt)
+#ifndef SGPR_GRAM_V
+#define SGPR_GRAM_V 0      // 0: explicit register double-buffering of the operand loads, 1: plain loop, unroll 4
+#endif
+#ifndef SGPR_GEMM_V
+#define SGPR_GEMM_V 0      // 0: weights of the next channel pair prefetched, 1: plain loop, unroll 2
+#endif
+#ifndef SGPR_GATHER_W
+#define SGPR_GATHER_W 3    // packed index words (4 neighbours each) fetched per gather step
+#endif
+
 namespace sgpr {
 
 // Optional per-phase clock stamps of CTA 0 (debug builds only: -DSGPR_TIMELINE); see tools/timeline.py.
@@ -145,6 +156,26 @@ __device__ __forceinline__ void gram_rows(const float* __restrict__ sXt, const f
         for (int q = 0; q < NPL; ++q) acc[r][q] = make_float2(0.0f, 0.0f);
     const float* pa = sXt + r0 * XS;
     const float* pb = sXt + lane * XS;
+#if SGPR_GRAM_V == 1
+#pragma unroll 4
+    for (int c = 0; c < c4n; ++c) {
+        float4 a[NR], b[NPL];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a[r] = *reinterpret_cast<const float4*>(pa + r * XS + 4 * c);
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) b[q] = (q < nq) ? *reinterpret_cast<const float4*>(pb + 32 * q * XS + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            if (q < nq) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    acc[r][q] = ffma2(make_float2(a[r].x, a[r].y), make_float2(b[q].x, b[q].y), acc[r][q]);
+                    acc[r][q] = ffma2(make_float2(a[r].z, a[r].w), make_float2(b[q].z, b[q].w), acc[r][q]);
+                }
+            }
+        }
+    }
+#else
     // software pipeline: the loads of channel group c+1 are in flight while the FFMA2s of group c issue
     float4 a[NR], b[NPL];
 #pragma unroll
@@ -174,6 +205,7 @@ __device__ __forceinline__ void gram_rows(const float* __restrict__ sXt, const f
 #pragma unroll
         for (int q = 0; q < NPL; ++q) b[q] = bn[q];
     }
+#endif
 #pragma unroll
     for (int q = 0; q < NPL; ++q) {
         const int c = lane + 32 * q;
@@ -347,6 +379,25 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ sXin, const 
             w[0] = *reinterpret_cast<const float2*>(wp + lane * 2);
         }
     };
+#if SGPR_GEMM_V == 1
+#pragma unroll 2
+    for (int c4 = 0; c4 < cin4; ++c4) {
+        float4 x[NR];
+#pragma unroll
+        for (int n = 0; n < NR; ++n) x[n] = *reinterpret_cast<const float4*>(px + n * XS + 4 * c4);
+        float2 wa[CPL], wb[CPL];
+        load_w(wa, 2 * c4);
+        load_w(wb, 2 * c4 + 1);
+#pragma unroll
+        for (int n = 0; n < NR; ++n)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) acc[n][j] = ffma2(make_float2(x[n].x, x[n].y), wa[j], acc[n][j]);
+#pragma unroll
+        for (int n = 0; n < NR; ++n)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) acc[n][j] = ffma2(make_float2(x[n].z, x[n].w), wb[j], acc[n][j]);
+    }
+#else
     // software pipeline over channel pairs: the weights of pair p+1 load while the FFMA2s of pair p issue
     const int npairs = 2 * cin4;
     float2 w0[CPL], w1[CPL];
@@ -367,6 +418,7 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ sXin, const 
 #pragma unroll
             for (int j = 0; j < CPL; ++j) acc[n][j] = ffma2(make_float2(x[n].z, x[n].w), w1[j], acc[n][j]);
     }
+#endif
     float al[CPL], be[CPL];
     if constexpr (EPI == 1) {
 #pragma unroll
@@ -420,6 +472,7 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
                                             const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ ab,
                                             float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane) {
     constexpr int CPL = COUT / 32;
+    constexpr int GW = SGPR_GATHER_W;
     float al[CPL], be[CPL];
 #pragma unroll
     for (int p = 0; p < CPL; ++p) { al[p] = __ldg(ab + lane * CPL + p); be[p] = __ldg(ab + COUT + lane * CPL + p); }
@@ -435,13 +488,13 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
 #pragma unroll
         for (int p = 0; p < CPL; ++p) { ai[p] = base[i * YS + p]; bi[p] = base[i * YS + COUT + p]; }
 #pragma unroll 1
-        for (int t = 0; t < nw; t += 3) {
-            uint32_t wd[3];
+        for (int t = 0; t < nw; t += GW) {
+            uint32_t wd[GW];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) wd[q] = row[min(t + q, nw - 1)];       // tail words repeat (harmless under max)
-            float v[12][CPL];
+            for (int q = 0; q < GW; ++q) wd[q] = row[min(t + q, nw - 1)];      // tail words repeat (harmless under max)
+            float v[4 * GW][CPL];
 #pragma unroll
-            for (int e = 0; e < 12; ++e) {
+            for (int e = 0; e < 4 * GW; ++e) {
                 const int j = (wd[e >> 2] >> (8 * (e & 3))) & 0xff;
                 if constexpr (CPL == 2) {
                     const float2 a = *reinterpret_cast<const float2*>(base + j * YS);
@@ -452,10 +505,9 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
             }
 #pragma unroll
             for (int p = 0; p < CPL; ++p) {
-                const float m0 = fmaxf(fmaxf(v[0][p], v[1][p]), fmaxf(v[2][p], v[3][p]));
-                const float m1 = fmaxf(fmaxf(v[4][p], v[5][p]), fmaxf(v[6][p], v[7][p]));
-                const float m2 = fmaxf(fmaxf(v[8][p], v[9][p]), fmaxf(v[10][p], v[11][p]));
-                m[p] = fmaxf(fmaxf(m[p], m0), fmaxf(m1, m2));
+#pragma unroll
+                for (int q = 0; q < GW; ++q)
+                    m[p] = fmaxf(m[p], fmaxf(fmaxf(v[4 * q][p], v[4 * q + 1][p]), fmaxf(v[4 * q + 2][p], v[4 * q + 3][p])));
             }
         }
 #pragma unroll

@@ -12,4 +12,4 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --cs
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgpr_embed -s 5 -c 2 -f -o gpurun_out/prof_embed python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/microbench.json; head -c 1500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err; tail -3 gpurun_out/sanitizer.log
 cat gpurun_out/perf_probe.jsonl
-SGPR_B200_LIB=$PWD/tools/variants/lib_timeline.so timeout 120 python tools/timeline.py 16 > gpurun_out/timeline.txt 2>&1; cat gpurun_out/timeline.txt | awk "NR<4 || /front start|select done|front done|barrier B|back done|layers done|attention|end/" | cut -c1-60
+SGPR_B200_LIB=$PWD/tools/variants/lib_tl_base.so timeout 120 python tools/timeline.py 16 > gpurun_out/timeline.txt 2>&1; cat gpurun_out/timeline.txt | awk "NR<4 || /front start|select done|front done|barrier B|back done|layers done|attention|end/" | cut -c1-60

@@ -29,3 +29,18 @@ for slot in sorted(names):
     row = t[:, slot] - t0
     if (t[:, slot] == 0).all(): continue
     print(f"{names[slot]:18s}" + "".join(f"{int(v):9d}" for v in row))
+
+# aggregated phase durations (cycles), mean over warps
+import numpy as _np
+def d(a, b):
+    return float(_np.mean(t[:, b] - t[:, a]))
+agg = {"gram": 0.0, "select": 0.0, "gemm/xyz": 0.0, "barrierB": 0.0, "back": 0.0, "barrierA+next": 0.0}
+for l in range(6):
+    s0 = 8 + l * 8
+    agg["gram"] += d(s0, s0 + 1); agg["select"] += d(s0 + 1, s0 + 2); agg["gemm/xyz"] += d(s0 + 2, s0 + 3)
+    if l: agg["barrierB"] += d(s0 + 3, s0 + 4); agg["back"] += d(s0 + 4, s0 + 5)
+    else: agg["back"] += d(s0 + 3, s0 + 5)
+    nxt = 8 + (l + 1) * 8 if l < 5 else 58
+    agg["barrierA+next"] += d(s0 + 5, nxt)
+agg["attention"] = d(58, 60); agg["head+end"] = d(60, 62); agg["total"] = d(0, 62)
+print("PHASES " + " ".join(f"{k}={v:.0f}" for k, v in agg.items()))
