@@ -191,7 +191,7 @@ class Engine:
     def embed(self, graphs: torch.Tensor, k: int, want_att: bool = False, want_emb: bool = False, trace: bool = False):
         """[M,15,N] -> dict(pooled [M,32], att [M,N,1]?, emb [M,N,32]?, knn [M,6,N,k] uint8?, layers [M,6,N,64]?)."""
         m, n = _check_graphs(graphs, "graphs")
-        graphs = self._dev(graphs, "graphs")
+        graphs = self._dev(graphs, "graphs", True)
         out = {"pooled": torch.empty(m, F3, dtype=torch.float32, device=self.device)}
         if want_att:
             out["att"] = torch.empty(m, n, 1, dtype=torch.float32, device=self.device)

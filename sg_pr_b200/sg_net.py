@@ -22,6 +22,7 @@ import torch.nn as nn
 
 from . import dgcnn
 from . import utils as _utils
+from .graph_store import GraphStore
 from .layers_batch import AttentionModule, TenorNetworkModule
 from .utils import listDir, load_paires, process_pair
 
@@ -174,6 +175,12 @@ class SGTrainer(object):
         self.initial_label_enumeration(train)
         self.setup_model(train)
         self.writer = _make_writer(self.args.logdir)
+        # evaluation-side host pipeline: graphs are parsed once, and — with `embed_cache` — embedded
+        # once, so a pair list over a sequence costs one EdgeConv pass per GRAPH instead of two per PAIR.  Scores are
+        # bit-identical either way (tests/test_gpu_parity.py::test_pairs_equal_embed_plus_head).
+        self.embed_cache = True
+        self._graph_store = None
+        self._emb = None
 
     # ---- construction ----------------------------------------------------------------------------------------
     def setup_model(self, train=True):
@@ -399,10 +406,62 @@ class SGTrainer(object):
         print("forward time: ", time.time() - start)
         return prediction, gt
 
+    def _store(self):
+        if self._graph_store is None or self._graph_store.node_num != int(self.args.node_num):
+            self._graph_store = GraphStore(self.args.node_num, self.number_of_labels)
+        return self._graph_store
+
+    def _pooled_rows(self, paths):
+        """Row indices into the device-resident pooled-vector table for `paths` (all static graphs), embedding the ones
+        not seen yet under the current weights / K / node_num."""
+        module = self.model.module
+        eng = module.engine()
+        key = (module._packed_version, int(self.args.K), int(self.args.node_num))
+        if self._emb is None or self._emb["key"] != key:
+            self._emb = {"key": key, "index": {}, "pool": torch.empty(1024, 32, device=eng.device), "count": 0}
+        emb, store = self._emb, self._store()
+        fresh = [p for p in dict.fromkeys(paths) if p not in emb["index"]]
+        if fresh:
+            blocks = torch.stack([store.block(p) for p in fresh]).pin_memory()
+            pooled = eng.embed(blocks, int(self.args.K))["pooled"]
+            need = emb["count"] + len(fresh)
+            if need > emb["pool"].shape[0]:
+                grown = torch.empty(max(need, 2 * emb["pool"].shape[0]), 32, device=eng.device)
+                grown[:emb["count"]] = emb["pool"][:emb["count"]]
+                emb["pool"] = grown
+            emb["pool"][emb["count"]:need] = pooled
+            for i, p in enumerate(fresh):
+                emb["index"][p] = emb["count"] + i
+            emb["count"] = need
+        return [emb["index"][p] for p in paths]
+
     def eval_batch_pair(self, batch):
         """sg_net.py:503-525: batch of [path_a, path_b] -> (pred[B], gt[B]).  The call eval_pair.py / eval_batch.py make."""
-        prediction, _, _, gt = self._eval_dicts([process_pair(graph_pair) for graph_pair in batch])
+        self.model.eval()
+        store = self._store()
+        gt = np.array([store.target(a, b, self.args.p_thresh) for a, b in batch], dtype=np.float64).reshape(-1)
+        static = all(store.is_static(a) and store.is_static(b) for a, b in batch)
+        if self.embed_cache and static and torch.cuda.is_available() and len(batch) > 0:
+            eng = self.model.module.engine()
+            rows = self._pooled_rows([p for pair in batch for p in pair])
+            idx = torch.tensor(rows, dtype=torch.int32).view(-1, 2).to(eng.device, non_blocking=True)
+            prediction = eng.score_pairs(self._emb["pool"], idx)
+        else:
+            f1, f2, _ = store.pair_batch(batch, self.args.p_thresh, pin=torch.cuda.is_available())
+            with torch.no_grad():
+                prediction, _, _ = self.model({"features_1": f1, "features_2": f2, "target": torch.from_numpy(gt)})
         return prediction.cpu().detach().numpy().reshape(-1), gt
+
+    def eval_sequence(self, paths, row_block=None):
+        """All ordered pairs of a list of graph files: scores[i, j] = model(graph i, graph j) as a device tensor — the
+        N x N scan the reference only has offline (data_process/gen_sem_kitti_graph_pairs.py:43-52).  `row_block=(lo, hi)`
+        restricts the rows (multi-GPU sharding, see sg_pr_b200/scan.py)."""
+        self.model.eval()
+        eng = self.model.module.engine()
+        rows = torch.tensor(self._pooled_rows(list(paths)), device=eng.device)
+        pooled = self._emb["pool"][rows]
+        lo, hi = row_block if row_block is not None else (0, len(paths))
+        return eng.score_matrix(pooled[lo:hi].contiguous(), pooled)
 
     def write_soft_label(self, data_dir, out_dir=None, thresh=0.5):
         """sg_net.py:528-564: re-label pair files with the model's decision and report precision / recall."""

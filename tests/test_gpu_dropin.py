@@ -62,13 +62,26 @@ def test_eval_batch_loop_and_repack_on_weight_change(tree, golden_dir):
     for pair, got in zip(pairs, pred_db):
         a, b = (os.path.basename(p)[:-5] for p in pair)
         assert abs(float(got) - float(z[f"K20_N64_{a}_{b}_score"][0])) <= 1e-5, (a, b)
-    launches = trainer.model.module.engine().launch_count()
-    assert launches == len(batches)                       # ONE fused launch per batch
+    eng = trainer.model.module.engine()
+    # embed-once evaluation: 3 distinct graphs -> ONE embed launch, then one pair-head launch per batch
+    assert eng.launch_count() == 1 + len(batches)
+    again, _ = trainer.eval_batch_pair(batches[0])
+    assert np.array_equal(again, np.array(pred_db[:len(again)])) and eng.launch_count() == 2 + len(batches)
+    # the reference-shaped path (both graphs of every pair through the fused kernel) gives the same bits
+    trainer.embed_cache = False
+    fused, _ = trainer.eval_batch_pair(batches[0])
+    assert np.array_equal(fused, again)
+    trainer.embed_cache = True
     # change a weight in place -> next forward must use it
     with torch.no_grad():
         trainer.model.module.scoring_layer.bias.add_(1.0)
-    pred2, _ = trainer.eval_batch_pair(batches[0])
+    pred2, _ = trainer.eval_batch_pair(batches[0])            # the pooled-vector cache is keyed on the weights too
     assert np.abs(pred2 - np.array(pred_db[:len(pred2)])).max() > 1e-3
+    mat = trainer.eval_sequence([f"{root}/data/{n}.json" for n in names]).cpu().numpy()
+    # batches[0] = (0,0), (0,3), (0,250), (3,0) in the order of `names`
+    assert mat.shape == (3, 3)
+    for got, (i, j) in zip(pred2, ((0, 0), (0, 1), (0, 2), (1, 0))):
+        assert abs(float(mat[i, j]) - float(got)) <= 2e-6
     # swapping in another checkpoint through load_state_dict is picked up as well
     ck = np.load(os.path.join(golden_dir, "model_3_20_08.npz"))
     trainer.model.load_state_dict({"module." + k: torch.from_numpy(ck[k].copy()) for k in ck.files})

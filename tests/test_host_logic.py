@@ -79,6 +79,27 @@ def test_process_pair_and_transfer_to_torch_match_reference(tree, golden_dir):
     assert abs(pair["distance"] - 133.13) < 0.01
 
 
+def test_graph_store_matches_reference_host_prep(tree, golden_dir):
+    """GraphStore blocks / targets == what the reference's process_pair + transfer_to_torch produced (golden)."""
+    from sg_pr_b200.graph_store import GraphStore
+    root, _ = tree
+    z = np.load(os.path.join(golden_dir, "ref_fixture_pairs.npz"))
+    for K, N in ((10, 100), (20, 64)):
+        store = GraphStore(N, 12)
+        for a, b in (("0", "250"), ("0", "3"), ("3", "0"), ("0", "0"), ("250", "0"), ("3", "250")):
+            pa, pb = f"{root}/data/{a}.json", f"{root}/data/{b}.json"
+            f1, f2, gt = store.pair_batch([[pa, pb]], 3)
+            p = f"K{K}_N{N}_{a}_{b}_"
+            np.testing.assert_array_equal(f1.numpy(), z[p + "features_1"])
+            np.testing.assert_array_equal(f2.numpy(), z[p + "features_2"])
+            assert gt[0] == float(z[p + "target"]) and store.is_static(pa)
+        assert len(store) == 3                          # three files parsed once each, however many pairs
+    small = GraphStore(16, 12)
+    np.random.seed(0)
+    b1 = small.block(f"{root}/data/0.json")
+    assert b1.shape == (15, 16) and not small.is_static(f"{root}/data/0.json") and float(b1[3:].sum()) == 16.0
+
+
 def test_subsampling_when_graph_exceeds_node_num(tree):
     from sg_pr_b200.parser_sg import sgpr_args
     from sg_pr_b200.sg_net import SGTrainer
