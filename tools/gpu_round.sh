@@ -13,3 +13,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgpr
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/microbench.json; head -c 1500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err; tail -3 gpurun_out/sanitizer.log
 cat gpurun_out/perf_probe.jsonl
 SGPR_B200_LIB=$PWD/tools/variants/lib_tl_base.so timeout 120 python tools/timeline.py 16 > gpurun_out/timeline.txt 2>&1; cat gpurun_out/timeline.txt | awk "NR<4 || /front start|select done|front done|barrier B|back done|layers done|attention|end/" | cut -c1-60
+timeout 300 python tools/eval_batch_bench.py --graphs 1000 --pairs 12800 2>&1 | grep -E "^\{" > gpurun_out/eval_batch_bench.jsonl; cat gpurun_out/eval_batch_bench.jsonl | cut -c1-220
