@@ -226,13 +226,10 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     a.dedup = ctx->dedup;
     const int npl = (N <= 32) ? 1 : (N <= 64) ? 2 : 4;
     const SmemLayout L = make_layout(32 * npl, a.KS);
-    const int per_sm = (npl <= 2) ? 2 : 1;           // graph pipelines ("halves") per CTA; one CTA per SM
+    const int per_sm = (npl <= 2) ? 2 : 1;
     const int capacity = ctx->sm_count * per_sm;
-    if (a.G < 1) return SGPR_OK;
-    // one CTA per SM; with two halves per CTA the second halves only get work once every SM has one graph
-    const int grid = a.G < ctx->sm_count ? a.G : ctx->sm_count;
-    const int threads = kThreads * per_sm;
-    const size_t smem_bytes = static_cast<size_t>(L.total) * per_sm;
+    int grid = a.G < capacity ? a.G : capacity;
+    if (grid < 1) return SGPR_OK;
     a.order = nullptr;
     a.work_ctr = nullptr;
     // more graphs than SMs: place / pop them by measured size so that co-resident CTAs balance (results unchanged)
@@ -250,9 +247,9 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
         if (!resident) a.work_ctr = ctx->d_ctrs + 1;
     }
     switch (npl) {
-        case 1: sgpr_embed_kernel<1><<<grid, threads, smem_bytes, st>>>(a, ctx->pw, ctx->hp); break;
-        case 2: sgpr_embed_kernel<2><<<grid, threads, smem_bytes, st>>>(a, ctx->pw, ctx->hp); break;
-        default: sgpr_embed_kernel<4><<<grid, threads, smem_bytes, st>>>(a, ctx->pw, ctx->hp); break;
+        case 1: sgpr_embed_kernel<1><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
+        case 2: sgpr_embed_kernel<2><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
+        default: sgpr_embed_kernel<4><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
     }
     ctx->launches += 1;
     cudaError_t e = cudaGetLastError();

@@ -54,7 +54,7 @@ namespace sgpr {
 __device__ long long g_timeline[kWarps * 128];
 __device__ int g_smid[1024];
 __device__ long long g_cta_t[2048];
-#define SGPR_TL(slot) do { if (blockIdx.x == 0 && threadIdx.x < kThreads && (threadIdx.x & 31) == 0) g_timeline[(threadIdx.x >> 5) * 128 + (slot)] = clock64(); } while (0)
+#define SGPR_TL(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_timeline[(threadIdx.x >> 5) * 128 + (slot)] = clock64(); } while (0)
 #else
 #define SGPR_TL(slot) do { } while (0)
 #endif
@@ -100,12 +100,6 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int ks) {
 }
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-
-// Barrier over the 256 threads that work on one graph.  The fused kernel hosts up to two graphs per CTA ("halves",
-// one CTA per SM), each with its own named barrier; id 0 with 256 threads is __syncthreads() for a 256-thread CTA.
-__device__ __forceinline__ void half_sync(int bar_id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kThreads) : "memory");
-}
 __device__ __forceinline__ void cmpx(float& a, float& b) {
     const float lo = fminf(a, b), hi = fmaxf(a, b);
     a = lo; b = hi;
@@ -585,7 +579,7 @@ __device__ __forceinline__ float group16_sum(float v) {       // sum over the 16
 
 __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, const float* __restrict__ e2,
                                               const PackedWeights& W, const HeadParams& H, float* __restrict__ scratch,
-                                              float* __restrict__ score_out, int tid, int bar_id) {
+                                              float* __restrict__ score_out, int tid) {
     float* P = scratch;          // [512]  P[b*16+t] = sum_a e1[a] * W[a][b*16+t]   (layers_batch.py:78)
     float* s = scratch + 512;    // [16]
     // all 64 weight loads of a thread's two outputs are issued before the first FMA: one L2 round trip, not eight
@@ -602,7 +596,7 @@ __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, cons
         P[tid] = acc0;
         P[256 + tid] = acc1;
     }
-    half_sync(bar_id);
+    __syncthreads();
     // thread (t, part): t = tid / 16 is the NTN neuron, part = tid % 16 a slice of the contraction
     const int t = tid >> 4, part = tid & 15;
     {
@@ -617,7 +611,7 @@ __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, cons
         blk = group16_sum(blk);
         if (part == 0) s[t] = fmaxf(__fadd_rn(__fadd_rn(bil, blk), __ldg(W.ntn_b + t)), 0.0f);                            // :82
     }
-    half_sync(bar_id);
+    __syncthreads();
     {
         // h[u] = relu(fc1_w[u] . s + fc1_b[u]) with (u, part) = (t, part); then score = sigmoid(fc2_w . h + fc2_b)
         float h = group16_sum(__fmul_rn(s[part], H.fc1_w[t * kT + part]));                                                // sg_net.py:134
@@ -625,7 +619,7 @@ __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, cons
         // one value per half-warp -> collect the 16 h's in warp 0 via shared memory
         if (part == 0) P[t] = __fmul_rn(h, H.fc2_w[t]);
     }
-    half_sync(bar_id);
+    __syncthreads();
     if (tid < 32) {
         float z = (tid < kBn) ? P[tid] : 0.0f;                                                                          // sg_net.py:136
         z = group16_sum(z);
@@ -695,19 +689,12 @@ __device__ __forceinline__ void conv_end_dispatch(const float* sCat, const float
 #ifndef SGPR_MINBLOCKS_SMALL
 #define SGPR_MINBLOCKS_SMALL 2
 #endif
-// One CTA per SM.  For N <= 64 a CTA hosts TWO independent graph pipelines ("halves" of 256 threads, each with its
-// own shared-memory arena, mbarriers and named barrier): which two graphs share an SM is then decided by `order`
-// (heavy with light) instead of by the hardware block scheduler.  Slot of (CTA c, half h) = c + h * gridDim.x.
 template <int NPL>
-__global__ void __launch_bounds__(kThreads * ((NPL <= 2) ? 2 : 1), 1)
+__global__ void __launch_bounds__(kThreads, (NPL <= 2) ? SGPR_MINBLOCKS_SMALL : 1)
 sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) {
     constexpr int NMAX = 32 * NPL;
-    constexpr int HALVES = (NPL <= 2) ? 2 : 1;
-    extern __shared__ __align__(128) unsigned char smem_all[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const SmemLayout L = make_layout(NMAX, A.KS);
-    const int half = (HALVES == 2) ? static_cast<int>(threadIdx.x >> 8) : 0;
-    const int bar_id = 1 + half;
-    unsigned char* smem = smem_all + half * L.total;
     float* sW = reinterpret_cast<float*>(smem + L.w);
     float* sIn = reinterpret_cast<float*>(smem + L.in);
     float* sX = reinterpret_cast<float*>(smem + L.x);
@@ -719,43 +706,40 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar);
     uint8_t* sIdx = smem + L.idx;
     uint8_t* sCnt = smem + L.cnt;
-    __shared__ int sFlagH[HALVES];
-    __shared__ int sLastH[HALVES][kWarps];
-    __shared__ int sSlotH[HALVES];
-    int& sFlag = sFlagH[half];
-    int* sLast = sLastH[half];
-    int& sSlot = sSlotH[half];
+    __shared__ int sFlag;
+    __shared__ int sLast[kWarps];
 
-    const int tid = threadIdx.x & (kThreads - 1), warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = A.N, k = A.k, KS = A.KS;
     uint64_t* barIn = bars;
     uint64_t* barW = bars + 1;
     uint32_t phIn = 0, phW = 0;
 
 #ifdef SGPR_TIMELINE
-    if (tid == 0 && blockIdx.x + half * gridDim.x < 1024) {
+    if (tid == 0 && blockIdx.x < 1024) {
         unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-        g_smid[blockIdx.x + half * gridDim.x] = static_cast<int>(sm);
+        g_smid[blockIdx.x] = static_cast<int>(sm);
         long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_cta_t[2 * (blockIdx.x + half * gridDim.x)] = t;
+        g_cta_t[2 * blockIdx.x] = t;
     }
 #endif
     if (tid == 0) { mbar_init(barIn, 1); mbar_init(barW, 1); fence_mbar_init(); }
     // zero the feature tiles once so rows beyond the active ones never hold junk
     for (int e = tid; e < NMAX * XS; e += kThreads) { sX[e] = 0.0f; sCat[e] = 0.0f; }
     for (int e = tid; e < 2 * NMAX; e += kThreads) sXX[e] = 0.0f;
-    half_sync(bar_id);
+    __syncthreads();
 
     const uint32_t inBytes = static_cast<uint32_t>(kInCh * N * 4);
 
+    __shared__ int sSlot;
 #pragma unroll 1
-    for (int it = blockIdx.x + half * gridDim.x;; it += HALVES * gridDim.x) {
+    for (int it = blockIdx.x;; it += gridDim.x) {
         int slot = it;
         if (A.work_ctr) {                               // dynamic: next heaviest unprocessed graph
             if (tid == 0) sSlot = atomicAdd(A.work_ctr, 1);
-            half_sync(bar_id);
+            __syncthreads();
             slot = sSlot;
-            half_sync(bar_id);
+            __syncthreads();
         }
         if (slot >= A.G) break;
         const int g = A.order ? __ldg(A.order + slot) : slot;
@@ -773,7 +757,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             bulk_g2s(sW, W.w_s2, 64 * 128 * 4, barW);
         }
         if (bulk_ok) { mbar_wait(barIn, phIn); phIn ^= 1; }
-        else { for (int e = tid; e < kInCh * N; e += kThreads) sIn[e] = __ldg(gin + e); half_sync(bar_id); }
+        else { for (int e = tid; e < kInCh * N; e += kThreads) sIn[e] = __ldg(gin + e); __syncthreads(); }
 
         SGPR_TL(1);
         // ---- layer-0 tile (x, y, z, 0) + squared norms for every node, and the last non-zero node ----
@@ -789,7 +773,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         }
         last = __reduce_max_sync(0xffffffffu, last);
         if (lane == 0) sLast[warp] = last;
-        half_sync(bar_id);
+        __syncthreads();
         int R = N;
         if (A.dedup) {
             int m = -1;
@@ -830,7 +814,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
                 __syncwarp();
                 norms_rows(sX, sXX, 16, w0, w1, lane);
             } else {
-                half_sync(bar_id);                               // barrier B: every A|B row is in place, sW is consumed
+                __syncthreads();                               // barrier B: every A|B row is in place, sW is consumed
                 SGPR_TL(8 + l * 8 + 4);
                 if (tid == 0 && D.next_w) { mbar_expect_tx(barW, D.next_bytes); bulk_g2s(sW, D.next_w, D.next_bytes, barW); }
                 // ---- back: gather-max for own rows ----
@@ -853,7 +837,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
                 }
             }
             SGPR_TL(8 + l * 8 + 5);
-            half_sync(bar_id);                                   // barrier A: the next layer's input (or sE) is complete
+            __syncthreads();                                   // barrier A: the next layer's input (or sE) is complete
             SGPR_TL(8 + l * 8 + 6);
             if (tr || tkl) {                                   // debug taps: every trailing pad is a copy of row R-1
                 if (tr) for (int e = tid; e < (N - R) * 64; e += kThreads) tr[(R + e / 64) * 64 + (e & 63)] = tr[(R - 1) * 64 + (e & 63)];
@@ -865,7 +849,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         float* sE = sX;   // node embeddings, stride XS (first 32 columns)
         // every trailing pad is a copy of row R-1
         for (int e = tid; e < (N - R) * kF3; e += kThreads) sE[(R + (e >> 5)) * XS + (e & 31)] = sE[(R - 1) * XS + (e & 31)];
-        half_sync(bar_id);
+        __syncthreads();
         if (A.emb) {
             float* eo = A.emb + static_cast<size_t>(g) * N * kF3;
             for (int e = tid; e < N * kF3; e += kThreads) eo[e] = sE[(e >> 5) * XS + (e & 31)];
@@ -895,14 +879,14 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             }
             sRed[warp * 32 + lane] = colsum;
         }
-        half_sync(bar_id);
+        __syncthreads();
         if (tid < kF3) {
             float s = 0.0f;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) s = __fadd_rn(s, sRed[w * 32 + tid]);
             sCtx[tid] = tanhf(s / static_cast<float>(N));
         }
-        half_sync(bar_id);
+        __syncthreads();
         {   // att[n] = sigmoid(E[n] . ctx); pooled[a] = sum_n E[n][a] att[n]   (per-warp partials, then 8-way sum)
             const float cb = sCtx[lane];
             float* ao = A.pairs ? ((g & 1) ? A.att1 : A.att0) : A.att0;
@@ -932,7 +916,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             }
             sRed[warp * 32 + lane] = pool;
         }
-        half_sync(bar_id);
+        __syncthreads();
         if (tid < kF3) {
             float s = 0.0f;
 #pragma unroll
@@ -945,9 +929,9 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         // ================= pair head, run by whichever CTA of the pair finishes last =================
         if (A.pairs) {
             __threadfence();
-            half_sync(bar_id);
+            __syncthreads();
             if (tid == 0) sFlag = atomicAdd(A.counters + (g >> 1), 1);
-            half_sync(bar_id);
+            __syncthreads();
             if (sFlag == 1) {
                 __threadfence();
                 float* e1 = sRed;        // side 0 pooled
@@ -958,17 +942,17 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
                     (side ? e2 : e1)[a] = v;
                 }
                 if (tid == 0) A.counters[g >> 1] = 0;
-                half_sync(bar_id);
-                pair_head_cta(e1, e2, W, H, sY, A.score + (g >> 1), tid, bar_id);
+                __syncthreads();
+                pair_head_cta(e1, e2, W, H, sY, A.score + (g >> 1), tid);
             }
         }
-        half_sync(bar_id);
+        __syncthreads();
         SGPR_TL(62);
     }
 #ifdef SGPR_TIMELINE
-    if (tid == 0 && blockIdx.x + half * gridDim.x < 1024) {
+    if (tid == 0 && blockIdx.x < 1024) {
         long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_cta_t[2 * (blockIdx.x + half * gridDim.x) + 1] = t;
+        g_cta_t[2 * blockIdx.x + 1] = t;
     }
 #endif
 }

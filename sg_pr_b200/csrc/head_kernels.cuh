@@ -84,7 +84,7 @@ sgpr_score_pairs_kernel(const float* __restrict__ pooled, const int32_t* __restr
             e[tid] = __ldg(pooled + static_cast<size_t>(pair_idx[2 * p + side]) * kF3 + (tid & 31));
         }
         __syncthreads();
-        pair_head_cta(e, e + 32, W, H, scratch, score + p, tid, 0);
+        pair_head_cta(e, e + 32, W, H, scratch, score + p, tid);
         __syncthreads();
     }
 }
