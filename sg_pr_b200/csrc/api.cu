@@ -232,9 +232,11 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     if (grid < 1) return SGPR_OK;
     a.order = nullptr;
     a.work_ctr = nullptr;
-    // more graphs than SMs: place / pop them by measured size so that co-resident CTAs balance (results unchanged)
-    // (skipped when the graphs sit in pinned host memory: the pre-pass would pull them over PCIe a second time)
-    if (ctx->balance && a.G > ctx->sm_count && is_device_memory(a.g0)) {
+    // persistent launches (more graphs than resident CTAs): pop the graphs heaviest-first (LPT) so that the tail of the
+    // launch is short; results are unchanged.  Not worth its ~3 us pre-pass while every graph has its own resident CTA
+    // (the hardware's CTA->SM placement cannot be steered, profiles/r01_variants_timeline.txt), and skipped when the
+    // graphs sit in pinned host memory (the pre-pass would pull them over PCIe a second time).
+    if (ctx->balance && a.G > capacity && is_device_memory(a.g0)) {
         int rc = ensure(ctx->d_order, ctx->order_cap, static_cast<size_t>(2) * a.G);
         if (rc) return rc;
         const int resident = (a.G <= capacity) ? 1 : 0;

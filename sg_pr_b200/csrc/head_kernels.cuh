@@ -13,11 +13,11 @@ namespace sgpr {
 
 // ---- work ordering -------------------------------------------------------------------------------------------
 // Per-graph cost of the fused kernel grows with its active rows R (embed_kernel.cuh: nodes up to the last non-zero
-// one + 1).  This pre-pass measures R for every graph and builds `order[slot] -> graph`:
-//   * resident launches with two CTAs per SM (S < G <= 2S): CTA j and CTA S+j share an SM, CTAs G-S..S-1 have one
-//     to themselves -> the heaviest graphs go to the lone CTAs, the rest are paired heaviest-with-lightest;
-//   * persistent launches (G beyond the resident capacity): descending R, popped through a work counter (LPT).
-// It changes only WHERE each graph runs; results are bit-identical.
+// one + 1).  This pre-pass measures R for every graph and builds `order[slot] -> graph` in descending R; persistent
+// launches (G beyond the resident capacity) pop the slots through a work counter (longest-processing-time-first).
+// (`resident` selects a static heavy-with-light pairing for S < G <= 2S that assumes CTA j and CTA S+j share an SM;
+// the hardware honours that for only ~30 % of the SMs, so the host does not use it — kept for experiments.)
+// It changes only WHEN/WHERE each graph runs; results are bit-identical.
 __global__ void __launch_bounds__(kThreads)
 sgpr_order_kernel(const float* __restrict__ g0, const float* __restrict__ g1, int pairs, int G, int N, int dedup, int S,
                   int resident, int* __restrict__ rows, int* __restrict__ order, int* __restrict__ done_ctr,
