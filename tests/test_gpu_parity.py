@@ -96,9 +96,6 @@ def test_stage_parity_vs_oracle(eng, kitti_state, n, k):
     np.testing.assert_allclose(got["pooled"].cpu().numpy(), want["pooled"].squeeze(-1).numpy(), atol=5e-5, rtol=1e-5)
 
 
-from tests.helpers import NEAR_TIE_REL, near_tie_flips  # noqa: E402
-
-
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_headline_batch_scores(eng, kitti_state, seed):
     """BASELINE config 2 shape: batch 128, 64-node graphs, k=20 — every score within 1e-5 of the oracle, except pairs

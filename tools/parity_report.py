@@ -11,8 +11,8 @@ from sg_pr_b200.engine import Engine
 
 sd = orc.load_state_npz(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "model_kitti.npz"))
 eng = Engine(0); eng.set_weights(sd)
-NEAR = 4e-6     # near tie: (k-th - (k+1)-th reference distance) <= NEAR * (xx_i + max_j xx_j) — the rounding scale of
-                # pd = 2 x_i.x_j - xx_j - xx_i (dgcnn.py:15-17), whose terms are ~sqrt(C) ulps of the squared norms
+NEAR = orc.NEAR_TIE   # near tie: swapped columns differ by <= NEAR * (xx_i + max_j xx_j) in reference distance — the
+                      # rounding scale of pd = 2 x_i.x_j - xx_j - xx_i (dgcnn.py:15-17)
 
 def run(n, k, pairs, seed0, chunk=256):
     rep = {"N": n, "k": k, "pairs": 0, "rows_checked": 0, "rows_equivalent": 0, "rows_exact_tie_swap": 0, "rows_near_tie": 0,
@@ -26,35 +26,31 @@ def run(n, k, pairs, seed0, chunk=256):
         score, a1, a2 = eng.forward_pairs(f1.cuda(), f2.cuda(), k)
         got1 = eng.embed(f1.cuda(), k, trace=True)["knn"].cpu().long()
         got2 = eng.embed(f2.cuda(), k, trace=True)["knn"].cpu().long()
-        first_bad = torch.zeros(b, 2, 2, dtype=torch.bool)      # [pair, side, branch] a non-near-tie first divergence
-        flipped = torch.zeros(b, dtype=torch.bool)
+        first_bad = torch.zeros(b, dtype=torch.bool)          # pair has a first divergence that is a real mismatch
+        flipped = torch.zeros(b, dtype=torch.bool)            # pair has any first divergence (tie swap / near tie / mismatch)
         for side, got in ((1, got1), (2, got2)):
             seen = torch.zeros(b, 2, dtype=torch.bool)
             for layer in range(6):
                 pd, idx, xin = want[f"knn_pd_{side}"][layer], want[f"knn_idx_{side}"][layer], want[f"layer_in_{side}"][layer]
-                ok = orc.knn_sets_equivalent(pd, idx, got[:, layer], xin)
+                code = orc.classify_knn_rows(pd, idx, got[:, layer], xin, NEAR)
                 br = layer // 3
                 fresh = ~seen[:, br]                                  # graphs whose branch has not diverged yet
                 rep["rows_checked"] += int(fresh.sum()) * n
-                rep["rows_equivalent"] += int(ok[fresh].sum())
-                for g, i in (~ok).nonzero().tolist():
+                rep["rows_equivalent"] += int((code[fresh] == 0).sum())
+                for g, i in (code > 0).nonzero().tolist():
                     if seen[g, br]:
                         continue
-                    srt = pd[g, i].sort(descending=True)[0]
-                    xx = (xin[g] * xin[g]).sum(0)
-                    gap_abs = float((srt[k - 1] - srt[k]).abs()) if k < n else 0.0
-                    scale = float(xx[i] + xx.max()) + 1e-30
-                    # the kernel's own pick: how far below the reference's k-th value is its worst selected column?
-                    mine = pd[g, i][got[g, layer, i]].min()
-                    depth = float((srt[k - 1] - mine).abs())
-                    kind = "exact_tie_swap" if depth == 0.0 else ("near_tie" if depth <= NEAR * scale else "mismatch")
+                    kind = {1: "exact_tie_swap", 2: "near_tie", 3: "mismatch"}[int(code[g, i])]
                     rep["rows_" + ("real_mismatch" if kind == "mismatch" else kind)] += 1
-                    if kind == "mismatch": first_bad[g, side - 1, br] = True
+                    if kind == "mismatch": first_bad[g] = True
                     if len(rep["mismatch_rows"]) < 40:
+                        srt = pd[g, i].sort(descending=True)[0]
+                        xx = (xin[g] * xin[g]).sum(0)
+                        depth = float((pd[g, i][idx[g, i]].sort()[0] - pd[g, i][got[g, layer, i]].sort()[0]).abs().max())
                         rep["mismatch_rows"].append({"pair": c0 + g, "side": side, "layer": layer, "row": i, "kind": kind,
-                                                     "gap_abs": gap_abs, "depth_abs": depth, "depth_over_scale": depth / scale,
-                                                     "kth_value": float(srt[k - 1])})
-                div = (~ok).any(dim=1)
+                                                     "gap_abs": float(srt[k - 1] - srt[min(k, n - 1)]), "depth_abs": depth,
+                                                     "depth_over_scale": depth / (float(xx[i] + xx.max()) + 1e-30)})
+                div = (code > 0).any(dim=1)
                 flipped |= div & ~seen[:, br]
                 seen[:, br] |= div
         err = (score.cpu() - want["score"]).abs()
@@ -62,8 +58,8 @@ def run(n, k, pairs, seed0, chunk=256):
         rep["pairs"] += b
         rep["pairs_within_1e-5"] += int(within.sum())
         off = ~within
-        rep["pairs_off_explained_by_near_tie"] += int((off & flipped & ~first_bad.any(dim=(1, 2))).sum())
-        rep["pairs_off_unexplained"] += int((off & (~flipped | first_bad.any(dim=(1, 2)))).sum())
+        rep["pairs_off_explained_by_near_tie"] += int((off & flipped & ~first_bad).sum())
+        rep["pairs_off_unexplained"] += int((off & (~flipped | first_bad)).sum())
         if (~flipped).any():
             rep["max_abs_dscore_unflipped_pairs"] = max(rep["max_abs_dscore_unflipped_pairs"], float(err[~flipped].max()))
             rep["max_abs_datt_unflipped"] = max(rep["max_abs_datt_unflipped"], float((a1.cpu() - want["att_1"]).abs()[~flipped].max()))
