@@ -413,6 +413,9 @@ int sgpr_debug_ctas(int* smid1024, long long* t2048) {
     if (cudaMemcpyFromSymbol(smid1024, g_smid, sizeof(int) * 1024) != cudaSuccess) return -2;
     return cudaMemcpyFromSymbol(t2048, g_cta_t, sizeof(long long) * 2048) == cudaSuccess ? 0 : -2;
 }
+int sgpr_debug_cta_graphs(int* g1024) {
+    return cudaMemcpyFromSymbol(g1024, g_cta_g, sizeof(int) * 1024) == cudaSuccess ? 0 : -2;
+}
 #endif
 
 size_t sgpr_packed_size(void) { return make_offsets().total; }

@@ -54,6 +54,7 @@ namespace sgpr {
 __device__ long long g_timeline[kWarps * 128];
 __device__ int g_smid[1024];
 __device__ long long g_cta_t[2048];
+__device__ int g_cta_g[1024];      // graph (and its active rows << 16) each CTA processed last
 #define SGPR_TL(slot) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_timeline[(threadIdx.x >> 5) * 128 + (slot)] = clock64(); } while (0)
 #else
 #define SGPR_TL(slot) do { } while (0)
@@ -781,6 +782,9 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             for (int w = 0; w < kWarps; ++w) m = max(m, sLast[w]);
             R = min(m + 2, N);      // nodes up to the last non-zero one, plus one representative of the trailing zero pads
         }
+#ifdef SGPR_TIMELINE
+        if (tid == 0 && blockIdx.x < 1024) g_cta_g[blockIdx.x] = g | (R << 16);
+#endif
         // rows owned by this warp for the whole graph
         const int rpw = (R + kWarps - 1) / kWarps;
         const int w0 = min(R, warp * rpw), w1 = min(R, w0 + rpw);
