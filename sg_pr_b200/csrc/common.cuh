@@ -5,7 +5,10 @@
 
 namespace sgpr {
 
-constexpr int kThreads = 256;          // one CTA = 8 warps works on one graph
+#ifndef SGPR_THREADS
+#define SGPR_THREADS 256
+#endif
+constexpr int kThreads = SGPR_THREADS; // one CTA (8 warps by default) works on one graph
 constexpr int kWarps   = kThreads / 32;
 
 constexpr int kLabels  = 12;           // sg_net.py:200-202

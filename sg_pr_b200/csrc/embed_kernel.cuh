@@ -64,7 +64,7 @@ struct EmbedArgs {
     const float* g0;        // graphs of side 0 (or all graphs when !pairs)   [*, 15, N]
     const float* g1;        // graphs of side 1 (pairs mode)
     int G;                  // number of graphs to embed (2*B in pairs mode: g = 2*b + side)
-    int N, k, KS;           // KS = k rounded up to 4 (neighbour-list row stride in bytes)
+    int N, k, KS;           // KS = k rounded up to 4 (neighbour-list row stride in 16-bit entries)
     int pairs;
     int dedup;              // 1: collapse trailing all-zero nodes into one row (exact); 0: process every node
     float* pooled;          // [G][32]
@@ -94,7 +94,7 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int ks) {
     L.xx = o;  o += 2 * nmax * 4;              // squared norms of the layer input (+ layer-0 copy); later attention scores
     L.red = o; o += (kWarps * 32 + 64) * 4;
     L.bar = o; o += 16;
-    L.idx = o; o += ((nmax * ks + 15) / 16) * 16;
+    L.idx = o; o += ((nmax * ks * 2 + 15) / 16) * 16;   // neighbour lists: ks 16-bit entries per node
     L.cnt = o; o += ((nmax + 15) / 16) * 16;
     L.total = o;
     return L;
@@ -142,156 +142,201 @@ __device__ __forceinline__ float pick_uniform(const float (&v)[EPL], int jt) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Distance rows of NR own nodes against all R columns (dgcnn.py:15-17):
+// Distance rows of NR own nodes against all columns (dgcnn.py:15-17):
 //     pd[i][c] = (2*dot(x_i,x_c) - xx_c) - xx_i      == -xx - inner - xx^T with inner = -2*dot, same rounding order
-// lane <-> column (c = lane + 32q).  Row i is stored in its own A|B row: sY[i*YS + (c>>5)*33 + (c&31)].
+// lane <-> column (c = lane + 32q).  Row i is stored in its own A|B row, sY[i*YS + c], for EVERY c < 32*NPL so that the
+// selection can read it with unconditional vector loads: columns R <= c < N (the collapsed zero pads) carry the pad
+// class's value pd[i][R-1], columns >= N carry -inf.  Only the NQ = ceil(R/32) column blocks that hold active nodes
+// are computed.
 // ------------------------------------------------------------------------------------------------------------
-template <int NPL, int NR>
+template <int NPL, int NQ, int NR>
 __device__ __forceinline__ void gram_rows(const float* __restrict__ sXt, const float* __restrict__ sXX,
-                                          float* __restrict__ sY, int c4n, int R, int r0, int lane) {
-    const int nq = (R + 31) >> 5;
-    float2 acc[NR][NPL];
+                                          float* __restrict__ sY, int c4n, int R, int N, int r0, int lane) {
+    float2 acc[NR][NQ];
 #pragma unroll
     for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) acc[r][q] = make_float2(0.0f, 0.0f);
+        for (int q = 0; q < NQ; ++q) acc[r][q] = make_float2(0.0f, 0.0f);
     const float* pa = sXt + r0 * XS;
     const float* pb = sXt + lane * XS;
 #if SGPR_GRAM_V == 1
 #pragma unroll 4
     for (int c = 0; c < c4n; ++c) {
-        float4 a[NR], b[NPL];
+        float4 a[NR], b[NQ];
 #pragma unroll
         for (int r = 0; r < NR; ++r) a[r] = *reinterpret_cast<const float4*>(pa + r * XS + 4 * c);
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) b[q] = (q < nq) ? *reinterpret_cast<const float4*>(pb + 32 * q * XS + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < NQ; ++q) b[q] = *reinterpret_cast<const float4*>(pb + 32 * q * XS + 4 * c);
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) {
-            if (q < nq) {
+        for (int q = 0; q < NQ; ++q) {
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    acc[r][q] = ffma2(make_float2(a[r].x, a[r].y), make_float2(b[q].x, b[q].y), acc[r][q]);
-                    acc[r][q] = ffma2(make_float2(a[r].z, a[r].w), make_float2(b[q].z, b[q].w), acc[r][q]);
-                }
+            for (int r = 0; r < NR; ++r) {
+                acc[r][q] = ffma2(make_float2(a[r].x, a[r].y), make_float2(b[q].x, b[q].y), acc[r][q]);
+                acc[r][q] = ffma2(make_float2(a[r].z, a[r].w), make_float2(b[q].z, b[q].w), acc[r][q]);
             }
         }
     }
 #else
     // software pipeline: the loads of channel group c+1 are in flight while the FFMA2s of group c issue
-    float4 a[NR], b[NPL];
+    float4 a[NR], b[NQ];
 #pragma unroll
     for (int r = 0; r < NR; ++r) a[r] = *reinterpret_cast<const float4*>(pa + r * XS);
 #pragma unroll
-    for (int q = 0; q < NPL; ++q) b[q] = (q < nq) ? *reinterpret_cast<const float4*>(pb + 32 * q * XS) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < NQ; ++q) b[q] = *reinterpret_cast<const float4*>(pb + 32 * q * XS);
 #pragma unroll 2
     for (int c = 0; c < c4n; ++c) {
-        float4 an[NR], bn[NPL];
+        float4 an[NR], bn[NQ];
         const int cn = min(c + 1, c4n - 1);
 #pragma unroll
         for (int r = 0; r < NR; ++r) an[r] = *reinterpret_cast<const float4*>(pa + r * XS + 4 * cn);
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) bn[q] = (q < nq) ? *reinterpret_cast<const float4*>(pb + 32 * q * XS + 4 * cn) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < NQ; ++q) bn[q] = *reinterpret_cast<const float4*>(pb + 32 * q * XS + 4 * cn);
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) {
-            if (q < nq) {
+        for (int q = 0; q < NQ; ++q) {
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    acc[r][q] = ffma2(make_float2(a[r].x, a[r].y), make_float2(b[q].x, b[q].y), acc[r][q]);
-                    acc[r][q] = ffma2(make_float2(a[r].z, a[r].w), make_float2(b[q].z, b[q].w), acc[r][q]);
-                }
+            for (int r = 0; r < NR; ++r) {
+                acc[r][q] = ffma2(make_float2(a[r].x, a[r].y), make_float2(b[q].x, b[q].y), acc[r][q]);
+                acc[r][q] = ffma2(make_float2(a[r].z, a[r].w), make_float2(b[q].z, b[q].w), acc[r][q]);
             }
         }
 #pragma unroll
         for (int r = 0; r < NR; ++r) a[r] = an[r];
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) b[q] = bn[q];
+        for (int q = 0; q < NQ; ++q) b[q] = bn[q];
     }
 #endif
+    float pd[NR][NQ];
 #pragma unroll
-    for (int q = 0; q < NPL; ++q) {
-        const int c = lane + 32 * q;
-        if (c < R) {
-            const float xxc = sXX[c];
+    for (int q = 0; q < NQ; ++q) {
+        const float xxc = sXX[lane + 32 * q];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const float dot = __fadd_rn(acc[r][q].x, acc[r][q].y);
-                const float t = __fsub_rn(__fmul_rn(2.0f, dot), xxc);
-                sY[(r0 + r) * YS + q * 33 + lane] = __fsub_rn(t, sXX[r0 + r]);
-            }
+        for (int r = 0; r < NR; ++r) {
+            const float dot = __fadd_rn(acc[r][q].x, acc[r][q].y);
+            const float t = __fsub_rn(__fmul_rn(2.0f, dot), xxc);
+            pd[r][q] = __fsub_rn(t, sXX[r0 + r]);
+        }
+    }
+    const int qp = (R - 1) >> 5, lp = (R - 1) & 31;             // where column R-1 lives
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        float own = pd[r][0];
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) own = (qp == q) ? pd[r][q] : own;
+        const float padv = __shfl_sync(0xffffffffu, own, lp);
+        float* dst = sY + (r0 + r) * YS + lane;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            const int c = lane + 32 * q;
+            float val = (c < N) ? padv : -INFINITY;
+            if (q < NQ) val = (c < R) ? pd[r][q] : val;
+            dst[32 * q] = val;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // k-NN selection (dgcnn.py:19 `topk`) for up to 8 own rows r0 .. r0+nr-1: pick the k largest of the row's N
-// distances, ties at the k-th value to the lowest column index.  Columns >= R that are < N all carry the pad-class
-// value pd[i][R-1]; columns >= N are -inf.  Only the SET matters downstream (max over neighbours), so the list is
-// emitted in ascending column order with the pad class, if selected, represented once by column R-1, then padded
-// to a multiple of 4.
+// distances, ties at the k-th value to the lowest column index.  The row holds 32*NPL values (gram_rows): columns
+// R <= c < N all carry the pad-class value pd[i][R-1], columns >= N are -inf.  Only the SET matters downstream (max
+// over neighbours), so the list is emitted in ascending column order with the pad class, if selected, represented
+// once by column R-1, then padded to a multiple of 4 entries.  A list entry is the 16-bit word offset `column * scale`
+// of the neighbour's row in the tile the gather reads (scale = row stride of that tile).
 //
 // 4 lanes cooperate on a row (lane = sub*8 + row), each holding EPL = NMAX/4 consecutive columns in registers:
-// in-register sort, two cross-lane bitonic merges, threshold = element NMAX-k of the sorted row, then count and
-// emit passes over the unsorted values.
+// in-register sort, two cross-lane bitonic merges — the last one pruned to the single output position that is the
+// threshold (element NMAX-k of the sorted row) — then count and emit passes over the unsorted values.
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fgt_mask(float a, float b) {          // all-ones if a > b (one FSET)
+    uint32_t m;
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
+    return m;
+}
+__device__ __forceinline__ uint32_t feq_mask(float a, float b) {
+    uint32_t m;
+    asm("set.eq.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
+    return m;
+}
+
 template <int NPL>
-__device__ __forceinline__ void select_rows(const float* __restrict__ sY, uint8_t* __restrict__ sIdx,
+__device__ __forceinline__ void select_rows(const float* __restrict__ sY, uint16_t* __restrict__ sIdx,
                                             uint8_t* __restrict__ sCnt, uint8_t* __restrict__ trace, int R, int N, int k,
-                                            int KS, int r0, int nr, int lane) {
+                                            int KS, int scale, int r0, int nr, int lane) {
     constexpr int NMAX = 32 * NPL;
     constexpr int EPL = 8 * NPL;
     const int sub = lane >> 3, rl = lane & 7;
     const int row = r0 + min(rl, nr - 1);             // lanes beyond nr shadow the last row (they never store)
     const bool live = rl < nr;
     const float* prow = sY + row * YS;
-    const float padval = prow[((R - 1) >> 5) * 33 + ((R - 1) & 31)];
     const int c0 = sub * EPL;
-    const float* pblk = prow + (c0 >> 5) * 33 + (c0 & 31);
     float o[EPL], v[EPL];
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) {
-        const int c = c0 + j;
-        const float x = (c < R) ? pblk[j] : ((c < N) ? padval : -INFINITY);
-        o[j] = x;
-        v[j] = x;
+    for (int j4 = 0; j4 < EPL / 4; ++j4) {
+        const float4 x = *reinterpret_cast<const float4*>(prow + c0 + 4 * j4);
+        o[4 * j4] = x.x; o[4 * j4 + 1] = x.y; o[4 * j4 + 2] = x.z; o[4 * j4 + 3] = x.w;
     }
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) v[j] = o[j];
     sort_regs<EPL>(v);
     // ---- merge across the 4 lanes of the row (bitonic "flip" merges; every exchange ascending) ----
+    {   // lanes (0,1) and (2,3): mirror exchange, element j meets the partner's element EPL-1-j, then sort in place
+        const bool keep_min = (sub & 1) == 0;
 #pragma unroll
-    for (int m = 1; m <= 2; m <<= 1) {
-        {   // mirror exchange with lane sub ^ (2m-1): element j meets the partner's element EPL-1-j
-            const bool keep_min = (sub & m) == 0;
-#pragma unroll
-            for (int j = 0; j < EPL / 2; ++j) {
-                const float pa = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - j], (2 * m - 1) * 8);
-                const float pb = __shfl_xor_sync(0xffffffffu, v[j], (2 * m - 1) * 8);
-                v[j] = keep_min ? fminf(v[j], pa) : fmaxf(v[j], pa);
-                v[EPL - 1 - j] = keep_min ? fminf(v[EPL - 1 - j], pb) : fmaxf(v[EPL - 1 - j], pb);
-            }
-        }
-        if (m == 2) {   // cross-lane half-cleaner over distance EPL (partner sub ^ 1)
-            const bool keep_min = (sub & 1) == 0;
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-                const float p = __shfl_xor_sync(0xffffffffu, v[j], 8);
-                v[j] = keep_min ? fminf(v[j], p) : fmaxf(v[j], p);
-            }
+        for (int j = 0; j < EPL / 2; ++j) {
+            const float pa = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - j], 8);
+            const float pb = __shfl_xor_sync(0xffffffffu, v[j], 8);
+            v[j] = keep_min ? fminf(v[j], pa) : fmaxf(v[j], pa);
+            v[EPL - 1 - j] = keep_min ? fminf(v[EPL - 1 - j], pb) : fmaxf(v[EPL - 1 - j], pb);
         }
 #pragma unroll
-        for (int d = EPL / 2; d >= 1; d >>= 1)     // in-register half-cleaners
+        for (int d = EPL / 2; d >= 1; d >>= 1)
 #pragma unroll
             for (int j = 0; j < EPL; ++j)
                 if ((j & d) == 0) cmpx(v[j], v[j | d]);
     }
-    // ---- threshold: k-th largest = sorted position NMAX - k ----
+    {   // pairs (0,1) with (2,3): mirror exchange with lane sub^3, half-cleaner with lane sub^1
+        const bool keep_lo = (sub & 2) == 0;
+#pragma unroll
+        for (int j = 0; j < EPL / 2; ++j) {
+            const float pa = __shfl_xor_sync(0xffffffffu, v[EPL - 1 - j], 24);
+            const float pb = __shfl_xor_sync(0xffffffffu, v[j], 24);
+            v[j] = keep_lo ? fminf(v[j], pa) : fmaxf(v[j], pa);
+            v[EPL - 1 - j] = keep_lo ? fminf(v[EPL - 1 - j], pb) : fmaxf(v[EPL - 1 - j], pb);
+        }
+        const bool keep_min = (sub & 1) == 0;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const float p = __shfl_xor_sync(0xffffffffu, v[j], 8);
+            v[j] = keep_min ? fminf(v[j], p) : fmaxf(v[j], p);
+        }
+    }
+    // ---- threshold: k-th largest = sorted position P = NMAX - k, i.e. element P % EPL of lane sub = P / EPL.  Each
+    // lane now holds a bitonic-cleaned block whose in-place sort would be log2(EPL) half-cleaner stages; only the one
+    // output position is needed, so every stage keeps just the half that feeds it (min or max by that bit of P).
     const int P = NMAX - k;
-    const float tl = pick_uniform<EPL>(v, P % EPL);
+    const int pe = P % EPL;
+    float tl;
+    {
+        float cur[EPL / 2];
+        {
+            const bool up = (pe & (EPL / 2)) != 0;
+#pragma unroll
+            for (int j = 0; j < EPL / 2; ++j) cur[j] = up ? fmaxf(v[j], v[j + EPL / 2]) : fminf(v[j], v[j + EPL / 2]);
+        }
+#pragma unroll
+        for (int d = EPL / 4; d >= 1; d >>= 1) {
+            const bool up = (pe & d) != 0;
+#pragma unroll
+            for (int j = 0; j < d; ++j) cur[j] = up ? fmaxf(cur[j], cur[j + d]) : fminf(cur[j], cur[j + d]);
+        }
+        tl = cur[0];
+    }
     const float thr = __shfl_sync(0xffffffffu, tl, rl + (P / EPL) * 8);
     // ---- count pass: per-lane bit masks over its EPL columns ----
     uint32_t mgt = 0, meq = 0;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
-        mgt |= (o[j] > thr) ? (1u << j) : 0u;
-        meq |= (o[j] == thr) ? (1u << j) : 0u;
+        mgt |= fgt_mask(o[j], thr) & (1u << j);
+        meq |= feq_mask(o[j], thr) & (1u << j);
     }
     const int ne = min(max(R - c0, 0), EPL);          // emittable columns of this lane (c < R)
     const uint32_t em = (ne >= 32) ? 0xffffffffu : ((1u << ne) - 1u);
@@ -315,7 +360,7 @@ __device__ __forceinline__ void select_rows(const float* __restrict__ sY, uint8_
     }
     // ---- emit pass ----
     if (live) {
-        uint8_t* list = sIdx + row * KS;
+        uint16_t* list = sIdx + row * KS;
         uint32_t ties = meq & em, keep = 0;
         for (int t = min(max(need - eq_before, 0), eq_e); t > 0; --t) {   // lowest t tied columns (t is 0 or 1 but for pads)
             const uint32_t low = ties & (0u - ties);
@@ -324,24 +369,25 @@ __device__ __forceinline__ void select_rows(const float* __restrict__ sY, uint8_
         }
         uint32_t taken = (mgt & em) | keep;
         int pos = base;
+        uint16_t last = 0;
         while (taken) {
             const int j = __ffs(taken) - 1;
-            list[pos++] = static_cast<uint8_t>(c0 + j);
+            last = static_cast<uint16_t>((c0 + j) * scale);
+            list[pos++] = last;
             taken &= taken - 1u;
         }
         // the lane that wrote the last entry pads the list to a multiple of 4 (repeats are harmless under max)
         if (pos == total && pos > base) {
-            const uint8_t last = list[pos - 1];
             for (int e = total; e < ((total + 3) & ~3); ++e) list[e] = last;
         }
         if (sub == 0) sCnt[row] = static_cast<uint8_t>((total + 3) & ~3);
         // debug tap: the k columns an undeduplicated run lists (pad class expanded, lowest index first)
         if (trace && sub == 0) {
             int ngt = 0;
-            for (int c = 0; c < N; ++c) ngt += ((c < R) ? prow[(c >> 5) * 33 + (c & 31)] : padval) > thr;
+            for (int c = 0; c < N; ++c) ngt += prow[c] > thr;
             int nd = k - ngt, p = 0;
             for (int c = 0; c < N && p < k; ++c) {
-                const float x = (c < R) ? prow[(c >> 5) * 33 + (c & 31)] : padval;
+                const float x = prow[c];
                 if (x > thr || (x == thr && nd-- > 0)) trace[row * k + p++] = static_cast<uint8_t>(c);
             }
         }
@@ -465,11 +511,12 @@ __device__ __forceinline__ void norms_rows(const float* __restrict__ sT, float* 
 // ------------------------------------------------------------------------------------------------------------
 // Gather-max + BN + LeakyReLU for own rows (sg_net.py:85-86 etc.): for node i and channel c
 //     out = LReLU(alpha_c * ((max_{j in knn(i)} A[j][c] - A[i][c]) + B[i][c]) + beta_c)
-// sY row = [A(0..COUT) | B(COUT..2COUT)]; a lane owns COUT/32 channels.  Neighbour rows are fetched 12 at a time
-// (three packed index words, then twelve independent loads) to keep the shared-memory pipe busy.
+// sY row = [A(0..COUT) | B(COUT..2COUT)]; a lane owns COUT/32 channels.  The neighbour list holds 16-bit word offsets
+// (j*YS) of the neighbour rows; 4*GW of them are fetched per step (GW 8-byte list words, then 4*GW independent row
+// loads) to keep the shared-memory pipe busy.
 // ------------------------------------------------------------------------------------------------------------
 template <int COUT>
-__device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const uint8_t* __restrict__ sIdx,
+__device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const uint16_t* __restrict__ sIdx,
                                             const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ ab,
                                             float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane) {
     constexpr int CPL = COUT / 32;
@@ -483,25 +530,26 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
         float m[CPL];
 #pragma unroll
         for (int p = 0; p < CPL; ++p) m[p] = -INFINITY;
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(sIdx + i * KS);
-        const int nw = sCnt[i] >> 2;                    // packed index words (4 neighbours each), >= 1
+        const uint2* row = reinterpret_cast<const uint2*>(sIdx + i * KS);
+        const int nw = sCnt[i] >> 2;                    // list words (4 neighbours each), >= 1
         float ai[CPL], bi[CPL];
 #pragma unroll
         for (int p = 0; p < CPL; ++p) { ai[p] = base[i * YS + p]; bi[p] = base[i * YS + COUT + p]; }
 #pragma unroll 1
         for (int t = 0; t < nw; t += GW) {
-            uint32_t wd[GW];
+            uint2 wd[GW];
 #pragma unroll
             for (int q = 0; q < GW; ++q) wd[q] = row[min(t + q, nw - 1)];      // tail words repeat (harmless under max)
             float v[4 * GW][CPL];
 #pragma unroll
             for (int e = 0; e < 4 * GW; ++e) {
-                const int j = (wd[e >> 2] >> (8 * (e & 3))) & 0xff;
+                const uint32_t w = (e & 2) ? wd[e >> 2].y : wd[e >> 2].x;
+                const uint32_t off = (e & 1) ? (w >> 16) : (w & 0xffffu);
                 if constexpr (CPL == 2) {
-                    const float2 a = *reinterpret_cast<const float2*>(base + j * YS);
+                    const float2 a = *reinterpret_cast<const float2*>(base + off);
                     v[e][0] = a.x; v[e][1] = a.y;
                 } else {
-                    v[e][0] = base[j * YS];
+                    v[e][0] = base[off];
                 }
             }
 #pragma unroll
@@ -525,9 +573,10 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
 // xyz layer 1 (3 -> 64) in the reference's direct form (sg_net.py:84-86) for own rows: per edge
 //     e = wa0*d0 + wa1*d1 + wa2*d2  (d = x_j - x_i, sequential FMA), max over the edges, then the centre
 //     terms wb.x_i appended in the same sequential order (monotone in e, so they commute with the max).
-// A lane owns output channels 2*lane, 2*lane+1; neighbour coordinates come from the layer-0 node tile.
+// A lane owns output channels 2*lane, 2*lane+1; neighbour coordinates come from the layer-0 node tile (list entries
+// are word offsets j*XS into it).
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uint8_t* __restrict__ sIdx,
+__device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uint16_t* __restrict__ sIdx,
                                          const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ s1,
                                          float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane) {
     // sT: the (x, y, z, 0) node tile of layer 0 (stride XS).  p0 = {wa0,wa1,wa2,wb0}, p1 = {wb1,wb2,alpha,beta} of
@@ -540,16 +589,16 @@ __device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uin
     for (int i = r0; i < r1; ++i) {
         const float4 xi = *reinterpret_cast<const float4*>(sT + i * XS);
         float m0 = -INFINITY, m1 = -INFINITY;
-        const uint8_t* row = sIdx + i * KS;
-        const int cnt = sCnt[i];
+        const uint2* row = reinterpret_cast<const uint2*>(sIdx + i * KS);
+        const int nw = sCnt[i] >> 2;
 #pragma unroll 1
-        for (int t = 0; t < cnt; t += 4) {
-            const uchar4 jj = *reinterpret_cast<const uchar4*>(row + t);
-            const int js[4] = {jj.x, jj.y, jj.z, jj.w};
+        for (int t = 0; t < nw; ++t) {
+            const uint2 wd = row[t];
+            const uint32_t js[4] = {wd.x & 0xffffu, wd.x >> 16, wd.y & 0xffffu, wd.y >> 16};
             float e0[4], e1[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float4 xj = *reinterpret_cast<const float4*>(sT + js[u] * XS);
+                const float4 xj = *reinterpret_cast<const float4*>(sT + js[u]);
                 const float d0 = __fsub_rn(xj.x, xi.x), d1 = __fsub_rn(xj.y, xi.y), d2 = __fsub_rn(xj.z, xi.z);
                 e0[u] = fmaf(p0.z, d2, fmaf(p0.y, d1, __fmul_rn(p0.x, d0)));
                 e1[u] = fmaf(q0.z, d2, fmaf(q0.y, d1, __fmul_rn(q0.x, d0)));
@@ -584,7 +633,8 @@ __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, cons
     float* P = scratch;          // [512]  P[b*16+t] = sum_a e1[a] * W[a][b*16+t]   (layers_batch.py:78)
     float* s = scratch + 512;    // [16]
     // all 64 weight loads of a thread's two outputs are issued before the first FMA: one L2 round trip, not eight
-    {
+    const bool act = tid < 256;                  // the head is laid out for 256 threads; extra warps only keep the barriers
+    if (act) {
         float w0[kF3], w1[kF3];
 #pragma unroll
         for (int a = 0; a < kF3; ++a) {
@@ -600,7 +650,7 @@ __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, cons
     __syncthreads();
     // thread (t, part): t = tid / 16 is the NTN neuron, part = tid % 16 a slice of the contraction
     const int t = tid >> 4, part = tid & 15;
-    {
+    if (act) {
         float bil = fmaf(P[(2 * part + 1) * kT + t], e2[2 * part + 1], __fmul_rn(P[(2 * part) * kT + t], e2[2 * part]));   // :79
         float blk = 0.0f;                                                                                                 // :80-81
 #pragma unroll
@@ -613,7 +663,7 @@ __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, cons
         if (part == 0) s[t] = fmaxf(__fadd_rn(__fadd_rn(bil, blk), __ldg(W.ntn_b + t)), 0.0f);                            // :82
     }
     __syncthreads();
-    {
+    if (act) {
         // h[u] = relu(fc1_w[u] . s + fc1_b[u]) with (u, part) = (t, part); then score = sigmoid(fc2_w . h + fc2_b)
         float h = group16_sum(__fmul_rn(s[part], H.fc1_w[t * kT + part]));                                                // sg_net.py:134
         h = fmaxf(__fadd_rn(h, H.fc1_b[t]), 0.0f);
@@ -643,7 +693,7 @@ struct FrontCtx {
     const float* sXX;
     float* sY;
     const float* sW;
-    uint8_t* sIdx;
+    uint16_t* sIdx;
     uint8_t* sCnt;
     uint8_t* trace_knn;
     int c4n, cout, R, N, k, KS, layer;
@@ -666,10 +716,13 @@ struct FrontCtx {
 template <int NPL>
 __device__ __forceinline__ void front_pass(const FrontCtx& F, int r0, int nr, int lane, uint64_t* barW, uint32_t& phW,
                                            bool& waited) {
-    SGPR_NR_SWITCH(nr, (gram_rows<NPL, NR>(F.sXt, F.sXX, F.sY, F.c4n, F.R, r0, lane)))
+    // column blocks holding active nodes: all of them, or (small graphs) the lower half
+    constexpr int NQH = (NPL >= 2) ? NPL / 2 : 1;
+    if (F.R <= 32 * NQH) { SGPR_NR_SWITCH(nr, (gram_rows<NPL, NQH, NR>(F.sXt, F.sXX, F.sY, F.c4n, F.R, F.N, r0, lane))) }
+    else                 { SGPR_NR_SWITCH(nr, (gram_rows<NPL, NPL, NR>(F.sXt, F.sXX, F.sY, F.c4n, F.R, F.N, r0, lane))) }
     __syncwarp();
     SGPR_TL(8 + F.layer * 8 + 1);
-    select_rows<NPL>(F.sY, F.sIdx, F.sCnt, F.trace_knn, F.R, F.N, F.k, F.KS, r0, nr, lane);
+    select_rows<NPL>(F.sY, F.sIdx, F.sCnt, F.trace_knn, F.R, F.N, F.k, F.KS, (F.layer == 0) ? XS : YS, r0, nr, lane);
     __syncwarp();                                      // the distance rows are dead; A|B may overwrite them
     SGPR_TL(8 + F.layer * 8 + 2);
     if (F.layer != 0) {
@@ -705,7 +758,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
     float* sXX0 = sXX + NMAX;                                  // [NMAX] norms of the layer-0 coordinates
     float* sRed = reinterpret_cast<float*>(smem + L.red);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar);
-    uint8_t* sIdx = smem + L.idx;
+    uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + L.idx);
     uint8_t* sCnt = smem + L.cnt;
     __shared__ int sFlag;
     __shared__ int sLast[kWarps];
