@@ -94,3 +94,33 @@ def test_score_matrix_matches_pairwise(kitti_state):
         for j in range(6):
             s = orc.forward_pairs(g[i:i + 1], g[j:j + 1], 20, kitti_state)["score"][0]
             assert abs(float(mat[i, j]) - float(s)) <= 1e-6
+
+
+# ---- training step: oracle restatement vs two optimiser steps of the reference itself ----------------
+@pytest.mark.parametrize("tag", ["n32_k10", "n64_k20"])
+def test_train_step_matches_reference(tag):
+    from oracle import sgpr_oracle_train as ort
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_train_{tag}.npz"))
+    sd = orc.load_state_npz(os.path.join(os.path.dirname(__file__), "golden", "model_kitti.npz"))
+    f1, f2 = torch.from_numpy(g["features_1"]), torch.from_numpy(g["features_2"])
+    target, k = torch.from_numpy(g["target"]), int(g["K"])
+    adam = ort.new_adam_state(sd)
+    for step in (1, 2):
+        r = ort.train_step(sd, f1, f2, target, k, adam, float(g["lr"]), float(g["weight_decay"]))
+        np.testing.assert_allclose(r["pred"].numpy(), g[f"pred{step}"], rtol=0, atol=2e-6)
+        assert abs(r["loss"] - float(g[f"loss{step}"])) < 2e-6
+        if step == 1:
+            for name, grad in r["grads"].items():
+                ref = g["grad1." + name]
+                scale = max(float(np.abs(ref).max()), 1e-8)
+                assert float(np.abs(grad.numpy() - ref).max()) <= 2e-4 * scale, name
+        for name, value in sd.items():
+            ref = g[f"state{step}." + name]
+            if name.endswith("num_batches_tracked"):
+                assert int(value) == int(ref)                    # +1 per side per step (two BatchNorm calls)
+                continue
+            # Adam's first steps move every weight by ~lr whatever the gradient's size, and for gradients near its eps
+            # (1e-8) the direction itself is rounding noise: nearly all elements agree to 2e-5, none is off by > lr
+            diff = np.abs(value.numpy() - ref)
+            ok = diff <= 2e-5 + 1e-5 * np.abs(ref)
+            assert ok.mean() >= 0.995 and diff.max() <= float(g["lr"]) * step, f"{name} step {step}: {diff.max()}"
