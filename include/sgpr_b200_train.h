@@ -1,0 +1,85 @@
+/*
+ * sgpr_b200_train.h — C ABI of the B200-native SG_PR TRAINING step (BASELINE config 3).
+ *
+ * The reference has no native layer; what this replaces is the device work of
+ *     SGTrainer.process_batch(batch, training=True)                       /root/reference/sg_net.py:312-345
+ * from the point where the batch tensors exist:
+ *     optimizer.zero_grad(); prediction = model(data)   (SG.forward in train mode, sg_net.py:112-138: the seven
+ *                                                        BatchNorm layers of sg_net.py:50-76 use batch statistics,
+ *                                                        one BatchNorm batch per side, sg_net.py:123-124)
+ *     losses = mean(binary_cross_entropy(prediction, target))             sg_net.py:335
+ *     losses.backward(); optimizer.step()               (Adam, lr, weight_decay — sg_net.py:337-338, 351-352)
+ *
+ * State lives on the device as ONE flat fp32 vector: the trainable parameters in their state_dict shapes followed by
+ * the BatchNorm running statistics (sgpr_train_layout lists name / offset / size of every tensor, names are the
+ * checkpoint keys of sg_net.py:164-174 without the "module." prefix).  The int64 `num_batches_tracked` counters are
+ * not part of it: each BatchNorm runs twice per step (once per side), the host adds 2 per step.
+ *
+ * Conventions are those of sgpr_b200.h: fp32, contiguous, device pointers, work enqueued on `stream` without
+ * synchronising, 0 / negative SGPR_E_* return codes with sgpr_last_error() text.  No CPU implementation exists behind
+ * this ABI.
+ */
+#ifndef SGPR_B200_TRAIN_H
+#define SGPR_B200_TRAIN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "sgpr_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgpr_train sgpr_train;   /* opaque: device state vector, Adam moments, workspace */
+
+/* Flat layout: *count tensors; names[i], offsets[i] (floats), sizes[i] (floats).  The first *n_params tensors are
+ * trainable (sgpr_train_param_count floats in total), the rest are running_mean / running_var buffers. */
+int     sgpr_train_layout(int* count, int* n_params, const char* const** names, const int64_t** offsets,
+                          const int64_t** sizes);
+int64_t sgpr_train_param_count(void);   /* 47,985 */
+int64_t sgpr_train_state_count(void);   /* 48,689 = parameters + 704 running statistics */
+
+/* Replaces SG(...).cuda() + torch.optim.Adam(model.parameters(), lr, weight_decay)   sg_net.py:158-176, 351-352 */
+int sgpr_train_create(sgpr_train** out, int device);
+int sgpr_train_destroy(sgpr_train* t);
+
+/* Upload / download the flat state (host pointers).  reset_optimizer != 0 zeroes Adam's moments and step count. */
+int sgpr_train_set_state(sgpr_train* t, const float* state_host, int reset_optimizer);
+int sgpr_train_get_state(sgpr_train* t, float* state_host);
+
+/* torch.optim.Adam defaults: betas (0.9, 0.999), eps 1e-8; the reference passes lr and weight_decay (config.yml). */
+int sgpr_train_set_optimizer(sgpr_train* t, float lr, float weight_decay, float beta1, float beta2, float eps);
+
+/*
+ * ONE optimiser step on a batch of B ordered pairs (the reference feeds every listed pair in both orders, so its B is
+ * twice the listed batch — sg_net.py:324-331):
+ *   f1_dev, f2_dev : [B][15][N]   data["features_1"/"features_2"]
+ *   target_dev     : [B]          data["target"] (0 / 1)
+ *   loss_dev       : [1]          mean BCE of this batch (before the update), may be NULL
+ *   pred_dev       : [B]          train-mode predictions (before the update), may be NULL
+ *   apply          : 1 = full step (Adam update + running statistics); 0 = forward + backward only (gradients stay
+ *                    readable through sgpr_train_get_grads, nothing is updated)
+ * B >= 1, 2 <= N <= SGPR_MAX_NODES, 1 <= k <= N, B*N*k > 1.
+ */
+int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, const float* target_dev, int B, int N, int k,
+                    float* loss_dev, float* pred_dev, int apply, void* stream);
+
+/* Gradients of the last step w.r.t. the trainable parameters (before weight decay), flat layout, host pointer. */
+int sgpr_train_get_grads(sgpr_train* t, float* grads_host);
+
+/* Number of optimiser steps applied so far / kernel launches enqueued so far. */
+int64_t sgpr_train_step_count(const sgpr_train* t);
+int64_t sgpr_train_launch_count(const sgpr_train* t);
+
+/*
+ * Debug/parity tap: copy an internal tensor of the LAST step to the host.  what: "yext","a","d","sumy","gz","enode",
+ * "idx" (layer = 0..5: xyz 1-3, sem 1-3), "yend","gzend","pooled","att","ctx","dpooled","stats","bsum" (layer ignored).
+ * Returns the number of bytes copied (<= cap_bytes) or a negative error.
+ */
+int64_t sgpr_train_debug_read(sgpr_train* t, const char* what, int layer, void* host, int64_t cap_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGPR_B200_TRAIN_H */

@@ -49,6 +49,37 @@ SYMBOLS = {
     "sgpr_launch_count": (C.c_int64, [C.c_void_p]),
 }
 
+# every symbol include/sgpr_b200_train.h declares
+c_i64_p = C.POINTER(C.c_int64)
+TRAIN_SYMBOLS = {
+    "sgpr_train_layout": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_char_p)),
+                                    C.POINTER(c_i64_p), C.POINTER(c_i64_p)]),
+    "sgpr_train_param_count": (C.c_int64, []),
+    "sgpr_train_state_count": (C.c_int64, []),
+    "sgpr_train_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "sgpr_train_destroy": (C.c_int, [C.c_void_p]),
+    "sgpr_train_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "sgpr_train_get_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgpr_train_set_optimizer": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "sgpr_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "sgpr_train_get_grads": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgpr_train_step_count": (C.c_int64, [C.c_void_p]),
+    "sgpr_train_launch_count": (C.c_int64, [C.c_void_p]),
+    "sgpr_train_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]),
+}
+SYMBOLS.update(TRAIN_SYMBOLS)
+
+
+def bind(lib, symbols):
+    """Type the given entry points of an already opened library (AttributeError if one is not exported)."""
+    for name, (res, args) in symbols.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
 _lib = None
 
 
@@ -61,11 +92,7 @@ def load():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m sg_pr_b200.build` (or __graft_entry__.build()). "
             "sg_pr_b200 has no CPU or PyTorch fallback for the SG_PR hot path.")
-    lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SYMBOLS.items():
-        fn = getattr(lib, name)       # AttributeError if the library does not export a declared symbol
-        fn.restype = res
-        fn.argtypes = args
+    lib = bind(C.CDLL(LIB_PATH), SYMBOLS)     # AttributeError if the library does not export a declared symbol
     _lib = lib
     return lib
 
@@ -74,7 +101,7 @@ class SgprError(RuntimeError):
     pass
 
 
-def check(rc: int, what: str):
+def check(rc: int, what: str, lib=None):
     if rc != SGPR_OK:
-        msg = load().sgpr_last_error()
+        msg = (lib or load()).sgpr_last_error()
         raise SgprError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

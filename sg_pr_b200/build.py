@@ -14,8 +14,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsgpr_b200.so")
-SOURCES = ["api.cu"]
-DEPS = ["api.cu", "common.cuh", "embed_kernel.cuh", "head_kernels.cuh", "pack.hpp", "sortnet32.inc", "sortnet16.inc", "sortnet8.inc"]
+SOURCES = ["api.cu", "train.cu"]
+DEPS = ["api.cu", "train.cu", "train_kernels.cuh", "common.cuh", "embed_kernel.cuh", "head_kernels.cuh", "pack.hpp", "sortnet32.inc", "sortnet16.inc", "sortnet8.inc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
@@ -31,7 +31,7 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, d) for d in DEPS] + [os.path.join(ROOT, "include", "sgpr_b200.h")]
+    deps = [os.path.join(CSRC, d) for d in DEPS] + [os.path.join(ROOT, "include", h) for h in ("sgpr_b200.h", "sgpr_b200_train.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -28,6 +28,7 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+void set_error_text(const char* text) { snprintf(g_err, sizeof(g_err), "%s", text); }
 
 #define CUDA_TRY(expr)                                                                                     \
     do {                                                                                                   \
@@ -62,6 +63,17 @@ int ensure(T*& ptr, size_t& cap, size_t need) {
 }
 
 }  // namespace
+
+// error reporting for the other translation units of the library (train.cu)
+int sgpr_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    set_error_text(buf);
+    return code;
+}
 
 struct sgpr_ctx {
     int device = 0;

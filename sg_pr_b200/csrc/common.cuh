@@ -1,6 +1,10 @@
 // Shared definitions for the sm_100a SG_PR kernels.
 #pragma once
+#ifdef SGPR_EMU                      // tests/emu: the same source built by the host compiler (test infrastructure only)
+#include "../../tests/emu/cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace sgpr {
@@ -58,6 +62,7 @@ struct HeadParams {
     float fc2_b;
 };
 
+#ifndef SGPR_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -90,6 +95,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+
+#endif  // !SGPR_EMU
 
 __device__ __forceinline__ float lrelu(float x) { return x > 0.0f ? x : x * kSlope; }
 

@@ -246,6 +246,10 @@ __device__ __forceinline__ void gram_rows(const float* __restrict__ sXt, const f
 // in-register sort, two cross-lane bitonic merges — the last one pruned to the single output position that is the
 // threshold (element NMAX-k of the sorted row) — then count and emit passes over the unsorted values.
 // ------------------------------------------------------------------------------------------------------------
+#ifdef SGPR_EMU
+__device__ __forceinline__ uint32_t fgt_mask(float a, float b) { return a > b ? 0xffffffffu : 0u; }
+__device__ __forceinline__ uint32_t feq_mask(float a, float b) { return a == b ? 0xffffffffu : 0u; }
+#else
 __device__ __forceinline__ uint32_t fgt_mask(float a, float b) {          // all-ones if a > b (one FSET)
     uint32_t m;
     asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
@@ -256,6 +260,7 @@ __device__ __forceinline__ uint32_t feq_mask(float a, float b) {
     asm("set.eq.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b));
     return m;
 }
+#endif
 
 template <int NPL>
 __device__ __forceinline__ void select_rows(const float* __restrict__ sY, uint16_t* __restrict__ sIdx,
@@ -711,6 +716,7 @@ struct FrontCtx {
         default: { constexpr int NR = 8; CALL; } break;                                            \
     }
 
+#ifndef SGPR_EMU   // everything below stages data with bulk TMA + mbarriers: device builds only
 // front of one pass (up to 8 own rows): distance rows -> selection -> GEMM rows.  Only the row-tiled pieces are
 // specialised on the row count; the selection network exists once.
 template <int NPL>
@@ -1013,5 +1019,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
     }
 #endif
 }
+
+#endif  // !SGPR_EMU
 
 }  // namespace sgpr

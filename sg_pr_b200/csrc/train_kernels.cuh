@@ -1,0 +1,1194 @@
+// Training step kernels: SGTrainer.process_batch(batch, training=True) from the point where the batch tensors exist
+// (/root/reference/sg_net.py:332-338): SG.forward in TRAIN mode (sg_net.py:112-138 with the seven BatchNorm layers of
+// sg_net.py:50-76 normalising by batch statistics, one BatchNorm batch per side because dgcnn_conv_pass is called once
+// per side, sg_net.py:123-124), mean binary cross entropy (sg_net.py:335), backward, Adam with L2 weight decay
+// (sg_net.py:351-352), running-statistics update (momentum 0.1, unbiased variance).
+//
+// Train-mode BatchNorm couples every graph of a side through the per-channel batch statistics, so — unlike the eval
+// path's single fused kernel — a layer cannot start before the previous layer's statistics are complete.  The step is a
+// short chain of launches with a grid-wide dependency (the kernel boundary) exactly where BatchNorm puts one:
+//
+//   pack | edge_fwd l=0,1,2 (xyz and sem branches of both sides in one grid) | end_fwd | att_fwd | head (fwd+loss+bwd)
+//        | att_bwd | end_bwd | edge_bwd l=2,1,0 | adam (+ running statistics, loss)
+//
+// Arithmetic form (tests/train_model.py holds the same algebra in torch, checked against autograd on the CPU):
+//   forward   y_ij = (A_j - A_i) + B_i,  A = Wa x, B = Wb x per node; BN+LeakyReLU is monotone per channel, so the max over
+//             neighbours is taken on y (max if gamma >= 0 else min) and only [node][channel] tensors are ever stored;
+//             sum_ij y and sum_ij y^2 accumulate in fp64 per (side, layer, channel).
+//   backward  dy_ij = s*gz_i*[j = ext] - r - q*y_ij  (s = gamma*istd, q = s*dgamma/e*istd, r = s*dbeta/e - q*mu) folds the
+//             BatchNorm backward into per-node terms: dB_i = T_i = s*gz_i - k*r - q*sum_j y_ij and
+//             dA_n = -T_n + s*S1_n - deg_n*(r + q*A_n) - q*S2_n with S1_n = sum of gz_i over the nodes i whose extreme
+//             neighbour is n, S2_n = sum of D_i = B_i - A_i over the nodes i that list n, deg_n = how many do.
+//   k-NN indices carry no gradient (topk indices, dgcnn.py:19).
+//
+// Per-parameter gradients are accumulated in registers across the graphs a persistent CTA processes and written as
+// per-CTA partials; the Adam kernel sums the partials in a fixed order (deterministic, no float atomics).
+#pragma once
+#include "../../include/sgpr_b200.h"
+#include "common.cuh"
+#include "embed_kernel.cuh"
+
+#ifdef SGPR_EMU
+#define SGPR_LAUNCH(kern, grid, block, smem, st, ...) emu::launch((grid), (block), (smem), [=] { kern(__VA_ARGS__); })
+#define SGPR_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#else
+#define SGPR_LAUNCH(kern, grid, block, smem, st, ...) kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__)
+#define SGPR_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
+namespace sgpr {
+namespace train {
+
+// ---- flat parameter vector (floats): conv weights in their state_dict shapes, BN gamma|beta per layer, head --------
+constexpr int P_S1W = 0;                    // dgcnn_s_conv1.0.weight [64][6]
+constexpr int P_S2W = P_S1W + 64 * 6;       // dgcnn_s_conv2.0.weight [64][128]
+constexpr int P_S3W = P_S2W + 64 * 128;     // dgcnn_s_conv3.0.weight [32][128]
+constexpr int P_F1W = P_S3W + 32 * 128;     // dgcnn_f_conv1.0.weight [64][24]
+constexpr int P_F2W = P_F1W + 64 * 24;      // dgcnn_f_conv2.0.weight [64][128]
+constexpr int P_F3W = P_F2W + 64 * 128;     // dgcnn_f_conv3.0.weight [32][128]
+constexpr int P_ENDW = P_F3W + 32 * 128;    // dgcnn_conv_end.0.weight [32][64]
+constexpr int P_BN = P_ENDW + 32 * 64;      // 7 x (gamma[C] | beta[C]), layers s1 s2 s3 f1 f2 f3 end
+constexpr int kBnFloats = 2 * (64 + 64 + 32 + 64 + 64 + 32 + 32);   // 704
+constexpr int P_ATT = P_BN + kBnFloats;     // attention.weight_matrix [32][32]
+constexpr int P_NTNW = P_ATT + 32 * 32;     // tensor_network.weight_matrix [32][32][16]
+constexpr int P_NTNV = P_NTNW + 32 * 32 * 16;   // tensor_network.weight_matrix_block [16][64]
+constexpr int P_NTNB = P_NTNV + 16 * 64;    // tensor_network.bias [16]
+constexpr int P_FC1W = P_NTNB + 16;         // fully_connected_first.weight [16][16]
+constexpr int P_FC1B = P_FC1W + 256;
+constexpr int P_FC2W = P_FC1B + 16;         // scoring_layer.weight [1][16]
+constexpr int P_FC2B = P_FC2W + 16;
+constexpr int P_TOTAL = P_FC2B + 1;         // 47,985 trainable floats
+constexpr int R_OFF = P_TOTAL;              // 7 x (running_mean[C] | running_var[C])
+constexpr int STATE_TOTAL = P_TOTAL + kBnFloats;
+constexpr int kHeadFloats = P_TOTAL - P_NTNW;   // 17,713: the head's parameters are contiguous
+
+// packed (channel-pair layout, pack.hpp::pair_index) copies of the GEMM matrices, rebuilt every step
+constexpr int WPK_S2 = 0, WPK_S3 = WPK_S2 + 64 * 128, WPK_F1 = WPK_S3 + 64 * 64, WPK_F2 = WPK_F1 + 12 * 128,
+              WPK_F3 = WPK_F2 + 64 * 128, WPK_END = WPK_F3 + 64 * 64, WPK_TOTAL = WPK_END + 64 * 32;
+
+constexpr float kMomentum = 0.1f;           // nn.BatchNorm default (sg_net.py:52)
+
+// layer index L: 0-2 xyz EdgeConv 1-3, 3-5 sem EdgeConv 1-3, 6 conv_end
+__host__ __device__ inline int layer_cin(int L) { return L == 0 ? 3 : (L == 3 ? 12 : 64); }
+__host__ __device__ inline int layer_cout(int L) { return (L == 2 || L == 5 || L == 6) ? 32 : 64; }
+__host__ __device__ inline int conv_off(int L) {
+    switch (L) {
+        case 0: return P_S1W; case 1: return P_S2W; case 2: return P_S3W; case 3: return P_F1W;
+        case 4: return P_F2W; case 5: return P_F3W; default: return P_ENDW;
+    }
+}
+__host__ __device__ inline int conv_size(int L) { return L == 6 ? 32 * 64 : layer_cout(L) * 2 * layer_cin(L); }
+__host__ __device__ inline int bn_off(int L) {          // offset of gamma within the BN block; beta follows at +C
+    switch (L) {
+        case 0: return 0; case 1: return 128; case 2: return 256; case 3: return 320;
+        case 4: return 448; case 5: return 576; default: return 640;
+    }
+}
+__host__ __device__ inline int wpk_off(int L) {
+    switch (L) {
+        case 1: return WPK_S2; case 2: return WPK_S3; case 3: return WPK_F1; case 4: return WPK_F2;
+        case 5: return WPK_F3; default: return WPK_END;
+    }
+}
+
+struct Segment {            // one contiguous slice of the parameter vector whose gradient arrives as per-CTA partials
+    int off, size, count, stride;
+    const float* part;
+};
+constexpr int kMaxSeg = 12;
+
+struct TrainWs {
+    int G;                  // pairs per step = graphs per side
+    int N, k, KS;
+    float eps;
+    const float* f[2];      // features_1 / features_2   [G][15][N]
+    const float* target;    // [G]
+    float* state;           // [STATE_TOTAL] parameters | running statistics
+    float* wpk;             // [WPK_TOTAL]
+    // per EdgeConv layer L = 0..5, every tensor [2*G][N][cout]  (side-major: sg = side*G + g)
+    float* yext[6];         // extreme over the neighbours of the pre-BN activation
+    float* a[6];            // A_i
+    float* d[6];            // B_i - A_i
+    float* sumy[6];         // sum_j y_ij
+    float* gz[6];           // d loss / d z (z = BN output), written by the backward of the layer above
+    uint8_t* enode[6];      // which neighbour achieved the extreme
+    uint8_t* idx[6];        // [2*G][N][k] neighbour lists
+    float* yend;            // [2*G][N][32] conv_end pre-BN
+    float* gzend;           // [2*G][N][32]
+    float* pooled;          // [2*G][32]
+    float* actx;            // [2*G][32]  tanh context
+    float* att;             // [2*G][N]
+    float* esum;            // [2*G][32]  sum_n emb
+    float* dpooled;         // [2*G][32]
+    double* stats;          // [2][7][2][64]  sum y | sum y^2
+    double* bsum;           // [2][7][2][64]  dbeta | dgamma
+    float* pred;            // [G]
+    float* losspart;        // [head grid]
+    float* grads;           // [P_TOTAL]
+    float* adam_m;
+    float* adam_v;
+    float* loss;            // [1]
+    int head_grid;
+    int nseg;
+    Segment seg[kMaxSeg];
+};
+
+__device__ __forceinline__ double* stat_ptr(double* base, int side, int L) { return base + (side * 7 + L) * 128; }
+
+// batch mean and 1/sqrt(var + eps) of channel c from the fp64 sums (biased variance, like nn.BatchNorm in train mode)
+__device__ __forceinline__ void bn_coef(const double* st, int c, double e, float eps, float& mu, float& istd) {
+    const double m = st[c] / e;
+    double var = st[64 + c] / e - m * m;
+    var = var > 0.0 ? var : 0.0;
+    mu = static_cast<float>(m);
+    istd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+__device__ __forceinline__ float bn_act(float y, float mu, float istd, float gamma, float beta) {
+    return lrelu(fmaf(__fmul_rn(__fsub_rn(y, mu), istd), gamma, beta));
+}
+__device__ __forceinline__ float slope_of(float x) { return x > 0.0f ? 1.0f : kSlope; }   // LeakyReLU'(z); sign(z) = sign(x)
+
+__device__ __forceinline__ int pair_index_dev(int ci, int co, int CO) {       // pack.hpp::pair_index
+    const int cpl = CO / 32;
+    const int p = ci >> 1, r = ci & 1;
+    const int lane = co / cpl, j = co % cpl;
+    return p * 2 * CO + (j >> 1) * 128 + lane * (cpl >= 2 ? 4 : 2) + (j & 1) * 2 + r;
+}
+
+// ---- pack: natural conv weights -> channel-pair GEMM layout [cin][A half | B half] ------------------------------------
+__global__ void __launch_bounds__(kThreads) sgpr_train_pack_kernel(const TrainWs T) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int L = 1; L <= 6; ++L) {
+        const int cin = layer_cin(L), cout = layer_cout(L);
+        const float* w = T.state + conv_off(L);
+        float* dst = T.wpk + wpk_off(L);
+        const int total = conv_size(L);
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+            if (L == 6) {                               // conv_end [32][64]: out f, in c
+                const int f = e >> 6, c = e & 63;
+                dst[pair_index_dev(c, f, 32)] = w[e];
+            } else {
+                const int c = e / (2 * cin), col = e % (2 * cin);
+                const int ci = col < cin ? col : col - cin;
+                const int co = col < cin ? c : cout + c;
+                dst[pair_index_dev(ci, co, 2 * cout)] = w[e];
+            }
+        }
+    }
+}
+
+// ---- shared-memory carve-outs ----------------------------------------------------------------------------------------
+struct FwdSmem { int w, x, y, xx, idx, cnt, prm, stat, total; };
+__host__ __device__ inline FwdSmem fwd_layout(int nmax, int ks) {
+    FwdSmem L;
+    int o = 0;
+    L.w = o;    o += 64 * 128 * 4;
+    L.x = o;    o += nmax * XS * 4;
+    L.y = o;    o += nmax * YS * 4;
+    L.xx = o;   o += nmax * 4;
+    L.idx = o;  o += ((nmax * ks * 2 + 15) / 16) * 16;
+    L.cnt = o;  o += ((nmax + 15) / 16) * 16;
+    L.prm = o;  o += 4 * 64 * 4;
+    L.stat = o; o += kWarps * 128 * 8;
+    L.total = o;
+    return L;
+}
+
+// fill the node-major input tile of EdgeConv layer l of branch br for graph (side, g); columns beyond cin stay zero
+__device__ __forceinline__ void fill_layer_input(const TrainWs& T, int l, int br, int side, int g, float* sX, float* sPrm,
+                                                 int tid) {
+    const int N = T.N, L = br * 3 + l;
+    if (l == 0) {
+        const float* gin = T.f[side] + static_cast<size_t>(g) * kInCh * N;
+        if (br == 0) {
+            for (int n = tid; n < N; n += kThreads)
+                *reinterpret_cast<float4*>(sX + n * XS) = make_float4(__ldg(gin + n), __ldg(gin + N + n), __ldg(gin + 2 * N + n), 0.0f);
+        } else {
+            for (int e = tid; e < N * kLabels; e += kThreads) {
+                const int c = e / N, n = e - c * N;
+                sX[n * XS + c] = __ldg(gin + (3 + c) * N + n);
+            }
+        }
+    } else {
+        if (tid < 64) {
+            float mu, istd;
+            bn_coef(stat_ptr(T.stats, side, L - 1), tid, static_cast<double>(T.G) * N * T.k, T.eps, mu, istd);
+            sPrm[tid] = mu;
+            sPrm[64 + tid] = istd;
+            sPrm[128 + tid] = T.state[P_BN + bn_off(L - 1) + tid];
+            sPrm[192 + tid] = T.state[P_BN + bn_off(L - 1) + 64 + tid];
+        }
+        __syncthreads();
+        const float* yp = T.yext[L - 1] + (static_cast<size_t>(side) * T.G + g) * N * 64;
+        for (int e = tid; e < N * 64; e += kThreads) {
+            const int n = e >> 6, c = e & 63;
+            sX[n * XS + c] = bn_act(yp[e], sPrm[c], sPrm[64 + c], sPrm[128 + c], sPrm[192 + c]);
+        }
+    }
+}
+
+// gather over the neighbour lists for own rows: extreme / arg-extreme / sums of y_ij = (A_j - A_i) + B_i
+template <int COUT>
+__device__ __forceinline__ void train_gather_rows(const float* __restrict__ sY, const uint16_t* __restrict__ sIdx, int KS,
+                                                  int k, const float* __restrict__ gamma, float* __restrict__ yext,
+                                                  float* __restrict__ ga, float* __restrict__ gd, float* __restrict__ gsum,
+                                                  uint8_t* __restrict__ enode, int r0, int r1, int lane,
+                                                  double (&acc1)[2], double (&acc2)[2]) {
+    constexpr int CPL = COUT / 32;
+    bool pos[CPL];
+#pragma unroll
+    for (int p = 0; p < CPL; ++p) pos[p] = gamma[lane * CPL + p] >= 0.0f;
+    for (int i = r0; i < r1; ++i) {
+        float ai[CPL], bi[CPL], best[CPL], s1[CPL], s2[CPL];
+        int bj[CPL];
+#pragma unroll
+        for (int p = 0; p < CPL; ++p) {
+            ai[p] = sY[i * YS + lane * CPL + p];
+            bi[p] = sY[i * YS + COUT + lane * CPL + p];
+            best[p] = pos[p] ? -INFINITY : INFINITY;
+            s1[p] = 0.0f; s2[p] = 0.0f; bj[p] = 0;
+        }
+        for (int e = 0; e < k; ++e) {
+            const int j = sIdx[i * KS + e];
+#pragma unroll
+            for (int p = 0; p < CPL; ++p) {
+                const float v = sY[j * YS + lane * CPL + p];
+                const float y = __fadd_rn(__fsub_rn(v, ai[p]), bi[p]);
+                s1[p] = __fadd_rn(s1[p], y);
+                s2[p] = fmaf(y, y, s2[p]);
+                const bool better = pos[p] ? (v > best[p]) : (v < best[p]);
+                best[p] = better ? v : best[p];
+                bj[p] = better ? j : bj[p];
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < CPL; ++p) {
+            const size_t o = static_cast<size_t>(i) * COUT + lane * CPL + p;
+            yext[o] = __fadd_rn(__fsub_rn(best[p], ai[p]), bi[p]);
+            ga[o] = ai[p];
+            gd[o] = __fsub_rn(bi[p], ai[p]);
+            gsum[o] = s1[p];
+            enode[o] = static_cast<uint8_t>(bj[p]);
+            acc1[p] += static_cast<double>(s1[p]);
+            acc2[p] += static_cast<double>(s2[p]);
+        }
+    }
+}
+
+// xyz layer 1 in the reference's direct per-edge form W_a (x_j - x_i) + W_b x_i (metre-scale coordinates would lose
+// ~5 bits in A_j - A_i; same choice and FMA order as embed_kernel.cuh::xyz_rows).  sW: natural [64][6].
+__device__ __forceinline__ void train_xyz_rows(const float* __restrict__ sX, const uint16_t* __restrict__ sIdx, int KS, int k,
+                                               const float* __restrict__ sW, const float* __restrict__ gamma,
+                                               float* __restrict__ yext, float* __restrict__ ga, float* __restrict__ gd,
+                                               float* __restrict__ gsum, uint8_t* __restrict__ enode, int r0, int r1,
+                                               int lane, double (&acc1)[2], double (&acc2)[2]) {
+    float wa[2][3], wb[2][3];
+    bool pos[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int c = 2 * lane + p;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) { wa[p][u] = sW[c * 6 + u]; wb[p][u] = sW[c * 6 + 3 + u]; }
+        pos[p] = gamma[c] >= 0.0f;
+    }
+    for (int i = r0; i < r1; ++i) {
+        const float4 xi = *reinterpret_cast<const float4*>(sX + i * XS);
+        float best[2], s1[2], s2[2];
+        int bj[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) { best[p] = pos[p] ? -INFINITY : INFINITY; s1[p] = 0.0f; s2[p] = 0.0f; bj[p] = 0; }
+        for (int e = 0; e < k; ++e) {
+            const int j = sIdx[i * KS + e];
+            const float4 xj = *reinterpret_cast<const float4*>(sX + j * XS);
+            const float d0 = __fsub_rn(xj.x, xi.x), d1 = __fsub_rn(xj.y, xi.y), d2 = __fsub_rn(xj.z, xi.z);
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const float ev = fmaf(wa[p][2], d2, fmaf(wa[p][1], d1, __fmul_rn(wa[p][0], d0)));
+                float y = fmaf(wb[p][0], xi.x, ev);
+                y = fmaf(wb[p][1], xi.y, y);
+                y = fmaf(wb[p][2], xi.z, y);
+                s1[p] = __fadd_rn(s1[p], y);
+                s2[p] = fmaf(y, y, s2[p]);
+                const bool better = pos[p] ? (ev > best[p]) : (ev < best[p]);
+                best[p] = better ? ev : best[p];
+                bj[p] = better ? j : bj[p];
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const size_t o = static_cast<size_t>(i) * 64 + 2 * lane + p;
+            float y = fmaf(wb[p][0], xi.x, best[p]);
+            y = fmaf(wb[p][1], xi.y, y);
+            y = fmaf(wb[p][2], xi.z, y);
+            const float av = fmaf(wa[p][2], xi.z, fmaf(wa[p][1], xi.y, __fmul_rn(wa[p][0], xi.x)));
+            const float bv = fmaf(wb[p][2], xi.z, fmaf(wb[p][1], xi.y, __fmul_rn(wb[p][0], xi.x)));
+            yext[o] = y;
+            ga[o] = av;
+            gd[o] = __fsub_rn(bv, av);
+            gsum[o] = s1[p];
+            enode[o] = static_cast<uint8_t>(bj[p]);
+            acc1[p] += static_cast<double>(s1[p]);
+            acc2[p] += static_cast<double>(s2[p]);
+        }
+    }
+}
+
+// CTA-wide reduction of per-thread fp64 channel sums (thread owns `cpl` channels lane*cpl+p; one row of 128 per warp:
+// [which][channel]) followed by one fp64 atomicAdd per channel into the (side, layer) statistics.
+__device__ __forceinline__ void flush_channel_sums(double* sStat, double* dst, const double (&acc1)[2], const double (&acc2)[2],
+                                                   int cpl, int cout, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    __syncthreads();
+    for (int p = 0; p < cpl; ++p) {
+        sStat[warp * 128 + lane * cpl + p] = acc1[p];
+        sStat[warp * 128 + 64 + lane * cpl + p] = acc2[p];
+    }
+    __syncthreads();
+    if (tid < 128 && (tid & 63) < cout) {
+        double s = 0.0;
+        for (int w = 0; w < kWarps; ++w) s += sStat[w * 128 + tid];
+        atomicAdd(dst + tid, s);
+    }
+    __syncthreads();
+}
+
+// =====================================================================================================================
+// EdgeConv layer l (0..2) forward for both branches and both sides: grid = multiple of 4, CTA -> (branch, side), loops g
+// =====================================================================================================================
+template <int NPL>
+__global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_fwd(const TrainWs T, int l) {
+    constexpr int NMAX = 32 * NPL;
+    SGPR_DYN_SMEM(smem);
+    const FwdSmem S = fwd_layout(NMAX, T.KS);
+    float* sW = reinterpret_cast<float*>(smem + S.w);
+    float* sX = reinterpret_cast<float*>(smem + S.x);
+    float* sY = reinterpret_cast<float*>(smem + S.y);
+    float* sXX = reinterpret_cast<float*>(smem + S.xx);
+    uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + S.idx);
+    uint8_t* sCnt = smem + S.cnt;
+    float* sPrm = reinterpret_cast<float*>(smem + S.prm);
+    double* sStat = reinterpret_cast<double*>(smem + S.stat);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int br = blockIdx.x & 1, side = (blockIdx.x >> 1) & 1;
+    const int L = br * 3 + l;
+    const int cin4 = (l == 0) ? (br ? 3 : 1) : 16, cout = layer_cout(L);
+    const int N = T.N, k = T.k, KS = T.KS;
+    const bool direct = (L == 0);
+
+    {   // this CTA's layer matrix, once
+        const float* src = direct ? T.state + P_S1W : T.wpk + wpk_off(L);
+        const int n = direct ? 64 * 6 : layer_cin(L) * 2 * cout;
+        for (int e = tid; e < n; e += kThreads) sW[e] = src[e];
+    }
+    for (int e = tid; e < NMAX * XS; e += kThreads) sX[e] = 0.0f;
+    for (int e = tid; e < NMAX; e += kThreads) sXX[e] = 0.0f;
+    __syncthreads();
+
+    const int rpw = (N + kWarps - 1) / kWarps;
+    const int w0 = min(N, warp * rpw), w1 = min(N, w0 + rpw);
+    const float* gamma = T.state + P_BN + bn_off(L);
+    double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};
+
+    for (int g = blockIdx.x >> 2; g < T.G; g += gridDim.x >> 2) {
+        const size_t sg = static_cast<size_t>(side) * T.G + g;
+        fill_layer_input(T, l, br, side, g, sX, sPrm, tid);
+        __syncthreads();
+        norms_rows(sX, sXX, cin4, w0, w1, lane);
+        __syncthreads();
+        // ---- front: distance rows -> k-NN selection -> per-node GEMM rows, for own rows ----
+        for (int r0 = w0; r0 < w1; r0 += 8) {
+            const int nr = min(8, w1 - r0);
+            SGPR_NR_SWITCH(nr, (gram_rows<NPL, NPL, NR>(sX, sXX, sY, cin4, N, N, r0, lane)))
+            __syncwarp();
+            select_rows<NPL>(sY, sIdx, sCnt, nullptr, N, N, k, KS, 1, r0, nr, lane);
+            __syncwarp();
+            if (!direct) {
+                if (cout == 64) { SGPR_NR_SWITCH(nr, (gemm_rows<NR, 4, 0>(sX, sW, sY, YS, nullptr, cin4, r0, lane))) }
+                else            { SGPR_NR_SWITCH(nr, (gemm_rows<NR, 2, 0>(sX, sW, sY, YS, nullptr, cin4, r0, lane))) }
+            }
+        }
+        __syncthreads();
+        // ---- back: gather over the neighbour lists for own rows ----
+        const size_t o = sg * N * cout;
+        if (direct)
+            train_xyz_rows(sX, sIdx, KS, k, sW, gamma, T.yext[L] + o, T.a[L] + o, T.d[L] + o, T.sumy[L] + o, T.enode[L] + o,
+                           w0, w1, lane, acc1, acc2);
+        else if (cout == 64)
+            train_gather_rows<64>(sY, sIdx, KS, k, gamma, T.yext[L] + o, T.a[L] + o, T.d[L] + o, T.sumy[L] + o,
+                                  T.enode[L] + o, w0, w1, lane, acc1, acc2);
+        else
+            train_gather_rows<32>(sY, sIdx, KS, k, gamma, T.yext[L] + o, T.a[L] + o, T.d[L] + o, T.sumy[L] + o,
+                                  T.enode[L] + o, w0, w1, lane, acc1, acc2);
+        uint8_t* gi = T.idx[L] + sg * N * k;
+        for (int i = w0; i < w1; ++i)
+            for (int e = lane; e < k; e += 32) gi[i * k + e] = static_cast<uint8_t>(sIdx[i * KS + e]);
+        __syncthreads();
+    }
+    flush_channel_sums(sStat, stat_ptr(T.stats, side, L), acc1, acc2, cout / 32, cout, tid);
+}
+
+// =====================================================================================================================
+// conv_end forward (sg_net.py:104-105 before the BatchNorm): y = W_end . cat(xyz3, sem3) per node; statistics
+// grid = multiple of 2, CTA -> side, loops g
+// =====================================================================================================================
+template <int NPL>
+__global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_fwd(const TrainWs T) {
+    constexpr int NMAX = 32 * NPL;
+    SGPR_DYN_SMEM(smem);
+    float* sW = reinterpret_cast<float*>(smem);                 // [64][32] pair layout
+    float* sX = sW + 64 * 32;                                   // [NMAX][XS] cat(xyz3, sem3)
+    float* sO = sX + NMAX * XS;                                 // [NMAX][XS] (first 32 columns)
+    float* sPrm = sO + NMAX * XS;                               // [4][64]
+    double* sStat = reinterpret_cast<double*>(sPrm + 256);      // [kWarps][128]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int side = blockIdx.x & 1;
+    const int N = T.N;
+    for (int e = tid; e < 64 * 32; e += kThreads) sW[e] = T.wpk[WPK_END + e];
+    for (int e = tid; e < NMAX * XS; e += kThreads) sX[e] = 0.0f;
+    if (tid < 64) {          // channel c < 32: xyz layer 3 (L = 2); c >= 32: sem layer 3 (L = 5)
+        const int L = tid < 32 ? 2 : 5, c = tid & 31;
+        float mu, istd;
+        bn_coef(stat_ptr(T.stats, side, L), c, static_cast<double>(T.G) * N * T.k, T.eps, mu, istd);
+        sPrm[tid] = mu;
+        sPrm[64 + tid] = istd;
+        sPrm[128 + tid] = T.state[P_BN + bn_off(L) + c];
+        sPrm[192 + tid] = T.state[P_BN + bn_off(L) + 32 + c];
+    }
+    __syncthreads();
+    const int rpw = (N + kWarps - 1) / kWarps;
+    const int w0 = min(N, warp * rpw), w1 = min(N, w0 + rpw);
+    double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};
+    for (int g = blockIdx.x >> 1; g < T.G; g += gridDim.x >> 1) {
+        const size_t sg = static_cast<size_t>(side) * T.G + g;
+        const float* y2 = T.yext[2] + sg * N * 32;
+        const float* y5 = T.yext[5] + sg * N * 32;
+        for (int e = tid; e < N * 64; e += kThreads) {
+            const int n = e >> 6, c = e & 63;
+            const float y = c < 32 ? y2[n * 32 + c] : y5[n * 32 + c - 32];
+            sX[n * XS + c] = bn_act(y, sPrm[c], sPrm[64 + c], sPrm[128 + c], sPrm[192 + c]);
+        }
+        __syncthreads();
+        for (int r0 = w0; r0 < w1; r0 += 8) {
+            const int nr = min(8, w1 - r0);
+            SGPR_NR_SWITCH(nr, (gemm_rows<NR, 1, 0>(sX, sW, sO, XS, nullptr, 16, r0, lane)))
+        }
+        __syncwarp();
+        float* yo = T.yend + sg * N * 32;
+        for (int i = w0; i < w1; ++i) {
+            const float y = sO[i * XS + lane];
+            yo[i * 32 + lane] = y;
+            acc1[0] += static_cast<double>(y);
+            acc2[0] += static_cast<double>(y) * static_cast<double>(y);
+        }
+        __syncthreads();
+    }
+    flush_channel_sums(sStat, stat_ptr(T.stats, side, 6), acc1, acc2, 1, 32, tid);
+}
+
+// =====================================================================================================================
+// conv_end BatchNorm + LeakyReLU, then attention pooling (layers_batch.py:28-39).  One CTA per (side, g) item.
+// =====================================================================================================================
+__global__ void __launch_bounds__(kThreads) sgpr_train_att_fwd(const TrainWs T) {
+    __shared__ float sE[SGPR_MAX_NODES * 33];
+    __shared__ float sPrm[4 * 32];
+    __shared__ float sSum[32], sCtx[32], sAtt[SGPR_MAX_NODES];
+    const int tid = threadIdx.x;
+    const int N = T.N;
+    const float* watt = T.state + P_ATT;
+    for (int item = blockIdx.x; item < 2 * T.G; item += gridDim.x) {
+        const int side = item / T.G;
+        if (tid < 32) {
+            float mu, istd;
+            bn_coef(stat_ptr(T.stats, side, 6), tid, static_cast<double>(T.G) * N, T.eps, mu, istd);
+            sPrm[tid] = mu;
+            sPrm[32 + tid] = istd;
+            sPrm[64 + tid] = T.state[P_BN + bn_off(6) + tid];
+            sPrm[96 + tid] = T.state[P_BN + bn_off(6) + 32 + tid];
+        }
+        __syncthreads();
+        const float* y = T.yend + static_cast<size_t>(item) * N * 32;
+        for (int e = tid; e < N * 32; e += kThreads) {
+            const int n = e >> 5, c = e & 31;
+            sE[n * 33 + c] = bn_act(y[e], sPrm[c], sPrm[32 + c], sPrm[64 + c], sPrm[96 + c]);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float s = 0.0f;
+            for (int n = 0; n < N; ++n) s = __fadd_rn(s, sE[n * 33 + tid]);
+            sSum[tid] = s;
+            T.esum[static_cast<size_t>(item) * 32 + tid] = s;
+        }
+        __syncthreads();
+        if (tid < 32) {          // context = tanh(mean_n(E W)) = tanh((sum_n E) W / N)
+            float s = 0.0f;
+            for (int a = 0; a < 32; ++a) s = fmaf(sSum[a], watt[a * 32 + tid], s);
+            const float c = tanhf(s / static_cast<float>(N));
+            sCtx[tid] = c;
+            T.actx[static_cast<size_t>(item) * 32 + tid] = c;
+        }
+        __syncthreads();
+        if (tid < N) {
+            float s = 0.0f;
+            for (int a = 0; a < 32; ++a) s = fmaf(sE[tid * 33 + a], sCtx[a], s);
+            const float av = sigmoidf_acc(s);
+            sAtt[tid] = av;
+            T.att[static_cast<size_t>(item) * N + tid] = av;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float s = 0.0f;
+            for (int n = 0; n < N; ++n) s = fmaf(sAtt[n], sE[n * 33 + tid], s);
+            T.pooled[static_cast<size_t>(item) * 32 + tid] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================================
+// Pair head forward (layers_batch.py:70-83, sg_net.py:131-136), mean BCE (sg_net.py:335) and the head's backward.
+// Persistent CTAs; parameter gradients in registers, written as one partial row of kHeadFloats per CTA.
+// =====================================================================================================================
+__global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs T, float* __restrict__ part) {
+    __shared__ float e12[64];              // e1 | e2 (the V-block input cat(e1, e2), layers_batch.py:80)
+    __shared__ float sP[512], sQ[512];
+    __shared__ float sS[16], sNt[16], sHpre[16], sH[16], sDh[16], sDs[16];
+    __shared__ float sDz;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t16 = tid >> 4, part16 = tid & 15;
+    const float* W = T.state + P_NTNW;
+    const float* V = T.state + P_NTNV;
+    const float* nb = T.state + P_NTNB;
+    const float* w1 = T.state + P_FC1W;
+    const float* b1 = T.state + P_FC1B;
+    const float* w2 = T.state + P_FC2W;
+    const float* b2 = T.state + P_FC2B;
+    const int G = T.G;
+    float gW[64], gV[4], gW1 = 0.0f, gNb = 0.0f, gB1 = 0.0f, gW2 = 0.0f, gB2 = 0.0f, loss = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 64; ++m) gW[m] = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) gV[m] = 0.0f;
+    const float* e1 = e12;
+    const float* e2 = e12 + 32;
+
+    for (int p = blockIdx.x; p < G; p += gridDim.x) {
+        if (tid < 64) e12[tid] = T.pooled[(static_cast<size_t>(tid >> 5) * G + p) * 32 + (tid & 31)];
+        __syncthreads();
+        for (int m = 0; m < 2; ++m) {                       // P[b*16+t] = sum_a e1[a] W[a][b][t]
+            const int bt = tid + 256 * m;
+            float acc = 0.0f;
+#pragma unroll 8
+            for (int a = 0; a < 32; ++a) acc = fmaf(e1[a], W[a * 512 + bt], acc);
+            sP[bt] = acc;
+        }
+        __syncthreads();
+        {   // s[t] = sum_b P[b][t] e2[b] + V[t] . cat + bias[t];  thread (t16, part16) sums a slice
+            float bil = fmaf(sP[(2 * part16 + 1) * 16 + t16], e2[2 * part16 + 1], __fmul_rn(sP[(2 * part16) * 16 + t16], e2[2 * part16]));
+            float blk = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) blk = fmaf(V[t16 * 64 + part16 * 4 + q], e12[part16 * 4 + q], blk);
+            bil = group16_sum(bil);
+            blk = group16_sum(blk);
+            if (part16 == 0) {
+                const float s = __fadd_rn(__fadd_rn(bil, blk), nb[t16]);
+                sS[t16] = s;
+                sNt[t16] = fmaxf(s, 0.0f);
+            }
+        }
+        __syncthreads();
+        {
+            float h = group16_sum(__fmul_rn(sNt[part16], w1[t16 * 16 + part16]));
+            if (part16 == 0) {
+                h = __fadd_rn(h, b1[t16]);
+                sHpre[t16] = h;
+                sH[t16] = fmaxf(h, 0.0f);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float z = lane < 16 ? __fmul_rn(sH[lane], w2[lane]) : 0.0f;
+            z = warp_sum(z);
+            if (lane == 0) {
+                const float pr = sigmoidf_acc(__fadd_rn(z, b2[0]));
+                const float tg = T.target[p];
+                T.pred[p] = pr;
+                // torch.nn.functional.binary_cross_entropy clamps both logs at -100
+                loss += -(tg * fmaxf(logf(pr), -100.0f) + (1.0f - tg) * fmaxf(logf(1.0f - pr), -100.0f));
+                sDz = (pr - tg) / static_cast<float>(G);
+            }
+        }
+        __syncthreads();
+        const float dz = sDz;
+        if (tid < 16) sDh[tid] = sHpre[tid] > 0.0f ? dz * w2[tid] : 0.0f;
+        __syncthreads();
+        if (tid < 16) {
+            float s = 0.0f;
+            for (int u = 0; u < 16; ++u) s = fmaf(sDh[u], w1[u * 16 + tid], s);
+            sDs[tid] = sS[tid] > 0.0f ? s : 0.0f;
+        }
+        __syncthreads();
+        const float q0 = e2[tid >> 4] * sDs[part16];               // q[b*16+t] = e2[b] ds[t], bt = tid
+        const float q1 = e2[16 + (tid >> 4)] * sDs[part16];        // bt = tid + 256
+        sQ[tid] = q0;
+        sQ[256 + tid] = q1;
+        // ---- parameter gradients ----
+#pragma unroll
+        for (int m = 0; m < 64; ++m) gW[m] = fmaf(e1[m >> 1], (m & 1) ? q1 : q0, gW[m]);    // flat index tid + 256 m
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { const int e = tid + 256 * m; gV[m] = fmaf(sDs[e >> 6], e12[e & 63], gV[m]); }
+        gW1 = fmaf(sDh[t16], sNt[part16], gW1);
+        if (tid < 16) {
+            gNb += sDs[tid];
+            gB1 += sDh[tid];
+            gW2 = fmaf(dz, sH[tid], gW2);
+        }
+        if (tid == 0) gB2 += dz;
+        __syncthreads();
+        // ---- d loss / d pooled vectors ----
+        for (int u = 0; u < 4; ++u) {                        // de1[a] = sum_bt W[a][bt] q[bt] + sum_t ds[t] V[t][a]
+            const int a = warp * 4 + u;
+            float s = 0.0f;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) s = fmaf(W[a * 512 + lane + 32 * i], sQ[lane + 32 * i], s);
+            s = warp_sum(s);
+            if (lane == 0) {
+                for (int t = 0; t < 16; ++t) s = fmaf(sDs[t], V[t * 64 + a], s);
+                T.dpooled[static_cast<size_t>(p) * 32 + a] = s;
+            }
+        }
+        if (tid < 32) {                                      // de2[b] = sum_t P[b][t] ds[t] + sum_t ds[t] V[t][32+b]
+            float s = 0.0f;
+            for (int t = 0; t < 16; ++t) s = fmaf(sP[tid * 16 + t], sDs[t], s);
+            for (int t = 0; t < 16; ++t) s = fmaf(sDs[t], V[t * 64 + 32 + tid], s);
+            T.dpooled[(static_cast<size_t>(G) + p) * 32 + tid] = s;
+        }
+        __syncthreads();
+    }
+    float* row = part + static_cast<size_t>(blockIdx.x) * kHeadFloats;
+#pragma unroll
+    for (int m = 0; m < 64; ++m) row[tid + 256 * m] = gW[m];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) row[16384 + tid + 256 * m] = gV[m];
+    row[16384 + 1024 + 16 + tid] = gW1;
+    if (tid < 16) {
+        row[16384 + 1024 + tid] = gNb;
+        row[16384 + 1024 + 16 + 256 + tid] = gB1;
+        row[16384 + 1024 + 16 + 256 + 16 + tid] = gW2;
+    }
+    if (tid == 0) {
+        row[kHeadFloats - 1] = gB2;
+        T.losspart[blockIdx.x] = loss;
+    }
+}
+
+// =====================================================================================================================
+// Attention backward + the LeakyReLU of conv_end: gz_end = d loss / d (conv_end BN output), dbeta/dgamma sums.
+// grid = multiple of 2, CTA -> side, loops g.  part: [grid][1024] attention.weight_matrix partials.
+// =====================================================================================================================
+__global__ void __launch_bounds__(kThreads) sgpr_train_att_bwd(const TrainWs T, float* __restrict__ part) {
+    __shared__ float sE[SGPR_MAX_NODES * 33];
+    __shared__ float sYh[SGPR_MAX_NODES * 33];
+    __shared__ float sPrm[4 * 32];
+    __shared__ float sDp[32], sCtx[32], sSum[32], sDcbar[32], sV[32], sAtt[SGPR_MAX_NODES], sDsig[SGPR_MAX_NODES];
+    __shared__ double sRed[8 * 64];
+    const int tid = threadIdx.x;
+    const int side = blockIdx.x & 1;
+    const int N = T.N;
+    const float* watt = T.state + P_ATT;
+    float gA[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    double accb = 0.0, accg = 0.0;                     // channel tid & 31
+    if (tid < 32) {
+        float mu, istd;
+        bn_coef(stat_ptr(T.stats, side, 6), tid, static_cast<double>(T.G) * N, T.eps, mu, istd);
+        sPrm[tid] = mu;
+        sPrm[32 + tid] = istd;
+        sPrm[64 + tid] = T.state[P_BN + bn_off(6) + tid];
+        sPrm[96 + tid] = T.state[P_BN + bn_off(6) + 32 + tid];
+    }
+    __syncthreads();
+    for (int g = blockIdx.x >> 1; g < T.G; g += gridDim.x >> 1) {
+        const size_t sg = static_cast<size_t>(side) * T.G + g;
+        const float* y = T.yend + sg * N * 32;
+        for (int e = tid; e < N * 32; e += kThreads) {
+            const int n = e >> 5, c = e & 31;
+            const float yh = __fmul_rn(__fsub_rn(y[e], sPrm[c]), sPrm[32 + c]);
+            sYh[n * 33 + c] = yh;
+            sE[n * 33 + c] = lrelu(fmaf(yh, sPrm[64 + c], sPrm[96 + c]));
+        }
+        if (tid < 32) {
+            sDp[tid] = T.dpooled[sg * 32 + tid];
+            sCtx[tid] = T.actx[sg * 32 + tid];
+            sSum[tid] = T.esum[sg * 32 + tid];
+        }
+        if (tid < N) sAtt[tid] = T.att[sg * N + tid];
+        __syncthreads();
+        if (tid < N) {
+            float s = 0.0f;
+            for (int a = 0; a < 32; ++a) s = fmaf(sE[tid * 33 + a], sDp[a], s);
+            const float av = sAtt[tid];
+            sDsig[tid] = s * av * (1.0f - av);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float s = 0.0f;
+            for (int n = 0; n < N; ++n) s = fmaf(sDsig[n], sE[n * 33 + tid], s);
+            const float c = sCtx[tid];
+            sDcbar[tid] = s * (1.0f - c * c) / static_cast<float>(N);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float s = 0.0f;
+            for (int b = 0; b < 32; ++b) s = fmaf(sDcbar[b], watt[tid * 32 + b], s);
+            sV[tid] = s;
+        }
+        __syncthreads();
+        float* gzo = T.gzend + sg * N * 32;
+        for (int e = tid; e < N * 32; e += kThreads) {
+            const int n = e >> 5, c = e & 31;
+            const float de = fmaf(sAtt[n], sDp[c], fmaf(sDsig[n], sCtx[c], sV[c]));
+            const float gzv = de * slope_of(sE[n * 33 + c]);
+            gzo[e] = gzv;
+            accb += static_cast<double>(gzv);
+            accg += static_cast<double>(gzv) * static_cast<double>(sYh[n * 33 + c]);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { const int e = tid + 256 * m; gA[m] = fmaf(sSum[e >> 5], sDcbar[e & 31], gA[m]); }
+        __syncthreads();
+    }
+    float* row = part + static_cast<size_t>(blockIdx.x) * 1024;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) row[tid + 256 * m] = gA[m];
+    sRed[(tid >> 5) * 64 + (tid & 31)] = accb;
+    sRed[(tid >> 5) * 64 + 32 + (tid & 31)] = accg;
+    __syncthreads();
+    if (tid < 64) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += sRed[w * 64 + tid];
+        atomicAdd(stat_ptr(T.bsum, side, 6) + (tid >> 5) * 64 + (tid & 31), s);
+    }
+}
+
+// =====================================================================================================================
+// conv_end backward: BatchNorm backward with the complete dbeta/dgamma, d cat(xyz3, sem3), dW_end, and the gz of the
+// two third EdgeConv layers (+ their dbeta/dgamma sums).  grid = multiple of 2, CTA -> side.  part: [grid][2048].
+// =====================================================================================================================
+template <int NPL>
+__global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_bwd(const TrainWs T, float* __restrict__ part) {
+    constexpr int NMAX = 32 * NPL;
+    constexpr int DS = 36;                                        // row stride of the dy tile
+    SGPR_DYN_SMEM(smem);
+    float* sWn = reinterpret_cast<float*>(smem);                // [32][64] natural
+    float* sX = sWn + 32 * 64;                                  // [NMAX][XS] cat(xyz3, sem3)
+    float* sDy = sX + NMAX * XS;                                // [NMAX][DS]
+    float* sPrm = sDy + NMAX * DS;                              // [4][64] previous-layer BN terms
+    float* sEnd = sPrm + 256;                                   // [4][32]: mu, istd, s, (unused) | dbeta/e, dgamma/e
+    double* sRed = reinterpret_cast<double*>(sEnd + 192);       // [4][128]
+    const int tid = threadIdx.x;
+    const int side = blockIdx.x & 1;
+    const int N = T.N;
+    const double e_end = static_cast<double>(T.G) * N;
+    for (int e = tid; e < 32 * 64; e += kThreads) sWn[e] = T.state[P_ENDW + e];
+    for (int e = tid; e < NMAX * XS; e += kThreads) sX[e] = 0.0f;
+    if (tid < 64) {
+        const int L = tid < 32 ? 2 : 5, c = tid & 31;
+        float mu, istd;
+        bn_coef(stat_ptr(T.stats, side, L), c, static_cast<double>(T.G) * N * T.k, T.eps, mu, istd);
+        sPrm[tid] = mu;
+        sPrm[64 + tid] = istd;
+        sPrm[128 + tid] = T.state[P_BN + bn_off(L) + c];
+        sPrm[192 + tid] = T.state[P_BN + bn_off(L) + 32 + c];
+    }
+    if (tid < 32) {
+        float mu, istd;
+        bn_coef(stat_ptr(T.stats, side, 6), tid, e_end, T.eps, mu, istd);
+        const double* bs = stat_ptr(T.bsum, side, 6);
+        sEnd[tid] = mu;
+        sEnd[32 + tid] = istd;
+        sEnd[64 + tid] = T.state[P_BN + bn_off(6) + tid] * istd;
+        sEnd[96 + tid] = static_cast<float>(bs[tid] / e_end);
+        sEnd[128 + tid] = static_cast<float>(bs[64 + tid] / e_end);
+    }
+    __syncthreads();
+    float gW[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) gW[m] = 0.0f;
+    double accb = 0.0, accg = 0.0;                     // channel tid & 63 of cat
+    const int f0 = 2 * (tid >> 4), c0 = 4 * (tid & 15);
+    for (int g = blockIdx.x >> 1; g < T.G; g += gridDim.x >> 1) {
+        const size_t sg = static_cast<size_t>(side) * T.G + g;
+        const float* y2 = T.yext[2] + sg * N * 32;
+        const float* y5 = T.yext[5] + sg * N * 32;
+        for (int e = tid; e < N * 64; e += kThreads) {
+            const int n = e >> 6, c = e & 63;
+            const float y = c < 32 ? y2[n * 32 + c] : y5[n * 32 + c - 32];
+            sX[n * XS + c] = bn_act(y, sPrm[c], sPrm[64 + c], sPrm[128 + c], sPrm[192 + c]);
+        }
+        const float* ye = T.yend + sg * N * 32;
+        const float* gze = T.gzend + sg * N * 32;
+        for (int e = tid; e < N * 32; e += kThreads) {
+            const int n = e >> 5, c = e & 31;
+            const float yh = __fmul_rn(__fsub_rn(ye[e], sEnd[c]), sEnd[32 + c]);
+            sDy[n * DS + c] = sEnd[64 + c] * (gze[e] - sEnd[96 + c] - yh * sEnd[128 + c]);
+        }
+        __syncthreads();
+        float* gz2 = T.gz[2] + sg * N * 32;
+        float* gz5 = T.gz[5] + sg * N * 32;
+        for (int e = tid; e < N * 64; e += kThreads) {             // d cat[n][c] = sum_f dy[n][f] W[f][c]
+            const int n = e >> 6, c = e & 63;
+            float s = 0.0f;
+#pragma unroll 8
+            for (int f = 0; f < 32; ++f) s = fmaf(sDy[n * DS + f], sWn[f * 64 + c], s);
+            const float gzv = s * slope_of(sX[n * XS + c]);
+            const float yprev = c < 32 ? y2[n * 32 + c] : y5[n * 32 + c - 32];
+            const float yh = __fmul_rn(__fsub_rn(yprev, sPrm[c]), sPrm[64 + c]);
+            if (c < 32) gz2[n * 32 + c] = gzv; else gz5[n * 32 + c - 32] = gzv;
+            accb += static_cast<double>(gzv);
+            accg += static_cast<double>(gzv) * static_cast<double>(yh);
+        }
+        for (int n = 0; n < N; ++n) {                              // dW_end[f][c] += dy[n][f] cat[n][c]
+            const float2 dy = *reinterpret_cast<const float2*>(sDy + n * DS + f0);
+            const float4 x = *reinterpret_cast<const float4*>(sX + n * XS + c0);
+            gW[0] = fmaf(dy.x, x.x, gW[0]); gW[1] = fmaf(dy.x, x.y, gW[1]); gW[2] = fmaf(dy.x, x.z, gW[2]); gW[3] = fmaf(dy.x, x.w, gW[3]);
+            gW[4] = fmaf(dy.y, x.x, gW[4]); gW[5] = fmaf(dy.y, x.y, gW[5]); gW[6] = fmaf(dy.y, x.z, gW[6]); gW[7] = fmaf(dy.y, x.w, gW[7]);
+        }
+        __syncthreads();
+    }
+    float* row = part + static_cast<size_t>(blockIdx.x) * 2048;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) row[(f0 + u) * 64 + c0 + v] = gW[u * 4 + v];
+    sRed[(tid >> 6) * 128 + (tid & 63)] = accb;
+    sRed[(tid >> 6) * 128 + 64 + (tid & 63)] = accg;
+    __syncthreads();
+    if (tid < 128) {
+        const int which = tid >> 6, c = tid & 63;
+        double s = 0.0;
+        for (int w = 0; w < 4; ++w) s += sRed[w * 128 + tid];
+        atomicAdd(stat_ptr(T.bsum, side, c < 32 ? 2 : 5) + which * 64 + (c & 31), s);
+    }
+}
+
+// =====================================================================================================================
+// EdgeConv layer l backward for both branches and both sides (grid = multiple of 4, CTA -> (branch, side), loops g).
+// part: [grid/2 per branch][cout * 2 cin] conv-weight partials in the state_dict layout.
+// =====================================================================================================================
+struct BwdSmem { int w, x, gz, d, da, en, adj, radj, c, prm, red, total; };
+__host__ __device__ inline BwdSmem bwd_layout(int nmax) {
+    BwdSmem L;
+    int o = 0;
+    L.w = o;    o += 64 * 128 * 4;
+    L.x = o;    o += nmax * XS * 4;
+    L.gz = o;   o += nmax * XS * 4;
+    L.d = o;    o += nmax * XS * 4;
+    L.da = o;   o += nmax * XS * 4;
+    L.en = o;   o += nmax * 64;
+    L.adj = o;  o += nmax * 16;
+    L.radj = o; o += nmax * 16;
+    L.c = o;    o += 4 * 64 * 4;
+    L.prm = o;  o += 4 * 64 * 4;
+    L.red = o;  o += kWarps * 128 * 8;
+    L.total = o;
+    return L;
+}
+
+// dWa[c][ci] += sum_n dA[n][c] x[n][ci], dWb likewise with dB: thread tile CPT output channels x 4 input channels
+template <int CPT>
+__device__ __forceinline__ void accum_dw(const float* __restrict__ sX, const float* __restrict__ sDA,
+                                         const float* __restrict__ sDB, int N, int c0, int ci0, float (&ga)[16], float (&gb)[16]) {
+    for (int n = 0; n < N; ++n) {
+        const float4 x = *reinterpret_cast<const float4*>(sX + n * XS + ci0);
+        float da[CPT], db[CPT];
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) { da[u] = sDA[n * XS + c0 + u]; db[u] = sDB[n * XS + c0 + u]; }
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) {
+            ga[u * 4 + 0] = fmaf(da[u], x.x, ga[u * 4 + 0]); ga[u * 4 + 1] = fmaf(da[u], x.y, ga[u * 4 + 1]);
+            ga[u * 4 + 2] = fmaf(da[u], x.z, ga[u * 4 + 2]); ga[u * 4 + 3] = fmaf(da[u], x.w, ga[u * 4 + 3]);
+            gb[u * 4 + 0] = fmaf(db[u], x.x, gb[u * 4 + 0]); gb[u * 4 + 1] = fmaf(db[u], x.y, gb[u * 4 + 1]);
+            gb[u * 4 + 2] = fmaf(db[u], x.z, gb[u * 4 + 2]); gb[u * 4 + 3] = fmaf(db[u], x.w, gb[u * 4 + 3]);
+        }
+    }
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_bwd(const TrainWs T, int l, float* __restrict__ part0,
+                                                                                   float* __restrict__ part1) {
+    constexpr int NMAX = 32 * NPL;
+    constexpr int SLOTS = 4 * NPL;                    // nodes per warp
+    SGPR_DYN_SMEM(smem);
+    const BwdSmem S = bwd_layout(NMAX);
+    float* sWn = reinterpret_cast<float*>(smem + S.w);          // natural [cout][2 cin]
+    float* sX = reinterpret_cast<float*>(smem + S.x);
+    float* sGZ = reinterpret_cast<float*>(smem + S.gz);         // gz, later dB
+    float* sD = reinterpret_cast<float*>(smem + S.d);
+    float* sDA = reinterpret_cast<float*>(smem + S.da);
+    uint8_t* sEN = smem + S.en;
+    unsigned long long* sAdj = reinterpret_cast<unsigned long long*>(smem + S.adj);     // [NMAX][2]
+    unsigned long long* sRadj = reinterpret_cast<unsigned long long*>(smem + S.radj);
+    float* sC = reinterpret_cast<float*>(smem + S.c);           // s | q | r | (spare)
+    float* sPrm = reinterpret_cast<float*>(smem + S.prm);       // previous layer: mu | istd | gamma | beta
+    double* sRed = reinterpret_cast<double*>(smem + S.red);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int br = blockIdx.x & 1, side = (blockIdx.x >> 1) & 1;
+    const int L = br * 3 + l;
+    const int cin = layer_cin(L), cout = layer_cout(L), cpl = cout / 32;
+    const int N = T.N, k = T.k;
+    const double e_edge = static_cast<double>(T.G) * N * k;
+
+    for (int e = tid; e < cout * 2 * cin; e += kThreads) sWn[e] = T.state[conv_off(L) + e];
+    for (int e = tid; e < NMAX * XS; e += kThreads) sX[e] = 0.0f;
+    if (tid < cout) {
+        float mu, istd;
+        bn_coef(stat_ptr(T.stats, side, L), tid, e_edge, T.eps, mu, istd);
+        const double* bs = stat_ptr(T.bsum, side, L);
+        const float s = T.state[P_BN + bn_off(L) + tid] * istd;
+        const float pterm = s * static_cast<float>(bs[tid] / e_edge);
+        const float q = s * static_cast<float>(bs[64 + tid] / e_edge) * istd;
+        sC[tid] = s;
+        sC[64 + tid] = q;
+        sC[128 + tid] = pterm - q * mu;
+    }
+    __syncthreads();
+
+    float ga[16], gb[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) { ga[m] = 0.0f; gb[m] = 0.0f; }
+    double accb[2] = {0.0, 0.0}, accg[2] = {0.0, 0.0};          // previous layer's channels 2*lane, 2*lane+1
+    const int rpw = (N + kWarps - 1) / kWarps;
+    const int w0 = min(N, warp * rpw), w1 = min(N, w0 + rpw);
+    const float kf = static_cast<float>(k);
+
+    for (int g = blockIdx.x >> 2; g < T.G; g += gridDim.x >> 2) {
+        const size_t sg = static_cast<size_t>(side) * T.G + g;
+        const size_t o = sg * N * cout;
+        fill_layer_input(T, l, br, side, g, sX, sPrm, tid);
+        {
+            const float* gz = T.gz[L] + o;
+            const float* gd = T.d[L] + o;
+            const uint8_t* en = T.enode[L] + o;
+            for (int e = tid; e < N * cout; e += kThreads) {
+                const int n = e / cout, c = e - n * cout;
+                sGZ[n * XS + c] = gz[e];
+                sD[n * XS + c] = gd[e];
+                sEN[n * 64 + c] = en[e];
+            }
+            if (tid < N) {
+                const uint8_t* gi = T.idx[L] + (sg * N + tid) * k;
+                unsigned long long m0 = 0ull, m1 = 0ull;
+                for (int e = 0; e < k; ++e) {
+                    const int j = gi[e];
+                    if (j < 64) m0 |= 1ull << j; else m1 |= 1ull << (j - 64);
+                }
+                sAdj[2 * tid] = m0;
+                sAdj[2 * tid + 1] = m1;
+            }
+        }
+        __syncthreads();
+        if (tid < N) {                                           // reverse adjacency: who lists node tid
+            unsigned long long m0 = 0ull, m1 = 0ull;
+            for (int i = 0; i < N; ++i) {
+                const unsigned long long w = sAdj[2 * i + (tid >> 6)];
+                if ((w >> (tid & 63)) & 1ull) { if (i < 64) m0 |= 1ull << i; else m1 |= 1ull << (i - 64); }
+            }
+            sRadj[2 * tid] = m0;
+            sRadj[2 * tid + 1] = m1;
+        }
+        __syncthreads();
+        // ---- per-node terms: warp -> nodes warp, warp + 8, ...; lane -> channels lane*cpl + p ----
+        float treg[SLOTS][2];
+        {
+            const float* ga_ = T.a[L] + o;
+            const float* gs_ = T.sumy[L] + o;
+            int slot = 0;
+            for (int n = warp; n < N; n += kWarps, ++slot) {
+                unsigned long long m[2] = {sRadj[2 * n], sRadj[2 * n + 1]};
+                const float deg = static_cast<float>(__popcll(m[0]) + __popcll(m[1]));
+                float s1[2] = {0.0f, 0.0f}, s2[2] = {0.0f, 0.0f};
+                for (int h = 0; h < 2; ++h) {
+                    unsigned long long mm = m[h];
+                    while (mm) {
+                        const int i = 64 * h + __ffsll(static_cast<long long>(mm)) - 1;
+                        mm &= mm - 1ull;
+                        for (int p = 0; p < cpl; ++p) {
+                            const int c = lane * cpl + p;
+                            s2[p] = __fadd_rn(s2[p], sD[i * XS + c]);
+                            if (sEN[i * 64 + c] == n) s1[p] = __fadd_rn(s1[p], sGZ[i * XS + c]);
+                        }
+                    }
+                }
+                for (int p = 0; p < cpl; ++p) {
+                    const int c = lane * cpl + p;
+                    const float s = sC[c], q = sC[64 + c], r = sC[128 + c];
+                    const float t = s * sGZ[n * XS + c] - kf * r - q * gs_[n * cout + c];
+                    sDA[n * XS + c] = -t + s * s1[p] - deg * (r + q * ga_[n * cout + c]) - q * s2[p];
+                    treg[slot][p] = t;
+                }
+            }
+        }
+        __syncthreads();                                        // every S1 read of gz is done: dB may replace it
+        {
+            int slot = 0;
+            for (int n = warp; n < N; n += kWarps, ++slot)
+                for (int p = 0; p < cpl; ++p) sGZ[n * XS + lane * cpl + p] = treg[slot][p];
+        }
+        __syncthreads();
+        // ---- dX = dA Wa + dB Wb -> gz of the layer below (+ its dbeta / dgamma sums) ----
+        if (l > 0) {
+            const float* yp = T.yext[L - 1] + sg * N * 64;
+            float* gzp = T.gz[L - 1] + sg * N * 64;
+            for (int r0 = w0; r0 < w1; r0 += 4) {
+                float2 acc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] = make_float2(0.0f, 0.0f);
+                int rows[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rows[u] = min(r0 + u, w1 - 1);
+                for (int c = 0; c < cout; ++c) {
+                    const float2 wa = *reinterpret_cast<const float2*>(sWn + c * 128 + 2 * lane);
+                    const float2 wb = *reinterpret_cast<const float2*>(sWn + c * 128 + 64 + 2 * lane);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float da = sDA[rows[u] * XS + c], db = sGZ[rows[u] * XS + c];
+                        acc[u].x = fmaf(da, wa.x, acc[u].x); acc[u].y = fmaf(da, wa.y, acc[u].y);
+                        acc[u].x = fmaf(db, wb.x, acc[u].x); acc[u].y = fmaf(db, wb.y, acc[u].y);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (r0 + u < w1) {
+                        const int n = r0 + u;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int ci = 2 * lane + h;
+                            const float dx = h ? acc[u].y : acc[u].x;
+                            const float gzv = dx * slope_of(sX[n * XS + ci]);
+                            gzp[n * 64 + ci] = gzv;
+                            const float yh = __fmul_rn(__fsub_rn(yp[n * 64 + ci], sPrm[ci]), sPrm[64 + ci]);
+                            accb[h] += static_cast<double>(gzv);
+                            accg[h] += static_cast<double>(gzv) * static_cast<double>(yh);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- conv-weight gradient tiles ----
+        if (cin == 64) {
+            if (cout == 64) accum_dw<4>(sX, sDA, sGZ, N, 4 * (tid >> 4), 4 * (tid & 15), ga, gb);
+            else            accum_dw<2>(sX, sDA, sGZ, N, 2 * (tid >> 4), 4 * (tid & 15), ga, gb);
+        } else if (cin == 12) {
+            accum_dw<1>(sX, sDA, sGZ, N, tid >> 2, 4 * (tid & 3), ga, gb);
+        } else if (tid < 64) {
+            accum_dw<1>(sX, sDA, sGZ, N, tid, 0, ga, gb);
+        }
+        __syncthreads();
+    }
+    // ---- partial rows: [cout][Wa(cin) | Wb(cin)] ----
+    float* row = (br ? part1 : part0) + static_cast<size_t>(blockIdx.x >> 1) * (cout * 2 * cin);
+    {
+        int cpt, c0, ci0;
+        bool active = true;
+        if (cin == 64) { cpt = cout == 64 ? 4 : 2; c0 = cpt * (tid >> 4); ci0 = 4 * (tid & 15); }
+        else if (cin == 12) { cpt = 1; c0 = tid >> 2; ci0 = 4 * (tid & 3); }
+        else { cpt = 1; c0 = tid; ci0 = 0; active = tid < 64; }
+        if (active) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u < cpt) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        if (ci0 + v < cin) {
+                            row[(c0 + u) * 2 * cin + ci0 + v] = ga[u * 4 + v];
+                            row[(c0 + u) * 2 * cin + cin + ci0 + v] = gb[u * 4 + v];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (l > 0) {
+        __syncthreads();
+        sRed[warp * 128 + 2 * lane] = accb[0];
+        sRed[warp * 128 + 2 * lane + 1] = accb[1];
+        sRed[warp * 128 + 64 + 2 * lane] = accg[0];
+        sRed[warp * 128 + 64 + 2 * lane + 1] = accg[1];
+        __syncthreads();
+        if (tid < 128) {
+            double s = 0.0;
+            for (int w = 0; w < kWarps; ++w) s += sRed[w * 128 + tid];
+            atomicAdd(stat_ptr(T.bsum, side, L - 1) + tid, s);
+        }
+    }
+}
+
+// =====================================================================================================================
+// Optimiser: gradient = fixed-order sum of the partials (BN gamma/beta: the fp64 sums of both sides); torch.optim.Adam
+// with L2 weight decay (sg_net.py:351-352); BatchNorm running statistics, side 1 then side 2; mean loss.
+// =====================================================================================================================
+struct AdamArgs {
+    float lr, wd, b1, b2, eps;
+    float bc1;          // 1 - b1^t
+    float bc2_sqrt;     // sqrt(1 - b2^t)
+    int apply;          // 0: gradients only (no parameter, moment or running-statistics update)
+};
+
+__global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs T, const AdamArgs A) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < T.head_grid; ++i) s += T.losspart[i];
+        T.loss[0] = s / static_cast<float>(T.G);
+    }
+    if (e < P_TOTAL) {
+        float g = 0.0f;
+        if (e >= P_BN && e < P_BN + kBnFloats) {
+            int L = 6;
+            while (bn_off(L) > e - P_BN) --L;
+            const int C = layer_cout(L), r = e - P_BN - bn_off(L);
+            const int which = r < C ? 1 : 0, c = r < C ? r : r - C;        // gamma <- dgamma (slot 1), beta <- dbeta (slot 0)
+            g = static_cast<float>(stat_ptr(T.bsum, 0, L)[which * 64 + c] + stat_ptr(T.bsum, 1, L)[which * 64 + c]);
+        } else {
+            for (int s = 0; s < T.nseg; ++s) {
+                const Segment& sg = T.seg[s];
+                if (e >= sg.off && e < sg.off + sg.size) {
+                    const float* p = sg.part + (e - sg.off);
+                    for (int j = 0; j < sg.count; ++j) g += p[static_cast<size_t>(j) * sg.stride];
+                    break;
+                }
+            }
+        }
+        T.grads[e] = g;
+        if (A.apply) {
+            const float p = T.state[e];
+            g = fmaf(A.wd, p, g);
+            const float m = A.b1 * T.adam_m[e] + (1.0f - A.b1) * g;
+            const float v = A.b2 * T.adam_v[e] + (1.0f - A.b2) * g * g;
+            T.adam_m[e] = m;
+            T.adam_v[e] = v;
+            const float denom = sqrtf(v) / A.bc2_sqrt + A.eps;
+            T.state[e] = p - (A.lr / A.bc1) * (m / denom);
+        }
+    } else if (e < STATE_TOTAL && A.apply) {
+        int L = 6;
+        const int r0 = e - R_OFF;
+        while (bn_off(L) > r0) --L;
+        const int C = layer_cout(L), r = r0 - bn_off(L);
+        const int is_var = r >= C, c = is_var ? r - C : r;
+        const double cnt = (L == 6) ? static_cast<double>(T.G) * T.N : static_cast<double>(T.G) * T.N * T.k;
+        float run = T.state[e];
+        for (int side = 0; side < 2; ++side) {
+            const double* st = stat_ptr(T.stats, side, L);
+            const double m = st[c] / cnt;
+            double var = st[64 + c] / cnt - m * m;
+            var = var > 0.0 ? var : 0.0;
+            const float val = is_var ? static_cast<float>(var * cnt / (cnt - 1.0)) : static_cast<float>(m);
+            run = (1.0f - kMomentum) * run + kMomentum * val;
+        }
+        T.state[e] = run;
+    }
+}
+
+}  // namespace train
+}  // namespace sgpr

@@ -166,6 +166,21 @@ class _DeviceReplica(torch.nn.Module):
         return self.module(*inputs, **kwargs)
 
 
+class _DeviceAdam:
+    """What `self.optimizer` is in this drop-in: torch.optim.Adam's role (sg_net.py:351-352) is played by the Adam
+    kernel that ends every device training step, so zero_grad()/step() have nothing left to do on the host."""
+
+    def __init__(self, trainer):
+        self.defaults = {"lr": float(trainer.args.learning_rate), "weight_decay": float(trainer.args.weight_decay),
+                         "betas": (0.9, 0.999), "eps": 1e-8}
+
+    def zero_grad(self, set_to_none=True):
+        return None
+
+    def step(self, closure=None):
+        return None
+
+
 class SGTrainer(object):
     """Trainer / evaluator with the reference's public surface (sg_net.py:141-564)."""
 
@@ -290,8 +305,37 @@ class SGTrainer(object):
                 "target": torch.FloatTensor(np.array(targets))}
 
     # ---- training ------------------------------------------------------------------------------------------------
+    def _device_trainer(self):
+        """The device-resident training state (csrc/train_kernels.cuh): created on first use from the module's current
+        parameters, with the optimiser settings the reference passes to torch.optim.Adam (sg_net.py:351-352)."""
+        if getattr(self, "_train_engine", None) is None:
+            from .train_engine import TrainEngine
+            self._train_engine = TrainEngine(torch.device("cuda", int(self.args.gpu)))
+            self._train_engine.set_state(self.model.module.state_dict(), reset_optimizer=True)
+            self._train_engine.set_optimizer(float(self.args.learning_rate), float(self.args.weight_decay))
+            self._unsynced_steps = 0
+        return self._train_engine
+
+    def sync_model_from_device(self):
+        """Copy the parameters / running statistics the training kernels hold back into `self.model` (before an
+        eval-mode pass, `state_dict()` or `torch.save`).  num_batches_tracked advances by 2 per step: every BatchNorm
+        runs once per side (sg_net.py:123-124)."""
+        eng = getattr(self, "_train_engine", None)
+        if eng is None or not getattr(self, "_unsynced_steps", 0):
+            return
+        module = self.model.module
+        state = eng.get_state()
+        with torch.no_grad():
+            for name, target in module.state_dict().items():
+                if name in state:
+                    target.copy_(state[name].reshape(target.shape))
+                elif name.endswith("num_batches_tracked"):
+                    target.add_(2 * self._unsynced_steps)
+        self._unsynced_steps = 0
+
     def process_batch(self, batch, training=True):
-        """sg_net.py:312-345: every listed pair is fed in both orders; BCE; (training) backward + Adam step."""
+        """sg_net.py:312-345: every listed pair is fed in both orders; BCE; (training) backward + Adam step — the whole
+        device part of a training step is ONE call into the C-ABI (sgpr_train_step)."""
         self.optimizer.zero_grad()
         f1, f2, targets = [], [], []
         for graph_pair in batch:
@@ -300,19 +344,24 @@ class SGTrainer(object):
             f2 += [data["features_2"], data["features_1"]]
             targets += [data["target"], data["target"]]
         data = self._stack(f1, f2, targets)
+        if training:
+            eng = self._device_trainer()
+            dev = eng.device
+            loss, prediction = eng.step(data["features_1"].to(dev, non_blocking=True),
+                                        data["features_2"].to(dev, non_blocking=True),
+                                        data["target"].to(dev, non_blocking=True), int(self.args.K), apply=True)
+            self._unsynced_steps += 1
+            return (loss.item(), prediction.cpu().numpy().reshape(-1), data["target"].numpy().reshape(-1))
+        self.sync_model_from_device()
         prediction, _, _ = self.model(data)
         losses = torch.mean(torch.nn.functional.binary_cross_entropy(prediction, data["target"].to(prediction.device)))
-        if training:
-            losses.backward()
-            self.optimizer.step()
         return (losses.item(), prediction.cpu().detach().numpy().reshape(-1),
                 data["target"].cpu().detach().numpy().reshape(-1))
 
     def fit(self):
         """sg_net.py:347-384."""
         print("\nModel training.\n")
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.args.learning_rate,
-                                          weight_decay=self.args.weight_decay)
+        self.optimizer = _DeviceAdam(self)
         f1_max_his = 0
         self.model.train()
         epochs = trange(self.args.epochs, leave=True, desc="Epoch")
@@ -337,6 +386,7 @@ class SGTrainer(object):
                 self.writer.add_scalar("eval_loss", loss, step)
                 self.writer.add_scalar("f1_max_score", f1_max, step)
                 os.makedirs(self.args.logdir, exist_ok=True)
+                self.sync_model_from_device()
                 torch.save(self.model.state_dict(), self.args.logdir + "/" + str(epoch) + ".pth")
                 if f1_max_his <= f1_max:
                     f1_max_his = f1_max
@@ -355,8 +405,8 @@ class SGTrainer(object):
             print("Check split: ", split)
             exit(-1)
         if not hasattr(self, "optimizer"):     # the reference crashes here unless fit() ran first (sg_net.py:318)
-            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.args.learning_rate,
-                                              weight_decay=self.args.weight_decay)
+            self.optimizer = _DeviceAdam(self)
+        self.sync_model_from_device()
         losses, pred_db, gt_db = 0, [], []
         batches = self.create_batches(split="eval")
         for index, batch in tqdm(enumerate(batches), total=len(batches), desc="Eval Batches"):

@@ -1,0 +1,139 @@
+"""Host side of the device training step (include/sgpr_b200_train.h): flat state <-> state_dict, one call per step.
+
+What it stands in for is the device half of `SGTrainer.process_batch(batch, training=True)` (/root/reference/sg_net.py:
+332-338): train-mode forward, mean BCE, backward and the Adam update, all in csrc/train_kernels.cuh.  No method here
+has a CPU or eager-PyTorch implementation behind it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# state_dict shapes of the tensors in the flat layout (sg_net.py:44-76, layers_batch.py:16-18, 58-60)
+SHAPES = {
+    "dgcnn_s_conv1.0.weight": (64, 6, 1, 1), "dgcnn_s_conv2.0.weight": (64, 128, 1, 1),
+    "dgcnn_s_conv3.0.weight": (32, 128, 1, 1), "dgcnn_f_conv1.0.weight": (64, 24, 1, 1),
+    "dgcnn_f_conv2.0.weight": (64, 128, 1, 1), "dgcnn_f_conv3.0.weight": (32, 128, 1, 1),
+    "dgcnn_conv_end.0.weight": (32, 64, 1), "attention.weight_matrix": (32, 32),
+    "tensor_network.weight_matrix": (32, 32, 16), "tensor_network.weight_matrix_block": (16, 64),
+    "tensor_network.bias": (16, 1), "fully_connected_first.weight": (16, 16), "fully_connected_first.bias": (16,),
+    "scoring_layer.weight": (1, 16), "scoring_layer.bias": (1,),
+}
+BN_LAYERS = ("dgcnn_s_conv1.1", "dgcnn_s_conv2.1", "dgcnn_s_conv3.1", "dgcnn_f_conv1.1", "dgcnn_f_conv2.1",
+             "dgcnn_f_conv3.1", "dgcnn_conv_end.1")
+
+
+def layout(lib=None) -> Tuple[List[Tuple[str, int, int]], int]:
+    """[(name, offset, size)] of the flat state vector and how many of the entries are trainable parameters."""
+    lib = lib or _lib.load()
+    count, n_params = C.c_int(), C.c_int()
+    names = C.POINTER(C.c_char_p)()
+    offs, sizes = _lib.c_i64_p(), _lib.c_i64_p()
+    _lib.check(lib.sgpr_train_layout(C.byref(count), C.byref(n_params), C.byref(names), C.byref(offs), C.byref(sizes)),
+               "sgpr_train_layout", lib)
+    return [(names[i].decode(), int(offs[i]), int(sizes[i])) for i in range(count.value)], n_params.value
+
+
+class TrainEngine:
+    """Device-resident parameters + Adam moments; `step()` is one optimiser step on a batch of ordered pairs."""
+
+    def __init__(self, device=0, lib=None):
+        self._lib = lib or _lib.load()
+        self._emulated = lib is not None           # tests/emu only: buffers are host memory
+        self.device = torch.device("cpu") if self._emulated else torch.device("cuda", int(torch.device(device).index or 0)
+                                                                              if not isinstance(device, int) else device)
+        self.layout, self.n_param_tensors = layout(self._lib)
+        self.n_params = int(self._lib.sgpr_train_param_count())
+        self.n_state = int(self._lib.sgpr_train_state_count())
+        handle = C.c_void_p()
+        _lib.check(self._lib.sgpr_train_create(C.byref(handle), 0 if self._emulated else self.device.index),
+                   "sgpr_train_create", self._lib)
+        self._h = handle
+        self._shape = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sgpr_train_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ------------------------------------------------------------------------------------------------------
+    def set_state(self, state: Dict[str, torch.Tensor], reset_optimizer: bool = True):
+        flat = np.zeros(self.n_state, dtype=np.float32)
+        for name, off, size in self.layout:
+            v = state[name].detach().to("cpu", torch.float32).contiguous().numpy().reshape(-1)
+            if v.size != size:
+                raise RuntimeError(f"size mismatch for {name}: checkpoint has {v.size} values, the kernels expect {size}")
+            flat[off:off + size] = v
+            self._shape[name] = tuple(state[name].shape)
+        _lib.check(self._lib.sgpr_train_set_state(self._h, flat.ctypes.data_as(C.c_void_p), int(reset_optimizer)),
+                   "sgpr_train_set_state", self._lib)
+
+    def _unflatten(self, flat: np.ndarray, entries) -> Dict[str, torch.Tensor]:
+        out = {}
+        for name, off, size in entries:
+            shape = self._shape.get(name) or SHAPES.get(name) or (size,)
+            out[name] = torch.from_numpy(flat[off:off + size].copy()).reshape(shape)
+        return out
+
+    def get_state(self) -> Dict[str, torch.Tensor]:
+        flat = np.empty(self.n_state, dtype=np.float32)
+        _lib.check(self._lib.sgpr_train_get_state(self._h, flat.ctypes.data_as(C.c_void_p)), "sgpr_train_get_state", self._lib)
+        return self._unflatten(flat, self.layout)
+
+    def grads(self) -> Dict[str, torch.Tensor]:
+        flat = np.empty(self.n_params, dtype=np.float32)
+        _lib.check(self._lib.sgpr_train_get_grads(self._h, flat.ctypes.data_as(C.c_void_p)), "sgpr_train_get_grads", self._lib)
+        return self._unflatten(flat, self.layout[:self.n_param_tensors])
+
+    def set_optimizer(self, lr: float, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8):
+        _lib.check(self._lib.sgpr_train_set_optimizer(self._h, lr, weight_decay, betas[0], betas[1], eps),
+                   "sgpr_train_set_optimizer", self._lib)
+
+    # ---- the step -----------------------------------------------------------------------------------------------------
+    def _buf(self, t: torch.Tensor, what: str) -> torch.Tensor:
+        if t.dtype != torch.float32:
+            raise TypeError(f"{what} must be float32")
+        if t.device != self.device:
+            raise RuntimeError(f"{what} must live on {self.device} (got {t.device})")
+        return t.contiguous()
+
+    def step(self, f1: torch.Tensor, f2: torch.Tensor, target: torch.Tensor, k: int, apply: bool = True):
+        """f1, f2 [B,15,N], target [B] on the device -> (loss [1], prediction [B]) device tensors (pre-update)."""
+        f1, f2, target = self._buf(f1, "features_1"), self._buf(f2, "features_2"), self._buf(target, "target")
+        if f1.dim() != 3 or f1.shape[1] != 15 or f2.shape != f1.shape or target.shape != (f1.shape[0],):
+            raise ValueError(f"expected features [B,15,N] x2 and target [B], got {tuple(f1.shape)}, {tuple(f2.shape)}, "
+                             f"{tuple(target.shape)}")
+        B, _, N = f1.shape
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        pred = torch.empty(B, dtype=torch.float32, device=self.device)
+        stream = None if self._emulated else C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self._lib.sgpr_train_step(self._h, f1.data_ptr(), f2.data_ptr(), target.data_ptr(), B, N, int(k),
+                                             loss.data_ptr(), pred.data_ptr(), int(apply), stream),
+                   "sgpr_train_step", self._lib)
+        return loss, pred
+
+    def step_count(self) -> int:
+        return int(self._lib.sgpr_train_step_count(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.sgpr_train_launch_count(self._h))
+
+    def debug_read(self, what: str, layer: int, shape, dtype=np.float32) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        n = self._lib.sgpr_train_debug_read(self._h, what.encode(), layer, out.ctypes.data_as(C.c_void_p), out.nbytes)
+        if n < 0:
+            _lib.check(int(n), "sgpr_train_debug_read", self._lib)
+        if n != out.nbytes:
+            raise RuntimeError(f"debug_read({what}): expected {out.nbytes} bytes, library holds {n}")
+        return out

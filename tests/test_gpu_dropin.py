@@ -104,15 +104,37 @@ def test_training_step_runs_on_device(tree):
     args = sgpr_args().load(cfg)
     args.K, args.node_num, args.batch_size = 10, 48, 4
     trainer = SGTrainer(args, True)
-    trainer.optimizer = torch.optim.Adam(trainer.model.parameters(), lr=1e-3, weight_decay=5e-4)
+    from sg_pr_b200.sg_net import _DeviceAdam
+    from sg_pr_b200.utils import process_pair
+    from oracle import sgpr_oracle_train as ort
+    import random
+    trainer.optimizer = _DeviceAdam(trainer)
     trainer.model.train()
+    state0 = {k: v.detach().cpu().clone() for k, v in trainer.model.module.state_dict().items()}
+    random.seed(3); np.random.seed(3)
     loss0, pred, gt = trainer.process_batch(trainer.training_graphs, True)
     assert pred.shape == (8,) and np.isfinite(loss0)
+    assert trainer._train_engine.launch_count() > 0                        # the step ran in the CUDA library
+    # the same step by the oracle (autograd + Adam on the CPU), host-side augmentation replayed with the same seeds
+    random.seed(3); np.random.seed(3)
+    f1, f2, tg = [], [], []
+    for pair in trainer.training_graphs:
+        d = trainer.transfer_to_torch(process_pair(pair), True)
+        f1 += [d["features_1"], d["features_2"]]
+        f2 += [d["features_2"], d["features_1"]]
+        tg += [d["target"], d["target"]]
+    batch = trainer._stack(f1, f2, tg)
+    want = ort.train_step(state0, batch["features_1"], batch["features_2"], batch["target"], 10, ort.new_adam_state(state0),
+                          float(args.learning_rate), float(args.weight_decay))
+    assert abs(loss0 - want["loss"]) < 5e-5 and np.abs(pred - want["pred"].numpy()).max() < 5e-5
     for _ in range(5):
         loss, _, _ = trainer.process_batch(trainer.training_graphs, True)
     assert loss < loss0
     model_loss, f1 = trainer.score("eval")                # eval mode -> fused kernel with the just-trained weights
     assert np.isfinite(model_loss) and 0.0 <= f1 <= 1.0
+    synced = trainer.model.module.state_dict()
+    assert int(synced["dgcnn_s_conv1.1.num_batches_tracked"]) == int(state0["dgcnn_s_conv1.1.num_batches_tracked"]) + 12
+    assert not torch.equal(synced["dgcnn_s_conv2.0.weight"].cpu(), state0["dgcnn_s_conv2.0.weight"])
 
 
 @pytest.mark.skipif(not os.path.isfile("/root/reference/eval_pair.py"), reason="reference tree not on this box")

@@ -1,0 +1,88 @@
+"""Training step on the B200 through the C-ABI (include/sgpr_b200_train.h) against the reference's golden training
+vectors: the same assertions as the emulated CPU twin, plus shapes the goldens do not cover checked against the
+oracle's own train step run live."""
+import numpy as np
+import pytest
+import torch
+
+from tests import train_checks as tc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from sg_pr_b200.train_engine import TrainEngine
+    e = TrainEngine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("tag,tol", [("n32_k10", 1e-5), ("n64_k20", 5e-5)])
+def test_gradients_match_reference(eng, tag, tol):
+    g, sd = tc.load_case(tag)
+    tc.check_gradients(eng, g, sd, "cuda", pred_tol=tol)
+
+
+@pytest.mark.parametrize("tag,tol", [("n32_k10", 1e-5), ("n64_k20", 5e-5)])
+def test_two_optimiser_steps_match_reference(eng, tag, tol):
+    g, sd = tc.load_case(tag)
+    tc.check_two_steps(eng, g, sd, "cuda", pred_tol=tol)
+
+
+@pytest.mark.parametrize("N,k,listed", [(100, 10, 6), (30, 7, 5), (128, 20, 3)])
+def test_step_matches_live_oracle(eng, kitti_state, N, k, listed):
+    """Shapes without golden vectors (the shipped config N=100/k=10, ragged N, the largest N): one full step vs the
+    oracle's autograd + Adam on the CPU."""
+    from oracle import sgpr_oracle_train as ort
+    from oracle.make_golden_train import train_batch
+    f1, f2, target = train_batch(listed, N, k, seed=5)
+    sd = {n: v.clone() for n, v in kitti_state.items()}
+    adam = ort.new_adam_state(sd)
+    want = ort.train_step(sd, f1, f2, target, k, adam, 1e-3, 5e-4)
+    eng.set_state(kitti_state, reset_optimizer=True)
+    eng.set_optimizer(1e-3, 5e-4)
+    loss, pred = eng.step(f1.cuda(), f2.cuda(), target.cuda(), k, apply=True)
+    np.testing.assert_allclose(pred.cpu().numpy(), want["pred"].numpy(), rtol=0, atol=5e-5)
+    assert abs(float(loss) - want["loss"]) < 5e-5
+    grads = eng.grads()
+    for name, ref in want["grads"].items():
+        scale = max(float(ref.abs().max()), 1e-8)
+        err = float((grads[name].reshape(ref.shape) - ref).abs().max())
+        assert err <= 2e-3 * scale, (name, err, scale)
+    state = eng.get_state()
+    for name, value in state.items():
+        if "running_" in name:
+            ref = sd[name]
+            assert float((value.reshape(ref.shape) - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), name
+
+
+def test_step_is_deterministic_in_everything_but_fp64_atomics(eng, kitti_state):
+    """Gradients come from fixed-order partial sums; only the fp64 statistics use atomics (order noise ~1e-16)."""
+    from oracle.make_golden_train import train_batch
+    f1, f2, target = train_batch(16, 64, 20, seed=9)
+    outs = []
+    for _ in range(2):
+        eng.set_state(kitti_state, reset_optimizer=True)
+        loss, pred = eng.step(f1.cuda(), f2.cuda(), target.cuda(), 20, apply=False)
+        outs.append((pred.cpu().clone(), {n: v.clone() for n, v in eng.grads().items()}))
+    assert float((outs[0][0] - outs[1][0]).abs().max()) <= 1e-6
+    for n in outs[0][1]:
+        a, b = outs[0][1][n], outs[1][1][n]
+        assert float((a - b).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-8), n
+
+
+def test_loud_errors(eng, kitti_state):
+    from sg_pr_b200 import _lib
+    from sg_pr_b200.train_engine import TrainEngine
+    fresh = TrainEngine(0)
+    f = torch.zeros(2, 15, 32, device="cuda")
+    t = torch.zeros(2, device="cuda")
+    with pytest.raises(_lib.SgprError, match="set_state"):
+        fresh.step(f, f, t, 10)
+    fresh.set_state(kitti_state)
+    with pytest.raises(_lib.SgprError, match="topk"):
+        fresh.step(f, f, t, 40)
+    with pytest.raises(RuntimeError):
+        fresh.step(f.cpu(), f.cpu(), t.cpu(), 10)
+    fresh.close()

@@ -18,12 +18,14 @@ def tree(golden_dir, tmp_path_factory):
 
 
 def test_abi_exports_every_declared_symbol():
-    """The library loads without a GPU and exports every function include/sgpr_b200.h declares."""
+    """The library loads without a GPU and exports every function include/*.h declares."""
     from sg_pr_b200 import _lib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    header = open(os.path.join(root, "include", "sgpr_b200.h")).read()
+    header = open(os.path.join(root, "include", "sgpr_b200.h")).read() + \
+        open(os.path.join(root, "include", "sgpr_b200_train.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)          # prose in comments is not a declaration
     declared = set(re.findall(r"\b(sgpr_[a-z0-9_]+)\s*\(", header))
-    declared -= {"sgpr_ctx"}
+    declared -= {"sgpr_ctx", "sgpr_train"}
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     lib = _lib.load()
     for name in declared:
@@ -43,6 +45,10 @@ def test_no_cpu_fallback():
     from sg_pr_b200.engine import Engine
     with pytest.raises(RuntimeError):
         Engine(0)
+    assert lib.sgpr_train_create(ctypes.byref(handle), 0) != 0           # the training step has no CPU path either
+    from sg_pr_b200.train_engine import TrainEngine
+    with pytest.raises(RuntimeError):
+        TrainEngine(0)
 
 
 def test_parser_reads_reference_layout(tree):
