@@ -58,12 +58,21 @@ int sgpr_train_set_optimizer(sgpr_train* t, float lr, float weight_decay, float 
  *   target_dev     : [B]          data["target"] (0 / 1)
  *   loss_dev       : [1]          mean BCE of this batch (before the update), may be NULL
  *   pred_dev       : [B]          train-mode predictions (before the update), may be NULL
- *   apply          : 1 = full step (Adam update + running statistics); 0 = forward + backward only (gradients stay
- *                    readable through sgpr_train_get_grads, nothing is updated)
- * B >= 1, 2 <= N <= SGPR_MAX_NODES, 1 <= k <= N, B*N*k > 1.
+ *   flags          : SGPR_TRAIN_APPLY     full step (Adam update + running statistics); without it forward + backward
+ *                                         only — gradients stay readable through sgpr_train_get_grads, nothing is updated
+ *                    SGPR_TRAIN_MIRRORED  the caller guarantees features_2[p] == features_1[p ^ 1] for every p (exactly
+ *                                         what process_batch builds: each listed pair (a, b) appears as (a, b) and
+ *                                         (b, a), sg_net.py:324-331).  Both sides then hold the same graphs, so the
+ *                                         second dgcnn_conv_pass (sg_net.py:124) has the same batch statistics and
+ *                                         activations as the first: the kernels embed every graph ONCE and back-
+ *                                         propagate the sum of its two roles' gradients.  f2_dev is not read (may be
+ *                                         NULL); B must be even.  Same result as the unmirrored call up to rounding.
+ * B >= 1, 2 <= N <= SGPR_MAX_NODES, 1 <= k <= N.
  */
+#define SGPR_TRAIN_APPLY    1
+#define SGPR_TRAIN_MIRRORED 2
 int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, const float* target_dev, int B, int N, int k,
-                    float* loss_dev, float* pred_dev, int apply, void* stream);
+                    float* loss_dev, float* pred_dev, int flags, void* stream);
 
 /* Gradients of the last step w.r.t. the trainable parameters (before weight decay), flat layout, host pointer. */
 int sgpr_train_get_grads(sgpr_train* t, float* grads_host);

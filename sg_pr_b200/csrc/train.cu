@@ -112,7 +112,7 @@ struct sgpr_train {
 
 namespace {
 
-constexpr int kMaxHeadGrid = 64;
+constexpr int kMaxHeadGrid = 148;
 constexpr size_t kSumDoubles = 2 * 2 * 7 * 128;
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
@@ -232,17 +232,19 @@ int sgpr_train_set_optimizer(sgpr_train* t, float lr, float weight_decay, float 
 }
 
 int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, const float* target_dev, int B, int N, int k,
-                    float* loss_dev, float* pred_dev, int apply, void* stream) {
+                    float* loss_dev, float* pred_dev, int flags, void* stream) {
     if (!t) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: NULL context");
     if (!t->has_state) return sgpr_fail(SGPR_E_NOWEIGHTS, "sgpr_train_step: call sgpr_train_set_state first");
     if (B < 1) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: batch %d < 1", B);
     if (N < 2 || N > SGPR_MAX_NODES) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: node_num %d outside [2,%d]", N, SGPR_MAX_NODES);
     if (k < 1 || k > N)
         return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: k=%d must satisfy 1 <= k <= node_num=%d (topk raises in the reference, dgcnn.py:19)", k, N);
-    if (!f1_dev || !f2_dev || !target_dev) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: NULL feature/target pointer");
+    const int apply = (flags & SGPR_TRAIN_APPLY) ? 1 : 0, mirrored = (flags & SGPR_TRAIN_MIRRORED) ? 1 : 0;
+    if (!f1_dev || (!f2_dev && !mirrored) || !target_dev) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: NULL feature/target pointer");
+    if (mirrored && (B & 1)) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: a mirrored batch holds every pair in both orders, B=%d is odd", B);
     Guard guard(t->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int G = B, SG = 2 * B;
+    const int G = B, S = mirrored ? 1 : 2, SG = S * B;
     const int npl = (N <= 32) ? 1 : (N <= 64) ? 2 : 4;
     const int nmax = 32 * npl;
     const int KS = (k + 3) & ~3;
@@ -253,7 +255,8 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
         const size_t per = static_cast<size_t>(SG) * N * layer_cout(L);
         need += 5 * align256(per * 4) + align256(per) + align256(static_cast<size_t>(SG) * N * k);
     }
-    need += 2 * align256(static_cast<size_t>(SG) * N * 32 * 4) + 4 * align256(static_cast<size_t>(SG) * 32 * 4) +
+    need += 2 * align256(static_cast<size_t>(SG) * N * 32 * 4) + 3 * align256(static_cast<size_t>(SG) * 32 * 4) +
+            align256(static_cast<size_t>(2) * G * 32 * 4) +
             align256(static_cast<size_t>(SG) * N * 4) + align256(static_cast<size_t>(G) * 4);
     if (need > t->ws_cap) {
         if (t->d_ws) cudaFree(t->d_ws);
@@ -264,10 +267,10 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
     }
     const int per_sm = (npl <= 2) ? 2 : 1;
     const int cap = t->sm_count * per_sm;
-    int grid4 = 4 * G < cap ? 4 * G : (cap / 4) * 4;        // (branch, side) x graphs
-    if (grid4 < 4) grid4 = 4;
-    int grid2 = 2 * G < cap ? 2 * G : (cap / 2) * 2;        // side x graphs
-    if (grid2 < 2) grid2 = 2;
+    int grid4 = 2 * S * G < cap ? 2 * S * G : (cap / (2 * S)) * (2 * S);        // (branch, side) x graphs
+    if (grid4 < 2 * S) grid4 = 2 * S;
+    int grid2 = S * G < cap ? S * G : (cap / S) * S;                            // side x graphs
+    if (grid2 < S) grid2 = S;
     int grid_att = SG < 4 * t->sm_count ? SG : 4 * t->sm_count;
     const int head_grid = G < kMaxHeadGrid ? G : kMaxHeadGrid;
     const int nb = grid4 / 2;                                // partial rows per branch in the EdgeConv backward
@@ -282,7 +285,7 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
     }
 
     TrainWs W{};
-    W.G = G; W.N = N; W.k = k; W.KS = KS; W.eps = 1e-5f;
+    W.G = G; W.S = S; W.mirrored = mirrored; W.N = N; W.k = k; W.KS = KS; W.eps = 1e-5f;
     W.f[0] = f1_dev; W.f[1] = f2_dev; W.target = target_dev;
     W.state = t->d_state; W.wpk = t->d_wpk;
     unsigned char* p = t->d_ws;
@@ -301,7 +304,7 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
     W.pooled = carve<float>(p, static_cast<size_t>(SG) * 32);
     W.actx = carve<float>(p, static_cast<size_t>(SG) * 32);
     W.esum = carve<float>(p, static_cast<size_t>(SG) * 32);
-    W.dpooled = carve<float>(p, static_cast<size_t>(SG) * 32);
+    W.dpooled = carve<float>(p, static_cast<size_t>(2) * G * 32);        // d/d e1 of pair p | d/d e2 of pair p
     W.att = carve<float>(p, static_cast<size_t>(SG) * N);
     W.pred = carve<float>(p, static_cast<size_t>(G));
     W.stats = t->d_sums;
@@ -358,7 +361,7 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
     const long long step = t->steps + 1;
     A.bc1 = static_cast<float>(1.0 - std::pow(static_cast<double>(t->b1), static_cast<double>(step)));
     A.bc2_sqrt = static_cast<float>(std::sqrt(1.0 - std::pow(static_cast<double>(t->b2), static_cast<double>(step))));
-    A.apply = apply ? 1 : 0;
+    A.apply = apply;
     SGPR_LAUNCH(sgpr_train_adam_kernel, (STATE_TOTAL + kThreads - 1) / kThreads, kThreads, 0, st, W, A);
     t->launches += 1;
     if (apply) t->steps = step;
@@ -386,7 +389,7 @@ int64_t sgpr_train_debug_read(sgpr_train* t, const char* what, int layer, void* 
     if (!t || !what || !host) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_debug_read: NULL argument");
     if (!t->has_last) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_debug_read: no step has run yet");
     const TrainWs& W = t->last;
-    const size_t SG = 2 * static_cast<size_t>(W.G);
+    const size_t SG = static_cast<size_t>(W.S) * W.G;
     const void* src = nullptr;
     size_t bytes = 0;
     const bool per_layer = !strcmp(what, "yext") || !strcmp(what, "a") || !strcmp(what, "d") || !strcmp(what, "sumy") ||
@@ -405,7 +408,7 @@ int64_t sgpr_train_debug_read(sgpr_train* t, const char* what, int layer, void* 
     else if (!strcmp(what, "gzend")) { src = W.gzend; bytes = SG * W.N * 32 * 4; }
     else if (!strcmp(what, "pooled")) { src = W.pooled; bytes = SG * 32 * 4; }
     else if (!strcmp(what, "ctx")) { src = W.actx; bytes = SG * 32 * 4; }
-    else if (!strcmp(what, "dpooled")) { src = W.dpooled; bytes = SG * 32 * 4; }
+    else if (!strcmp(what, "dpooled")) { src = W.dpooled; bytes = 2 * static_cast<size_t>(W.G) * 32 * 4; }
     else if (!strcmp(what, "att")) { src = W.att; bytes = SG * W.N * 4; }
     else if (!strcmp(what, "stats")) { src = W.stats; bytes = kSumDoubles / 2 * 8; }
     else if (!strcmp(what, "bsum")) { src = W.bsum; bytes = kSumDoubles / 2 * 8; }

@@ -99,6 +99,10 @@ constexpr int kMaxSeg = 12;
 
 struct TrainWs {
     int G;                  // pairs per step = graphs per side
+    int S;                  // BatchNorm batches processed: 2 (one per side), or 1 in mirrored mode
+    int mirrored;           // features_2[p] == features_1[p ^ 1] (process_batch's doubling, sg_net.py:324-331): side 2 holds
+                            // the same graphs as side 1, hence the same batch statistics, activations and — summed over
+                            // both roles of a graph — gradients; only side 1 is computed
     int N, k, KS;
     float eps;
     const float* f[2];      // features_1 / features_2   [G][15][N]
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     double* sStat = reinterpret_cast<double*>(smem + S.stat);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int br = blockIdx.x & 1, side = (blockIdx.x >> 1) & 1;
+    const int br = blockIdx.x & 1, side = (blockIdx.x >> 1) % T.S;
     const int L = br * 3 + l;
     const int cin4 = (l == 0) ? (br ? 3 : 1) : 16, cout = layer_cout(L);
     const int N = T.N, k = T.k, KS = T.KS;
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     const float* gamma = T.state + P_BN + bn_off(L);
     double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};
 
-    for (int g = blockIdx.x >> 2; g < T.G; g += gridDim.x >> 2) {
+    for (int g = (blockIdx.x >> 1) / T.S; g < T.G; g += (gridDim.x >> 1) / T.S) {
         const size_t sg = static_cast<size_t>(side) * T.G + g;
         fill_layer_input(T, l, br, side, g, sX, sPrm, tid);
         __syncthreads();
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_f
     float* sPrm = sO + NMAX * XS;                               // [4][64]
     double* sStat = reinterpret_cast<double*>(sPrm + 256);      // [kWarps][128]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int side = blockIdx.x & 1;
+    const int side = blockIdx.x % T.S;
     const int N = T.N;
     for (int e = tid; e < 64 * 32; e += kThreads) sW[e] = T.wpk[WPK_END + e];
     for (int e = tid; e < NMAX * XS; e += kThreads) sX[e] = 0.0f;
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_f
     const int rpw = (N + kWarps - 1) / kWarps;
     const int w0 = min(N, warp * rpw), w1 = min(N, w0 + rpw);
     double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};
-    for (int g = blockIdx.x >> 1; g < T.G; g += gridDim.x >> 1) {
+    for (int g = blockIdx.x / T.S; g < T.G; g += gridDim.x / T.S) {
         const size_t sg = static_cast<size_t>(side) * T.G + g;
         const float* y2 = T.yext[2] + sg * N * 32;
         const float* y5 = T.yext[5] + sg * N * 32;
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_att_fwd(const TrainWs T) 
     const int tid = threadIdx.x;
     const int N = T.N;
     const float* watt = T.state + P_ATT;
-    for (int item = blockIdx.x; item < 2 * T.G; item += gridDim.x) {
+    for (int item = blockIdx.x; item < T.S * T.G; item += gridDim.x) {
         const int side = item / T.G;
         if (tid < 32) {
             float mu, istd;
@@ -573,7 +577,10 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs
     const float* e2 = e12 + 32;
 
     for (int p = blockIdx.x; p < G; p += gridDim.x) {
-        if (tid < 64) e12[tid] = T.pooled[(static_cast<size_t>(tid >> 5) * G + p) * 32 + (tid & 31)];
+        if (tid < 64) {          // e2 of pair p: the graph of side 2 — in mirrored mode that is graph p ^ 1 of side 1
+            const size_t row = (tid < 32) ? static_cast<size_t>(p) : (T.mirrored ? static_cast<size_t>(p ^ 1) : static_cast<size_t>(G) + p);
+            e12[tid] = T.pooled[row * 32 + (tid & 31)];
+        }
         __syncthreads();
         for (int m = 0; m < 2; ++m) {                       // P[b*16+t] = sum_a e1[a] W[a][b][t]
             const int bt = tid + 256 * m;
@@ -693,7 +700,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_att_bwd(const TrainWs T, 
     __shared__ float sDp[32], sCtx[32], sSum[32], sDcbar[32], sV[32], sAtt[SGPR_MAX_NODES], sDsig[SGPR_MAX_NODES];
     __shared__ double sRed[8 * 64];
     const int tid = threadIdx.x;
-    const int side = blockIdx.x & 1;
+    const int side = blockIdx.x % T.S;
     const int N = T.N;
     const float* watt = T.state + P_ATT;
     float gA[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -707,7 +714,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_att_bwd(const TrainWs T, 
         sPrm[96 + tid] = T.state[P_BN + bn_off(6) + 32 + tid];
     }
     __syncthreads();
-    for (int g = blockIdx.x >> 1; g < T.G; g += gridDim.x >> 1) {
+    for (int g = blockIdx.x / T.S; g < T.G; g += gridDim.x / T.S) {
         const size_t sg = static_cast<size_t>(side) * T.G + g;
         const float* y = T.yend + sg * N * 32;
         for (int e = tid; e < N * 32; e += kThreads) {
@@ -717,7 +724,10 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_att_bwd(const TrainWs T, 
             sE[n * 33 + c] = lrelu(fmaf(yh, sPrm[64 + c], sPrm[96 + c]));
         }
         if (tid < 32) {
-            sDp[tid] = T.dpooled[sg * 32 + tid];
+            // mirrored: graph g is e1 of pair g and e2 of pair g ^ 1 — its gradient is the sum over both roles
+            sDp[tid] = T.mirrored ? __fadd_rn(T.dpooled[static_cast<size_t>(g) * 32 + tid],
+                                              T.dpooled[(static_cast<size_t>(T.G) + (g ^ 1)) * 32 + tid])
+                                  : T.dpooled[sg * 32 + tid];
             sCtx[tid] = T.actx[sg * 32 + tid];
             sSum[tid] = T.esum[sg * 32 + tid];
         }
@@ -785,7 +795,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_b
     float* sEnd = sPrm + 256;                                   // [4][32]: mu, istd, s, (unused) | dbeta/e, dgamma/e
     double* sRed = reinterpret_cast<double*>(sEnd + 192);       // [4][128]
     const int tid = threadIdx.x;
-    const int side = blockIdx.x & 1;
+    const int side = blockIdx.x % T.S;
     const int N = T.N;
     const double e_end = static_cast<double>(T.G) * N;
     for (int e = tid; e < 32 * 64; e += kThreads) sWn[e] = T.state[P_ENDW + e];
@@ -815,7 +825,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_b
     for (int m = 0; m < 8; ++m) gW[m] = 0.0f;
     double accb = 0.0, accg = 0.0;                     // channel tid & 63 of cat
     const int f0 = 2 * (tid >> 4), c0 = 4 * (tid & 15);
-    for (int g = blockIdx.x >> 1; g < T.G; g += gridDim.x >> 1) {
+    for (int g = blockIdx.x / T.S; g < T.G; g += gridDim.x / T.S) {
         const size_t sg = static_cast<size_t>(side) * T.G + g;
         const float* y2 = T.yext[2] + sg * N * 32;
         const float* y5 = T.yext[5] + sg * N * 32;
@@ -878,7 +888,7 @@ struct BwdSmem { int w, x, gz, d, da, en, adj, radj, c, prm, red, total; };
 __host__ __device__ inline BwdSmem bwd_layout(int nmax) {
     BwdSmem L;
     int o = 0;
-    L.w = o;    o += 64 * 128 * 4;
+    L.w = o;    // the conv matrix is read through the L1 (`__ldg`): keeping it out of shared memory lets two CTAs share an SM
     L.x = o;    o += nmax * XS * 4;
     L.gz = o;   o += nmax * XS * 4;
     L.d = o;    o += nmax * XS * 4;
@@ -919,7 +929,6 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     constexpr int SLOTS = 4 * NPL;                    // nodes per warp
     SGPR_DYN_SMEM(smem);
     const BwdSmem S = bwd_layout(NMAX);
-    float* sWn = reinterpret_cast<float*>(smem + S.w);          // natural [cout][2 cin]
     float* sX = reinterpret_cast<float*>(smem + S.x);
     float* sGZ = reinterpret_cast<float*>(smem + S.gz);         // gz, later dB
     float* sD = reinterpret_cast<float*>(smem + S.d);
@@ -932,13 +941,13 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     double* sRed = reinterpret_cast<double*>(smem + S.red);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int br = blockIdx.x & 1, side = (blockIdx.x >> 1) & 1;
+    const int br = blockIdx.x & 1, side = (blockIdx.x >> 1) % T.S;
     const int L = br * 3 + l;
     const int cin = layer_cin(L), cout = layer_cout(L), cpl = cout / 32;
     const int N = T.N, k = T.k;
     const double e_edge = static_cast<double>(T.G) * N * k;
 
-    for (int e = tid; e < cout * 2 * cin; e += kThreads) sWn[e] = T.state[conv_off(L) + e];
+    const float* Wn = T.state + conv_off(L);                    // natural [cout][2 cin]
     for (int e = tid; e < NMAX * XS; e += kThreads) sX[e] = 0.0f;
     if (tid < cout) {
         float mu, istd;
@@ -961,7 +970,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     const int w0 = min(N, warp * rpw), w1 = min(N, w0 + rpw);
     const float kf = static_cast<float>(k);
 
-    for (int g = blockIdx.x >> 2; g < T.G; g += gridDim.x >> 2) {
+    for (int g = (blockIdx.x >> 1) / T.S; g < T.G; g += (gridDim.x >> 1) / T.S) {
         const size_t sg = static_cast<size_t>(side) * T.G + g;
         const size_t o = sg * N * cout;
         fill_layer_input(T, l, br, side, g, sX, sPrm, tid);
@@ -1047,8 +1056,8 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
 #pragma unroll
                 for (int u = 0; u < 4; ++u) rows[u] = min(r0 + u, w1 - 1);
                 for (int c = 0; c < cout; ++c) {
-                    const float2 wa = *reinterpret_cast<const float2*>(sWn + c * 128 + 2 * lane);
-                    const float2 wb = *reinterpret_cast<const float2*>(sWn + c * 128 + 64 + 2 * lane);
+                    const float2 wa = __ldg(reinterpret_cast<const float2*>(Wn + c * 128 + 2 * lane));
+                    const float2 wb = __ldg(reinterpret_cast<const float2*>(Wn + c * 128 + 64 + 2 * lane));
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float da = sDA[rows[u] * XS + c], db = sGZ[rows[u] * XS + c];
@@ -1148,13 +1157,16 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
             while (bn_off(L) > e - P_BN) --L;
             const int C = layer_cout(L), r = e - P_BN - bn_off(L);
             const int which = r < C ? 1 : 0, c = r < C ? r : r - C;        // gamma <- dgamma (slot 1), beta <- dbeta (slot 0)
-            g = static_cast<float>(stat_ptr(T.bsum, 0, L)[which * 64 + c] + stat_ptr(T.bsum, 1, L)[which * 64 + c]);
+            double sum = 0.0;
+            for (int side = 0; side < T.S; ++side) sum += stat_ptr(T.bsum, side, L)[which * 64 + c];
+            g = static_cast<float>(sum);
         } else {
             for (int s = 0; s < T.nseg; ++s) {
                 const Segment& sg = T.seg[s];
                 if (e >= sg.off && e < sg.off + sg.size) {
                     const float* p = sg.part + (e - sg.off);
-                    for (int j = 0; j < sg.count; ++j) g += p[static_cast<size_t>(j) * sg.stride];
+#pragma unroll 8
+                    for (int j = 0; j < sg.count; ++j) g += __ldg(p + static_cast<size_t>(j) * sg.stride);
                     break;
                 }
             }
@@ -1178,8 +1190,8 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
         const int is_var = r >= C, c = is_var ? r - C : r;
         const double cnt = (L == 6) ? static_cast<double>(T.G) * T.N : static_cast<double>(T.G) * T.N * T.k;
         float run = T.state[e];
-        for (int side = 0; side < 2; ++side) {
-            const double* st = stat_ptr(T.stats, side, L);
+        for (int side = 0; side < 2; ++side) {          // two BatchNorm calls per step, side 1 first (sg_net.py:123-124)
+            const double* st = stat_ptr(T.stats, side < T.S ? side : T.S - 1, L);
             const double m = st[c] / cnt;
             double var = st[64 + c] / cnt - m * m;
             var = var > 0.0 ? var : 0.0;

@@ -347,9 +347,11 @@ class SGTrainer(object):
         if training:
             eng = self._device_trainer()
             dev = eng.device
-            loss, prediction = eng.step(data["features_1"].to(dev, non_blocking=True),
-                                        data["features_2"].to(dev, non_blocking=True),
-                                        data["target"].to(dev, non_blocking=True), int(self.args.K), apply=True)
+            # the batch holds every listed pair in both orders (features_2[p] == features_1[p ^ 1] by construction just
+            # above), so both sides are the same BatchNorm batch: one EdgeConv pass per graph serves both (mirrored step)
+            loss, prediction = eng.step(data["features_1"].to(dev, non_blocking=True), None,
+                                        data["target"].to(dev, non_blocking=True), int(self.args.K), apply=True,
+                                        mirrored=True)
             self._unsynced_steps += 1
             return (loss.item(), prediction.cpu().numpy().reshape(-1), data["target"].numpy().reshape(-1))
         self.sync_model_from_device()

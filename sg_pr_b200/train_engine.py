@@ -108,9 +108,12 @@ class TrainEngine:
             raise RuntimeError(f"{what} must live on {self.device} (got {t.device})")
         return t.contiguous()
 
-    def step(self, f1: torch.Tensor, f2: torch.Tensor, target: torch.Tensor, k: int, apply: bool = True):
-        """f1, f2 [B,15,N], target [B] on the device -> (loss [1], prediction [B]) device tensors (pre-update)."""
-        f1, f2, target = self._buf(f1, "features_1"), self._buf(f2, "features_2"), self._buf(target, "target")
+    def step(self, f1: torch.Tensor, f2: Optional[torch.Tensor], target: torch.Tensor, k: int, apply: bool = True,
+             mirrored: bool = False):
+        """f1, f2 [B,15,N], target [B] on the device -> (loss [1], prediction [B]) device tensors (pre-update).
+        mirrored=True: the caller guarantees f2[p] == f1[p ^ 1] (process_batch's doubling); f2 is then not read."""
+        f1, target = self._buf(f1, "features_1"), self._buf(target, "target")
+        f2 = f1 if (mirrored and f2 is None) else self._buf(f2, "features_2")
         if f1.dim() != 3 or f1.shape[1] != 15 or f2.shape != f1.shape or target.shape != (f1.shape[0],):
             raise ValueError(f"expected features [B,15,N] x2 and target [B], got {tuple(f1.shape)}, {tuple(f2.shape)}, "
                              f"{tuple(target.shape)}")
@@ -119,7 +122,8 @@ class TrainEngine:
         pred = torch.empty(B, dtype=torch.float32, device=self.device)
         stream = None if self._emulated else C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(self._lib.sgpr_train_step(self._h, f1.data_ptr(), f2.data_ptr(), target.data_ptr(), B, N, int(k),
-                                             loss.data_ptr(), pred.data_ptr(), int(apply), stream),
+                                             loss.data_ptr(), pred.data_ptr(), int(bool(apply)) | (2 if mirrored else 0),
+                                             stream),
                    "sgpr_train_step", self._lib)
         return loss, pred
 

@@ -18,16 +18,34 @@ def eng():
     e.close()
 
 
+@pytest.mark.parametrize("mirrored", [False, True])
 @pytest.mark.parametrize("tag,tol", [("n32_k10", 1e-5), ("n64_k20", 5e-5)])
-def test_gradients_match_reference(eng, tag, tol):
+def test_gradients_match_reference(eng, tag, tol, mirrored):
     g, sd = tc.load_case(tag)
-    tc.check_gradients(eng, g, sd, "cuda", pred_tol=tol)
+    tc.check_gradients(eng, g, sd, "cuda", pred_tol=tol, mirrored=mirrored)
 
 
+@pytest.mark.parametrize("mirrored", [False, True])
 @pytest.mark.parametrize("tag,tol", [("n32_k10", 1e-5), ("n64_k20", 5e-5)])
-def test_two_optimiser_steps_match_reference(eng, tag, tol):
+def test_two_optimiser_steps_match_reference(eng, tag, tol, mirrored):
     g, sd = tc.load_case(tag)
-    tc.check_two_steps(eng, g, sd, "cuda", pred_tol=tol)
+    tc.check_two_steps(eng, g, sd, "cuda", pred_tol=tol, mirrored=mirrored)
+
+
+def test_mirrored_equals_two_sided(eng, kitti_state):
+    """Embedding every graph once (mirrored) gives the two-sided step's predictions and gradients up to rounding."""
+    from oracle.make_golden_train import train_batch
+    f1, f2, target = train_batch(24, 64, 20, seed=11)
+    out = []
+    for mirrored in (False, True):
+        eng.set_state(kitti_state, reset_optimizer=True)
+        _, pred = eng.step(f1.cuda(), None if mirrored else f2.cuda(), target.cuda(), 20, apply=False, mirrored=mirrored)
+        out.append((pred.cpu().clone(), eng.grads()))
+    assert float((out[0][0] - out[1][0]).abs().max()) <= 2e-6
+    for n, a in out[0][1].items():
+        assert float((a - out[1][1][n]).abs().max()) <= 2e-5 * max(float(a.abs().max()), 1e-8), n
+    with pytest.raises(RuntimeError, match="odd"):
+        eng.step(f1[:3].cuda(), None, target[:3].cuda(), 20, mirrored=True)
 
 
 @pytest.mark.parametrize("N,k,listed", [(100, 10, 6), (30, 7, 5), (128, 20, 3)])

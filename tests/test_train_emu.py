@@ -33,17 +33,18 @@ def test_layout_covers_the_state_dict(emu_lib, kitti_state):
     assert all("running_" not in n for n in names[:n_params]) and all("running_" in n for n in names[n_params:])
 
 
-def test_emulated_gradients_match_reference(emu_lib):
+@pytest.mark.parametrize("mirrored", [False, True])
+def test_emulated_gradients_match_reference(emu_lib, mirrored):
     g, sd = tc.load_case("n32_k10")
     eng = TrainEngine(lib=emu_lib)
-    tc.check_gradients(eng, g, sd, "cpu", pred_tol=1e-5)
+    tc.check_gradients(eng, g, sd, "cpu", pred_tol=1e-5, mirrored=mirrored)
     eng.close()
 
 
 def test_emulated_two_optimiser_steps_match_reference(emu_lib):
     g, sd = tc.load_case("n32_k10")
     eng = TrainEngine(lib=emu_lib)
-    tc.check_two_steps(eng, g, sd, "cpu", pred_tol=1e-5)
+    tc.check_two_steps(eng, g, sd, "cpu", pred_tol=1e-5, mirrored=True)
     eng.close()
 
 

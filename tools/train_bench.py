@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--torch-baseline", action="store_true")
+    ap.add_argument("--two-sided", action="store_true", help="run both sides (default: mirrored, what process_batch does)")
     ap.add_argument("--cpu-baseline", action="store_true", help="one oracle step on the host CPU (slow: several seconds)")
     a = ap.parse_args()
 
@@ -37,18 +38,19 @@ def main():
     eng = TrainEngine(0)
     eng.set_state(sd)
     eng.set_optimizer(1e-3, 5e-4)
+    mirrored = not a.two_sided
     for _ in range(a.warmup):
-        eng.step(f1, f2, target, a.k)
+        eng.step(f1, f2, target, a.k, mirrored=mirrored)
     torch.cuda.synchronize()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        loss, pred = eng.step(f1, f2, target, a.k)
+        loss, pred = eng.step(f1, f2, target, a.k, mirrored=mirrored)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    out = {"what": "sgpr_train_step", "listed_pairs": a.listed, "forward_pairs": 2 * a.listed, "nodes": a.nodes, "k": a.k,
+    out = {"what": "sgpr_train_step (mirrored)" if mirrored else "sgpr_train_step (two-sided)", "listed_pairs": a.listed, "forward_pairs": 2 * a.listed, "nodes": a.nodes, "k": a.k,
            "ms_per_step": round(ms, 4), "listed_pairs_per_s": round(a.listed / ms * 1e3, 1),
            "launches_per_step": (eng.launch_count() - l0) // a.steps, "loss_after": float(loss)}
     print(json.dumps(out), flush=True)
