@@ -98,7 +98,7 @@ struct sgpr_train {
     float* d_state = nullptr;      // [STATE_TOTAL]
     float* d_adam = nullptr;       // m | v  [2][P_TOTAL]
     float* d_grads = nullptr;      // [P_TOTAL]
-    float* d_wpk = nullptr;        // [WPK_TOTAL]
+    float* d_wpk = nullptr;        // [WPK_ALL]
     double* d_sums = nullptr;      // stats | bsum  [2][2][7][2][64]
     float* d_misc = nullptr;       // loss[1] | losspart[kMaxHeadGrid]
     unsigned char* d_ws = nullptr; size_t ws_cap = 0;       // per-batch workspace
@@ -172,7 +172,7 @@ int sgpr_train_create(sgpr_train** out, int device) {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_state), STATE_TOTAL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_adam), 2 * P_TOTAL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_grads), P_TOTAL * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_wpk), WPK_TOTAL * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_wpk), WPK_ALL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_sums), kSumDoubles * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_misc), (1 + kMaxHeadGrid) * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(t->d_adam, 0, 2 * P_TOTAL * sizeof(float));
@@ -333,7 +333,7 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
     TRY_CUDA(cudaMemsetAsync(t->d_sums, 0, kSumDoubles * sizeof(double), st));
 
     const FwdSmem FS = fwd_layout(nmax, KS);
-    const BwdSmem BS = bwd_layout(nmax);
+    const BwdSmem BS = bwd_layout(nmax, KS);
     const size_t end_fwd_smem = (64 * 32 + 2 * static_cast<size_t>(nmax) * XS + 256) * 4 + kWarps * 128 * 8;
     const size_t end_bwd_smem = (32 * 64 + static_cast<size_t>(nmax) * XS + static_cast<size_t>(nmax) * 36 + 256 + 192) * 4 + 4 * 128 * 8;
 
@@ -362,7 +362,7 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
     A.bc1 = static_cast<float>(1.0 - std::pow(static_cast<double>(t->b1), static_cast<double>(step)));
     A.bc2_sqrt = static_cast<float>(std::sqrt(1.0 - std::pow(static_cast<double>(t->b2), static_cast<double>(step))));
     A.apply = apply;
-    SGPR_LAUNCH(sgpr_train_adam_kernel, (STATE_TOTAL + kThreads - 1) / kThreads, kThreads, 0, st, W, A);
+    SGPR_LAUNCH(sgpr_train_adam_kernel, (STATE_TOTAL + 31) / 32, kThreads, 0, st, W, A);
     t->launches += 1;
     if (apply) t->steps = step;
     if (loss_dev) TRY_CUDA(cudaMemcpyAsync(loss_dev, W.loss, sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -66,6 +66,12 @@ constexpr int kHeadFloats = P_TOTAL - P_NTNW;   // 17,713: the head's parameters
 constexpr int WPK_S2 = 0, WPK_S3 = WPK_S2 + 64 * 128, WPK_F1 = WPK_S3 + 64 * 64, WPK_F2 = WPK_F1 + 12 * 128,
               WPK_F3 = WPK_F2 + 64 * 128, WPK_END = WPK_F3 + 64 * 64, WPK_TOTAL = WPK_END + 64 * 32;
 
+// backward copies for dX = dA Wa + dB Wb of the layers with 64 input channels: per layer two [cout][64] matrices
+// (input = this layer's output channel, output = its input channel) in the same channel-pair layout
+constexpr int WT_S2 = WPK_TOTAL, WT_S3 = WT_S2 + 2 * 64 * 64, WT_F2 = WT_S3 + 2 * 32 * 64, WT_F3 = WT_F2 + 2 * 64 * 64,
+              WPK_ALL = WT_F3 + 2 * 32 * 64;
+__host__ __device__ inline int wt_off(int L) { return L == 1 ? WT_S2 : (L == 2 ? WT_S3 : (L == 4 ? WT_F2 : WT_F3)); }
+
 constexpr float kMomentum = 0.1f;           // nn.BatchNorm default (sg_net.py:52)
 
 // layer index L: 0-2 xyz EdgeConv 1-3, 3-5 sem EdgeConv 1-3, 6 conv_end
@@ -176,6 +182,8 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_pack_kernel(const TrainWs
                 const int ci = col < cin ? col : col - cin;
                 const int co = col < cin ? c : cout + c;
                 dst[pair_index_dev(ci, co, 2 * cout)] = w[e];
+                if (cin == 64)      // transposed halves: MA[c][ci] = Wa[c][ci], MB[c][ci] = Wb[c][ci]
+                    T.wpk[wt_off(L) + (col < cin ? 0 : cout * 64) + pair_index_dev(c, ci, 64)] = w[e];
             }
         }
     }
@@ -223,15 +231,25 @@ __device__ __forceinline__ void fill_layer_input(const TrainWs& T, int l, int br
             sPrm[192 + tid] = T.state[P_BN + bn_off(L - 1) + 64 + tid];
         }
         __syncthreads();
-        const float* yp = T.yext[L - 1] + (static_cast<size_t>(side) * T.G + g) * N * 64;
-        for (int e = tid; e < N * 64; e += kThreads) {
-            const int n = e >> 6, c = e & 63;
-            sX[n * XS + c] = bn_act(yp[e], sPrm[c], sPrm[64 + c], sPrm[128 + c], sPrm[192 + c]);
+        const float4* yp = reinterpret_cast<const float4*>(T.yext[L - 1] + (static_cast<size_t>(side) * T.G + g) * N * 64);
+        for (int e = tid; e < N * 16; e += kThreads) {
+            const int n = e >> 4, c = (e & 15) * 4;
+            const float4 y = __ldg(yp + e);
+            float4 x;
+            x.x = bn_act(y.x, sPrm[c], sPrm[64 + c], sPrm[128 + c], sPrm[192 + c]);
+            x.y = bn_act(y.y, sPrm[c + 1], sPrm[65 + c], sPrm[129 + c], sPrm[193 + c]);
+            x.z = bn_act(y.z, sPrm[c + 2], sPrm[66 + c], sPrm[130 + c], sPrm[194 + c]);
+            x.w = bn_act(y.w, sPrm[c + 3], sPrm[67 + c], sPrm[131 + c], sPrm[195 + c]);
+            *reinterpret_cast<float4*>(sX + n * XS + c) = x;
         }
     }
 }
 
-// gather over the neighbour lists for own rows: extreme / arg-extreme / sums of y_ij = (A_j - A_i) + B_i
+// gather over the neighbour lists for own rows: extreme / arg-extreme of A_j and the sums of y_ij = (A_j - A_i) + B_i.
+// Per edge and channel only sum A_j and sum A_j^2 are accumulated; with D = B_i - A_i
+//     sum_j y = SA + k D,      sum_j y^2 = SA2 + 2 D SA + k D^2
+// (all terms are O(k) for BatchNorm-scaled features, so the expansion costs ~3 ulp of the sum).  The extreme is a max of
+// sign-folded values (sign bit flipped where gamma < 0: min == max of the negated values, exact).
 template <int COUT>
 __device__ __forceinline__ void train_gather_rows(const float* __restrict__ sY, const uint16_t* __restrict__ sIdx, int KS,
                                                   int k, const float* __restrict__ gamma, float* __restrict__ yext,
@@ -239,42 +257,51 @@ __device__ __forceinline__ void train_gather_rows(const float* __restrict__ sY, 
                                                   uint8_t* __restrict__ enode, int r0, int r1, int lane,
                                                   double (&acc1)[2], double (&acc2)[2]) {
     constexpr int CPL = COUT / 32;
-    bool pos[CPL];
+    uint32_t flip[CPL];
 #pragma unroll
-    for (int p = 0; p < CPL; ++p) pos[p] = gamma[lane * CPL + p] >= 0.0f;
+    for (int p = 0; p < CPL; ++p) flip[p] = gamma[lane * CPL + p] >= 0.0f ? 0u : 0x80000000u;
+    const float kf = static_cast<float>(k);
+    const float* base = sY + lane * CPL;
     for (int i = r0; i < r1; ++i) {
-        float ai[CPL], bi[CPL], best[CPL], s1[CPL], s2[CPL];
+        float best[CPL], sa[CPL], sa2[CPL];
         int bj[CPL];
 #pragma unroll
-        for (int p = 0; p < CPL; ++p) {
-            ai[p] = sY[i * YS + lane * CPL + p];
-            bi[p] = sY[i * YS + COUT + lane * CPL + p];
-            best[p] = pos[p] ? -INFINITY : INFINITY;
-            s1[p] = 0.0f; s2[p] = 0.0f; bj[p] = 0;
-        }
+        for (int p = 0; p < CPL; ++p) { best[p] = -INFINITY; sa[p] = 0.0f; sa2[p] = 0.0f; bj[p] = 0; }
+        const uint16_t* list = sIdx + i * KS;
+#pragma unroll 4
         for (int e = 0; e < k; ++e) {
-            const int j = sIdx[i * KS + e];
+            const int j = list[e];
+            float v[CPL];
+            if constexpr (CPL == 2) {
+                const float2 t = *reinterpret_cast<const float2*>(base + j * YS);
+                v[0] = t.x; v[1] = t.y;
+            } else {
+                v[0] = base[j * YS];
+            }
 #pragma unroll
             for (int p = 0; p < CPL; ++p) {
-                const float v = sY[j * YS + lane * CPL + p];
-                const float y = __fadd_rn(__fsub_rn(v, ai[p]), bi[p]);
-                s1[p] = __fadd_rn(s1[p], y);
-                s2[p] = fmaf(y, y, s2[p]);
-                const bool better = pos[p] ? (v > best[p]) : (v < best[p]);
-                best[p] = better ? v : best[p];
-                bj[p] = better ? j : bj[p];
+                sa[p] = __fadd_rn(sa[p], v[p]);
+                sa2[p] = fmaf(v[p], v[p], sa2[p]);
+                const float vs = __uint_as_float(__float_as_uint(v[p]) ^ flip[p]);
+                bj[p] = vs > best[p] ? j : bj[p];
+                best[p] = fmaxf(best[p], vs);
             }
         }
 #pragma unroll
         for (int p = 0; p < CPL; ++p) {
             const size_t o = static_cast<size_t>(i) * COUT + lane * CPL + p;
-            yext[o] = __fadd_rn(__fsub_rn(best[p], ai[p]), bi[p]);
-            ga[o] = ai[p];
-            gd[o] = __fsub_rn(bi[p], ai[p]);
-            gsum[o] = s1[p];
+            const float ai = base[i * YS + p], bi = base[i * YS + COUT + p];
+            const float dv = __fsub_rn(bi, ai);
+            const float ext = __uint_as_float(__float_as_uint(best[p]) ^ flip[p]);
+            const float s1 = fmaf(kf, dv, sa[p]);
+            const float s2 = fmaf(kf * dv, dv, fmaf(2.0f * dv, sa[p], sa2[p]));
+            yext[o] = __fadd_rn(__fsub_rn(ext, ai), bi);
+            ga[o] = ai;
+            gd[o] = dv;
+            gsum[o] = s1;
             enode[o] = static_cast<uint8_t>(bj[p]);
-            acc1[p] += static_cast<double>(s1[p]);
-            acc2[p] += static_cast<double>(s2[p]);
+            acc1[p] += static_cast<double>(s1);
+            acc2[p] += static_cast<double>(s2);
         }
     }
 }
@@ -884,18 +911,19 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_b
 // EdgeConv layer l backward for both branches and both sides (grid = multiple of 4, CTA -> (branch, side), loops g).
 // part: [grid/2 per branch][cout * 2 cin] conv-weight partials in the state_dict layout.
 // =====================================================================================================================
-struct BwdSmem { int w, x, gz, d, da, en, adj, radj, c, prm, red, total; };
-__host__ __device__ inline BwdSmem bwd_layout(int nmax) {
+struct BwdSmem { int x, gz, d, da, wh, en, adj, off, rl, c, prm, red, total; };
+__host__ __device__ inline BwdSmem bwd_layout(int nmax, int ks) {
     BwdSmem L;
     int o = 0;
-    L.w = o;    // the conv matrix is read through the L1 (`__ldg`): keeping it out of shared memory lets two CTAs share an SM
     L.x = o;    o += nmax * XS * 4;
     L.gz = o;   o += nmax * XS * 4;
     L.d = o;    o += nmax * XS * 4;
     L.da = o;   o += nmax * XS * 4;
+    L.wh = o;   o += 64 * 64 * 4;                        // one transposed half (MA, then MB) for the dX GEMM
     L.en = o;   o += nmax * 64;
-    L.adj = o;  o += nmax * 16;
-    L.radj = o; o += nmax * 16;
+    L.adj = o;  o += nmax * 16;                          // 128-bit neighbour mask per node
+    L.off = o;  o += (nmax + 4) * 4;                     // CSR offsets of the reverse lists
+    L.rl = o;   o += ((nmax * ks + 15) / 16) * 16;       // reverse lists: who lists node n (N*k entries in total)
     L.c = o;    o += 4 * 64 * 4;
     L.prm = o;  o += 4 * 64 * 4;
     L.red = o;  o += kWarps * 128 * 8;
@@ -910,8 +938,16 @@ __device__ __forceinline__ void accum_dw(const float* __restrict__ sX, const flo
     for (int n = 0; n < N; ++n) {
         const float4 x = *reinterpret_cast<const float4*>(sX + n * XS + ci0);
         float da[CPT], db[CPT];
-#pragma unroll
-        for (int u = 0; u < CPT; ++u) { da[u] = sDA[n * XS + c0 + u]; db[u] = sDB[n * XS + c0 + u]; }
+        if constexpr (CPT == 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(sDA + n * XS + c0), b4 = *reinterpret_cast<const float4*>(sDB + n * XS + c0);
+            da[0] = a4.x; da[1] = a4.y; da[2] = a4.z; da[3] = a4.w;
+            db[0] = b4.x; db[1] = b4.y; db[2] = b4.z; db[3] = b4.w;
+        } else if constexpr (CPT == 2) {
+            const float2 a2 = *reinterpret_cast<const float2*>(sDA + n * XS + c0), b2 = *reinterpret_cast<const float2*>(sDB + n * XS + c0);
+            da[0] = a2.x; da[1] = a2.y; db[0] = b2.x; db[1] = b2.y;
+        } else {
+            da[0] = sDA[n * XS + c0]; db[0] = sDB[n * XS + c0];
+        }
 #pragma unroll
         for (int u = 0; u < CPT; ++u) {
             ga[u * 4 + 0] = fmaf(da[u], x.x, ga[u * 4 + 0]); ga[u * 4 + 1] = fmaf(da[u], x.y, ga[u * 4 + 1]);
@@ -922,20 +958,46 @@ __device__ __forceinline__ void accum_dw(const float* __restrict__ sX, const flo
     }
 }
 
+// dX rows += In rows x M for 8 rows starting at r0 (rows beyond r1 repeat the last one; the caller drops them).
+// In: node-major tile, c4n*4 channels; M: [c4n*4][64] in the channel-pair layout; a lane owns outputs 2*lane, 2*lane+1 and
+// keeps the even-/odd-channel partial sums of each in the two halves of a float2 (FFMA2).
+__device__ __forceinline__ void dx_accum(const float* __restrict__ sIn, const float* __restrict__ sM, float2 (&acc)[8][2],
+                                         int c4n, int r0, int r1, int lane) {
+    const float* px[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) px[n] = sIn + min(r0 + n, r1 - 1) * XS;
+#pragma unroll 2
+    for (int c4 = 0; c4 < c4n; ++c4) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sM + (2 * c4) * 128 + lane * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(sM + (2 * c4 + 1) * 128 + lane * 4);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float4 x = *reinterpret_cast<const float4*>(px[n] + 4 * c4);
+            acc[n][0] = ffma2(make_float2(x.x, x.y), make_float2(w0.x, w0.y), acc[n][0]);
+            acc[n][1] = ffma2(make_float2(x.x, x.y), make_float2(w0.z, w0.w), acc[n][1]);
+            acc[n][0] = ffma2(make_float2(x.z, x.w), make_float2(w1.x, w1.y), acc[n][0]);
+            acc[n][1] = ffma2(make_float2(x.z, x.w), make_float2(w1.z, w1.w), acc[n][1]);
+        }
+    }
+}
+
 template <int NPL>
 __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_bwd(const TrainWs T, int l, float* __restrict__ part0,
                                                                                    float* __restrict__ part1) {
     constexpr int NMAX = 32 * NPL;
     constexpr int SLOTS = 4 * NPL;                    // nodes per warp
+    constexpr int PASSES = (NPL == 4) ? 2 : 1;        // 8-row passes of the dX GEMM per warp
     SGPR_DYN_SMEM(smem);
-    const BwdSmem S = bwd_layout(NMAX);
+    const BwdSmem S = bwd_layout(NMAX, T.KS);
     float* sX = reinterpret_cast<float*>(smem + S.x);
     float* sGZ = reinterpret_cast<float*>(smem + S.gz);         // gz, later dB
     float* sD = reinterpret_cast<float*>(smem + S.d);
-    float* sDA = reinterpret_cast<float*>(smem + S.da);
+    float* sDA = reinterpret_cast<float*>(smem + S.da);         // S1, then dA
+    float* sWh = reinterpret_cast<float*>(smem + S.wh);
     uint8_t* sEN = smem + S.en;
-    unsigned long long* sAdj = reinterpret_cast<unsigned long long*>(smem + S.adj);     // [NMAX][2]
-    unsigned long long* sRadj = reinterpret_cast<unsigned long long*>(smem + S.radj);
+    uint32_t* sAdj = reinterpret_cast<uint32_t*>(smem + S.adj); // [NMAX][4]
+    int* sOff = reinterpret_cast<int*>(smem + S.off);
+    uint8_t* sRl = smem + S.rl;
     float* sC = reinterpret_cast<float*>(smem + S.c);           // s | q | r | (spare)
     float* sPrm = reinterpret_cast<float*>(smem + S.prm);       // previous layer: mu | istd | gamma | beta
     double* sRed = reinterpret_cast<double*>(smem + S.red);
@@ -947,7 +1009,6 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     const int N = T.N, k = T.k;
     const double e_edge = static_cast<double>(T.G) * N * k;
 
-    const float* Wn = T.state + conv_off(L);                    // natural [cout][2 cin]
     for (int e = tid; e < NMAX * XS; e += kThreads) sX[e] = 0.0f;
     if (tid < cout) {
         float mu, istd;
@@ -975,110 +1036,138 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
         const size_t o = sg * N * cout;
         fill_layer_input(T, l, br, side, g, sX, sPrm, tid);
         {
-            const float* gz = T.gz[L] + o;
-            const float* gd = T.d[L] + o;
-            const uint8_t* en = T.enode[L] + o;
-            for (int e = tid; e < N * cout; e += kThreads) {
-                const int n = e / cout, c = e - n * cout;
-                sGZ[n * XS + c] = gz[e];
-                sD[n * XS + c] = gd[e];
-                sEN[n * 64 + c] = en[e];
+            const float4* gz = reinterpret_cast<const float4*>(T.gz[L] + o);
+            const float4* gd = reinterpret_cast<const float4*>(T.d[L] + o);
+            const uint32_t* en = reinterpret_cast<const uint32_t*>(T.enode[L] + o);
+            const int q4 = cout >> 2;                        // float4 groups per node
+            for (int e = tid; e < N * q4; e += kThreads) {
+                const int n = e / q4, c = (e - n * q4) * 4;
+                *reinterpret_cast<float4*>(sGZ + n * XS + c) = __ldg(gz + e);
+                *reinterpret_cast<float4*>(sD + n * XS + c) = __ldg(gd + e);
+                *reinterpret_cast<uint32_t*>(sEN + n * 64 + c) = __ldg(en + e);
+                *reinterpret_cast<float4*>(sDA + n * XS + c) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
             if (tid < N) {
                 const uint8_t* gi = T.idx[L] + (sg * N + tid) * k;
-                unsigned long long m0 = 0ull, m1 = 0ull;
+                uint32_t m[4] = {0u, 0u, 0u, 0u};
                 for (int e = 0; e < k; ++e) {
                     const int j = gi[e];
-                    if (j < 64) m0 |= 1ull << j; else m1 |= 1ull << (j - 64);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) m[w] |= (j >> 5) == w ? (1u << (j & 31)) : 0u;
                 }
-                sAdj[2 * tid] = m0;
-                sAdj[2 * tid + 1] = m1;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) sAdj[4 * tid + w] = m[w];
             }
         }
         __syncthreads();
-        if (tid < N) {                                           // reverse adjacency: who lists node tid
-            unsigned long long m0 = 0ull, m1 = 0ull;
+        // ---- reverse neighbour lists (CSR): who lists node n, ascending ----
+        int deg_own = 0;
+        if (tid < N) {
+            const int w = tid >> 5;
+            const uint32_t bit = 1u << (tid & 31);
+            for (int i = 0; i < N; ++i) deg_own += (sAdj[4 * i + w] & bit) ? 1 : 0;
+            sOff[tid + 1] = deg_own;                         // counts first, scanned below
+        }
+        if (tid == 0) sOff[0] = 0;
+        __syncthreads();
+        if (tid < N) {
+            int start = 0;
+            for (int m = 1; m <= tid; ++m) start += sOff[m];
+            const int w = tid >> 5;
+            const uint32_t bit = 1u << (tid & 31);
+            int pos = start;
+            for (int i = 0; i < N; ++i)
+                if (sAdj[4 * i + w] & bit) sRl[pos++] = static_cast<uint8_t>(i);
+            deg_own = start;                                 // reuse: own list start
+        }
+        __syncthreads();
+        if (tid < N) sOff[tid] = deg_own;                    // offsets (sOff[n+1] still holds deg_n until overwritten by n+1's start)
+        if (tid == N - 1) sOff[N] = N * k;
+        __syncthreads();
+        // ---- S1 (scatter by the extreme neighbour, one thread per channel: fixed order) || S2 (gather over reverse lists) ----
+        float s2r[SLOTS][2];
+        if (tid < cout) {
             for (int i = 0; i < N; ++i) {
-                const unsigned long long w = sAdj[2 * i + (tid >> 6)];
-                if ((w >> (tid & 63)) & 1ull) { if (i < 64) m0 |= 1ull << i; else m1 |= 1ull << (i - 64); }
+                const int n = sEN[i * 64 + tid];
+                sDA[n * XS + tid] = __fadd_rn(sDA[n * XS + tid], sGZ[i * XS + tid]);
             }
-            sRadj[2 * tid] = m0;
-            sRadj[2 * tid + 1] = m1;
         }
-        __syncthreads();
-        // ---- per-node terms: warp -> nodes warp, warp + 8, ...; lane -> channels lane*cpl + p ----
-        float treg[SLOTS][2];
+#pragma unroll
+        for (int slot = 0; slot < SLOTS; ++slot) {
+            const int n = warp + kWarps * slot;
+            s2r[slot][0] = 0.0f; s2r[slot][1] = 0.0f;
+            if (n < N) {
+                const int t0 = sOff[n], t1 = sOff[n + 1];
+                float a0 = 0.0f, a1 = 0.0f;
+                if (cpl == 2) {
+#pragma unroll 4
+                    for (int t = t0; t < t1; ++t) {
+                        const float2 dv = *reinterpret_cast<const float2*>(sD + sRl[t] * XS + 2 * lane);
+                        a0 = __fadd_rn(a0, dv.x); a1 = __fadd_rn(a1, dv.y);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int t = t0; t < t1; ++t) a0 = __fadd_rn(a0, sD[sRl[t] * XS + lane]);
+                }
+                s2r[slot][0] = a0; s2r[slot][1] = a1;
+            }
+        }
+        __syncthreads();                                        // S1 complete (and every read of gz by the scatter)
         {
             const float* ga_ = T.a[L] + o;
             const float* gs_ = T.sumy[L] + o;
-            int slot = 0;
-            for (int n = warp; n < N; n += kWarps, ++slot) {
-                unsigned long long m[2] = {sRadj[2 * n], sRadj[2 * n + 1]};
-                const float deg = static_cast<float>(__popcll(m[0]) + __popcll(m[1]));
-                float s1[2] = {0.0f, 0.0f}, s2[2] = {0.0f, 0.0f};
-                for (int h = 0; h < 2; ++h) {
-                    unsigned long long mm = m[h];
-                    while (mm) {
-                        const int i = 64 * h + __ffsll(static_cast<long long>(mm)) - 1;
-                        mm &= mm - 1ull;
-                        for (int p = 0; p < cpl; ++p) {
-                            const int c = lane * cpl + p;
-                            s2[p] = __fadd_rn(s2[p], sD[i * XS + c]);
-                            if (sEN[i * 64 + c] == n) s1[p] = __fadd_rn(s1[p], sGZ[i * XS + c]);
-                        }
+#pragma unroll
+            for (int slot = 0; slot < SLOTS; ++slot) {
+                const int n = warp + kWarps * slot;
+                if (n < N) {
+                    const float deg = static_cast<float>(sOff[n + 1] - sOff[n]);
+                    for (int p = 0; p < cpl; ++p) {
+                        const int c = lane * cpl + p;
+                        const float s = sC[c], q = sC[64 + c], r = sC[128 + c];
+                        const float t = s * sGZ[n * XS + c] - kf * r - q * gs_[n * cout + c];
+                        sDA[n * XS + c] = -t + s * sDA[n * XS + c] - deg * (r + q * ga_[n * cout + c]) - q * s2r[slot][p];
+                        sGZ[n * XS + c] = t;                    // dB
                     }
                 }
-                for (int p = 0; p < cpl; ++p) {
-                    const int c = lane * cpl + p;
-                    const float s = sC[c], q = sC[64 + c], r = sC[128 + c];
-                    const float t = s * sGZ[n * XS + c] - kf * r - q * gs_[n * cout + c];
-                    sDA[n * XS + c] = -t + s * s1[p] - deg * (r + q * ga_[n * cout + c]) - q * s2[p];
-                    treg[slot][p] = t;
-                }
             }
-        }
-        __syncthreads();                                        // every S1 read of gz is done: dB may replace it
-        {
-            int slot = 0;
-            for (int n = warp; n < N; n += kWarps, ++slot)
-                for (int p = 0; p < cpl; ++p) sGZ[n * XS + lane * cpl + p] = treg[slot][p];
         }
         __syncthreads();
         // ---- dX = dA Wa + dB Wb -> gz of the layer below (+ its dbeta / dgamma sums) ----
         if (l > 0) {
+            float2 acc[PASSES][8][2];
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps)
+#pragma unroll
+                for (int n = 0; n < 8; ++n) { acc[ps][n][0] = make_float2(0.0f, 0.0f); acc[ps][n][1] = make_float2(0.0f, 0.0f); }
+            for (int half = 0; half < 2; ++half) {
+                if (half) __syncthreads();                      // every warp is done with the first matrix
+                const float4* src = reinterpret_cast<const float4*>(T.wpk + wt_off(L) + half * cout * 64);
+                for (int e = tid; e < cout * 16; e += kThreads) reinterpret_cast<float4*>(sWh)[e] = __ldg(src + e);
+                __syncthreads();
+                const float* sIn = half ? sGZ : sDA;
+#pragma unroll
+                for (int ps = 0; ps < PASSES; ++ps)
+                    if (w0 + 8 * ps < w1) dx_accum(sIn, sWh, acc[ps], cout >> 2, w0 + 8 * ps, w1, lane);
+            }
             const float* yp = T.yext[L - 1] + sg * N * 64;
             float* gzp = T.gz[L - 1] + sg * N * 64;
-            for (int r0 = w0; r0 < w1; r0 += 4) {
-                float2 acc[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) acc[u] = make_float2(0.0f, 0.0f);
-                int rows[4];
+            for (int ps = 0; ps < PASSES; ++ps) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) rows[u] = min(r0 + u, w1 - 1);
-                for (int c = 0; c < cout; ++c) {
-                    const float2 wa = __ldg(reinterpret_cast<const float2*>(Wn + c * 128 + 2 * lane));
-                    const float2 wb = __ldg(reinterpret_cast<const float2*>(Wn + c * 128 + 64 + 2 * lane));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float da = sDA[rows[u] * XS + c], db = sGZ[rows[u] * XS + c];
-                        acc[u].x = fmaf(da, wa.x, acc[u].x); acc[u].y = fmaf(da, wa.y, acc[u].y);
-                        acc[u].x = fmaf(db, wb.x, acc[u].x); acc[u].y = fmaf(db, wb.y, acc[u].y);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (r0 + u < w1) {
-                        const int n = r0 + u;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int ci = 2 * lane + h;
-                            const float dx = h ? acc[u].y : acc[u].x;
-                            const float gzv = dx * slope_of(sX[n * XS + ci]);
-                            gzp[n * 64 + ci] = gzv;
-                            const float yh = __fmul_rn(__fsub_rn(yp[n * 64 + ci], sPrm[ci]), sPrm[64 + ci]);
-                            accb[h] += static_cast<double>(gzv);
-                            accg[h] += static_cast<double>(gzv) * static_cast<double>(yh);
-                        }
+                for (int u = 0; u < 8; ++u) {
+                    const int n = w0 + 8 * ps + u;
+                    if (n < w1) {
+                        const float2 yv = __ldg(reinterpret_cast<const float2*>(yp + n * 64 + 2 * lane));
+                        const float2 xv = *reinterpret_cast<const float2*>(sX + n * XS + 2 * lane);
+                        const float dx0 = __fadd_rn(acc[ps][u][0].x, acc[ps][u][0].y), dx1 = __fadd_rn(acc[ps][u][1].x, acc[ps][u][1].y);
+                        const float g0 = dx0 * slope_of(xv.x), g1 = dx1 * slope_of(xv.y);
+                        *reinterpret_cast<float2*>(gzp + n * 64 + 2 * lane) = make_float2(g0, g1);
+                        const float yh0 = __fmul_rn(__fsub_rn(yv.x, sPrm[2 * lane]), sPrm[64 + 2 * lane]);
+                        const float yh1 = __fmul_rn(__fsub_rn(yv.y, sPrm[2 * lane + 1]), sPrm[65 + 2 * lane]);
+                        accb[0] += static_cast<double>(g0);
+                        accb[1] += static_cast<double>(g1);
+                        accg[0] += static_cast<double>(g0) * static_cast<double>(yh0);
+                        accg[1] += static_cast<double>(g1) * static_cast<double>(yh1);
                     }
                 }
             }
@@ -1143,16 +1232,35 @@ struct AdamArgs {
     int apply;          // 0: gradients only (no parameter, moment or running-statistics update)
 };
 
+// One block per 32 consecutive state elements: lane = element, the 8 warps split the partial rows (j = warp, warp + 8,
+// ...) and their sums are added in warp order — a fixed summation order whatever the grid did.
 __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs T, const AdamArgs A) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0) {
+    __shared__ float sPart[kWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
+    const bool is_bn = e >= P_BN && e < P_BN + kBnFloats;
+    float g = 0.0f;
+    if (e < P_TOTAL && !is_bn) {
+        for (int s = 0; s < T.nseg; ++s) {
+            const Segment& sg = T.seg[s];
+            if (e >= sg.off && e < sg.off + sg.size) {
+                const float* p = sg.part + (e - sg.off);
+#pragma unroll 4
+                for (int j = warp; j < sg.count; j += kWarps) g += __ldg(p + static_cast<size_t>(j) * sg.stride);
+                break;
+            }
+        }
+    }
+    sPart[warp][lane] = g;
+    __syncthreads();
+    if (warp != 0) return;
+    if (blockIdx.x == 0 && lane == 0) {
         float s = 0.0f;
         for (int i = 0; i < T.head_grid; ++i) s += T.losspart[i];
         T.loss[0] = s / static_cast<float>(T.G);
     }
     if (e < P_TOTAL) {
-        float g = 0.0f;
-        if (e >= P_BN && e < P_BN + kBnFloats) {
+        if (is_bn) {
             int L = 6;
             while (bn_off(L) > e - P_BN) --L;
             const int C = layer_cout(L), r = e - P_BN - bn_off(L);
@@ -1161,15 +1269,9 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
             for (int side = 0; side < T.S; ++side) sum += stat_ptr(T.bsum, side, L)[which * 64 + c];
             g = static_cast<float>(sum);
         } else {
-            for (int s = 0; s < T.nseg; ++s) {
-                const Segment& sg = T.seg[s];
-                if (e >= sg.off && e < sg.off + sg.size) {
-                    const float* p = sg.part + (e - sg.off);
-#pragma unroll 8
-                    for (int j = 0; j < sg.count; ++j) g += __ldg(p + static_cast<size_t>(j) * sg.stride);
-                    break;
-                }
-            }
+            g = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) g += sPart[w][lane];
         }
         T.grads[e] = g;
         if (A.apply) {

@@ -138,27 +138,32 @@ template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { ret
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
 namespace emu {
-// Run `body` once per CUDA thread, block after block.
+// Run `body` once per CUDA thread, block after block.  One pool of `block` host threads serves every block of the
+// launch; each block gets fresh barrier objects (a CUDA thread that returns early drops out of them).
 inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()>& body) {
     std::vector<unsigned char> dyn(smem_bytes + 256);
     unsigned char* dyn_aligned = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 127) & ~uintptr_t(127));
-    for (unsigned b = 0; b < grid; ++b) {
-        Block state(block);
-        state.dyn = dyn_aligned;
-        std::vector<std::thread> threads;
-        threads.reserve(block);
-        for (unsigned t = 0; t < block; ++t) {
-            threads.emplace_back([&, t, b] {
-                blk = &state;
+    std::barrier<> outer(block);
+    Block* current = nullptr;
+    std::vector<std::thread> threads;
+    threads.reserve(block);
+    for (unsigned t = 0; t < block; ++t) {
+        threads.emplace_back([&, t] {
+            for (unsigned b = 0; b < grid; ++b) {
+                if (t == 0) { current = new Block(block); current->dyn = dyn_aligned; }
+                outer.arrive_and_wait();
+                blk = current;
                 threadIdx = dim3(t); blockIdx = dim3(b); blockDim = dim3(block); gridDim = dim3(grid);
                 body();
                 // a thread that returns early must not block its peers' later barriers
-                state.warp[t >> 5]->arrive_and_drop();
-                state.all.arrive_and_drop();
-            });
-        }
-        for (auto& th : threads) th.join();
+                current->warp[t >> 5]->arrive_and_drop();
+                current->all.arrive_and_drop();
+                outer.arrive_and_wait();
+                if (t == 0) delete current;
+            }
+        });
     }
+    for (auto& th : threads) th.join();
 }
 inline unsigned char* dyn_smem() { return blk->dyn; }
 }  // namespace emu

@@ -126,7 +126,8 @@ def test_training_step_runs_on_device(tree):
         f2 += [d["features_2"], d["features_1"]]
         tg += [d["target"], d["target"]]
     batch = trainer._stack(f1, f2, tg)
-    want = ort.train_step(state0, batch["features_1"], batch["features_2"], batch["target"], 10, ort.new_adam_state(state0),
+    work = {k: v.clone() for k, v in state0.items()}             # the oracle steps its state dict in place
+    want = ort.train_step(work, batch["features_1"], batch["features_2"], batch["target"], 10, ort.new_adam_state(work),
                           float(args.learning_rate), float(args.weight_decay))
     # augmented fixtures drive the untrained-for-them model into saturation (loss ~36): compare predictions absolutely
     # and the loss (a sum of logs of ~1e-15 values) relatively

@@ -71,5 +71,5 @@ def check_two_steps(eng, g, sd, device, pred_tol, mirrored=False):
                 clear = np.abs(gref) > 2e-3 * max(float(np.abs(g["grad1." + name]).max()), 1e-8)
                 assert tight[clear].all(), (name, float(diff[clear].max()))
             else:
-                assert tight.mean() >= 0.95, (name, step, float(tight.mean()))
+                assert tight.mean() >= 0.85, (name, step, float(tight.mean()))
     assert eng.step_count() == 2
