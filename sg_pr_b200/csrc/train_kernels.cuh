@@ -206,9 +206,22 @@ __host__ __device__ inline FwdSmem fwd_layout(int nmax, int ks) {
     return L;
 }
 
-// fill the node-major input tile of EdgeConv layer l of branch br for graph (side, g); columns beyond cin stay zero
-__device__ __forceinline__ void fill_layer_input(const TrainWs& T, int l, int br, int side, int g, float* sX, float* sPrm,
-                                                 int tid) {
+// BatchNorm terms of the layer below (mu | istd | gamma | beta per channel) for a CTA's (side, layer): once per CTA
+__device__ __forceinline__ void load_prev_bn(const TrainWs& T, int Lprev, int side, float* sPrm, int tid) {
+    if (tid < 64) {
+        float mu, istd;
+        bn_coef(stat_ptr(T.stats, side, Lprev), tid, static_cast<double>(T.G) * T.N * T.k, T.eps, mu, istd);
+        sPrm[tid] = mu;
+        sPrm[64 + tid] = istd;
+        sPrm[128 + tid] = T.state[P_BN + bn_off(Lprev) + tid];
+        sPrm[192 + tid] = T.state[P_BN + bn_off(Lprev) + 64 + tid];
+    }
+}
+
+// fill the node-major input tile of EdgeConv layer l of branch br for graph (side, g); columns beyond cin stay zero.
+// l > 0 needs load_prev_bn + a barrier beforehand.
+__device__ __forceinline__ void fill_layer_input(const TrainWs& T, int l, int br, int side, int g, float* sX,
+                                                 const float* sPrm, int tid) {
     const int N = T.N, L = br * 3 + l;
     if (l == 0) {
         const float* gin = T.f[side] + static_cast<size_t>(g) * kInCh * N;
@@ -222,15 +235,6 @@ __device__ __forceinline__ void fill_layer_input(const TrainWs& T, int l, int br
             }
         }
     } else {
-        if (tid < 64) {
-            float mu, istd;
-            bn_coef(stat_ptr(T.stats, side, L - 1), tid, static_cast<double>(T.G) * N * T.k, T.eps, mu, istd);
-            sPrm[tid] = mu;
-            sPrm[64 + tid] = istd;
-            sPrm[128 + tid] = T.state[P_BN + bn_off(L - 1) + tid];
-            sPrm[192 + tid] = T.state[P_BN + bn_off(L - 1) + 64 + tid];
-        }
-        __syncthreads();
         const float4* yp = reinterpret_cast<const float4*>(T.yext[L - 1] + (static_cast<size_t>(side) * T.G + g) * N * 64);
         for (int e = tid; e < N * 16; e += kThreads) {
             const int n = e >> 4, c = (e & 15) * 4;
@@ -307,59 +311,60 @@ __device__ __forceinline__ void train_gather_rows(const float* __restrict__ sY, 
 }
 
 // xyz layer 1 in the reference's direct per-edge form W_a (x_j - x_i) + W_b x_i (metre-scale coordinates would lose
-// ~5 bits in A_j - A_i; same choice and FMA order as embed_kernel.cuh::xyz_rows).  sW: natural [64][6].
+// ~5 bits in A_j - A_i; same choice as embed_kernel.cuh::xyz_rows).  Per edge only e_ij = W_a (x_j - x_i) is formed; the
+// centre term c_i = W_b x_i joins per node: sum y = SE + k c, sum y^2 = SE2 + 2 c SE + k c^2.  sW: natural [64][6].
 __device__ __forceinline__ void train_xyz_rows(const float* __restrict__ sX, const uint16_t* __restrict__ sIdx, int KS, int k,
                                                const float* __restrict__ sW, const float* __restrict__ gamma,
                                                float* __restrict__ yext, float* __restrict__ ga, float* __restrict__ gd,
                                                float* __restrict__ gsum, uint8_t* __restrict__ enode, int r0, int r1,
                                                int lane, double (&acc1)[2], double (&acc2)[2]) {
     float wa[2][3], wb[2][3];
-    bool pos[2];
+    uint32_t flip[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int c = 2 * lane + p;
 #pragma unroll
         for (int u = 0; u < 3; ++u) { wa[p][u] = sW[c * 6 + u]; wb[p][u] = sW[c * 6 + 3 + u]; }
-        pos[p] = gamma[c] >= 0.0f;
+        flip[p] = gamma[c] >= 0.0f ? 0u : 0x80000000u;
     }
+    const float kf = static_cast<float>(k);
     for (int i = r0; i < r1; ++i) {
         const float4 xi = *reinterpret_cast<const float4*>(sX + i * XS);
-        float best[2], s1[2], s2[2];
+        float best[2], se[2], se2[2];
         int bj[2];
 #pragma unroll
-        for (int p = 0; p < 2; ++p) { best[p] = pos[p] ? -INFINITY : INFINITY; s1[p] = 0.0f; s2[p] = 0.0f; bj[p] = 0; }
+        for (int p = 0; p < 2; ++p) { best[p] = -INFINITY; se[p] = 0.0f; se2[p] = 0.0f; bj[p] = 0; }
+        const uint16_t* list = sIdx + i * KS;
+#pragma unroll 4
         for (int e = 0; e < k; ++e) {
-            const int j = sIdx[i * KS + e];
+            const int j = list[e];
             const float4 xj = *reinterpret_cast<const float4*>(sX + j * XS);
             const float d0 = __fsub_rn(xj.x, xi.x), d1 = __fsub_rn(xj.y, xi.y), d2 = __fsub_rn(xj.z, xi.z);
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 const float ev = fmaf(wa[p][2], d2, fmaf(wa[p][1], d1, __fmul_rn(wa[p][0], d0)));
-                float y = fmaf(wb[p][0], xi.x, ev);
-                y = fmaf(wb[p][1], xi.y, y);
-                y = fmaf(wb[p][2], xi.z, y);
-                s1[p] = __fadd_rn(s1[p], y);
-                s2[p] = fmaf(y, y, s2[p]);
-                const bool better = pos[p] ? (ev > best[p]) : (ev < best[p]);
-                best[p] = better ? ev : best[p];
-                bj[p] = better ? j : bj[p];
+                se[p] = __fadd_rn(se[p], ev);
+                se2[p] = fmaf(ev, ev, se2[p]);
+                const float vs = __uint_as_float(__float_as_uint(ev) ^ flip[p]);
+                bj[p] = vs > best[p] ? j : bj[p];
+                best[p] = fmaxf(best[p], vs);
             }
         }
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const size_t o = static_cast<size_t>(i) * 64 + 2 * lane + p;
-            float y = fmaf(wb[p][0], xi.x, best[p]);
-            y = fmaf(wb[p][1], xi.y, y);
-            y = fmaf(wb[p][2], xi.z, y);
             const float av = fmaf(wa[p][2], xi.z, fmaf(wa[p][1], xi.y, __fmul_rn(wa[p][0], xi.x)));
-            const float bv = fmaf(wb[p][2], xi.z, fmaf(wb[p][1], xi.y, __fmul_rn(wb[p][0], xi.x)));
-            yext[o] = y;
+            const float cb = fmaf(wb[p][2], xi.z, fmaf(wb[p][1], xi.y, __fmul_rn(wb[p][0], xi.x)));
+            const float ext = __uint_as_float(__float_as_uint(best[p]) ^ flip[p]);
+            const float s1 = fmaf(kf, cb, se[p]);
+            const float s2 = fmaf(kf * cb, cb, fmaf(2.0f * cb, se[p], se2[p]));
+            yext[o] = __fadd_rn(ext, cb);
             ga[o] = av;
-            gd[o] = __fsub_rn(bv, av);
-            gsum[o] = s1[p];
+            gd[o] = __fsub_rn(cb, av);
+            gsum[o] = s1;
             enode[o] = static_cast<uint8_t>(bj[p]);
-            acc1[p] += static_cast<double>(s1[p]);
-            acc2[p] += static_cast<double>(s2[p]);
+            acc1[p] += static_cast<double>(s1);
+            acc2[p] += static_cast<double>(s2);
         }
     }
 }
@@ -414,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     }
     for (int e = tid; e < NMAX * XS; e += kThreads) sX[e] = 0.0f;
     for (int e = tid; e < NMAX; e += kThreads) sXX[e] = 0.0f;
+    if (l > 0) load_prev_bn(T, L - 1, side, sPrm, tid);
     __syncthreads();
 
     const int rpw = (N + kWarps - 1) / kWarps;
@@ -911,8 +917,8 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_b
 // EdgeConv layer l backward for both branches and both sides (grid = multiple of 4, CTA -> (branch, side), loops g).
 // part: [grid/2 per branch][cout * 2 cin] conv-weight partials in the state_dict layout.
 // =====================================================================================================================
-struct BwdSmem { int x, gz, d, da, wh, en, adj, off, rl, c, prm, red, total; };
-__host__ __device__ inline BwdSmem bwd_layout(int nmax, int ks) {
+struct BwdSmem { int x, gz, d, da, wh, en, adj, c, prm, red, total; };
+__host__ __device__ inline BwdSmem bwd_layout(int nmax) {
     BwdSmem L;
     int o = 0;
     L.x = o;    o += nmax * XS * 4;
@@ -922,8 +928,6 @@ __host__ __device__ inline BwdSmem bwd_layout(int nmax, int ks) {
     L.wh = o;   o += 64 * 64 * 4;                        // one transposed half (MA, then MB) for the dX GEMM
     L.en = o;   o += nmax * 64;
     L.adj = o;  o += nmax * 16;                          // 128-bit neighbour mask per node
-    L.off = o;  o += (nmax + 4) * 4;                     // CSR offsets of the reverse lists
-    L.rl = o;   o += ((nmax * ks + 15) / 16) * 16;       // reverse lists: who lists node n (N*k entries in total)
     L.c = o;    o += 4 * 64 * 4;
     L.prm = o;  o += 4 * 64 * 4;
     L.red = o;  o += kWarps * 128 * 8;
@@ -988,7 +992,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     constexpr int SLOTS = 4 * NPL;                    // nodes per warp
     constexpr int PASSES = (NPL == 4) ? 2 : 1;        // 8-row passes of the dX GEMM per warp
     SGPR_DYN_SMEM(smem);
-    const BwdSmem S = bwd_layout(NMAX, T.KS);
+    const BwdSmem S = bwd_layout(NMAX);
     float* sX = reinterpret_cast<float*>(smem + S.x);
     float* sGZ = reinterpret_cast<float*>(smem + S.gz);         // gz, later dB
     float* sD = reinterpret_cast<float*>(smem + S.d);
@@ -996,8 +1000,6 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     float* sWh = reinterpret_cast<float*>(smem + S.wh);
     uint8_t* sEN = smem + S.en;
     uint32_t* sAdj = reinterpret_cast<uint32_t*>(smem + S.adj); // [NMAX][4]
-    int* sOff = reinterpret_cast<int*>(smem + S.off);
-    uint8_t* sRl = smem + S.rl;
     float* sC = reinterpret_cast<float*>(smem + S.c);           // s | q | r | (spare)
     float* sPrm = reinterpret_cast<float*>(smem + S.prm);       // previous layer: mu | istd | gamma | beta
     double* sRed = reinterpret_cast<double*>(smem + S.red);
@@ -1021,6 +1023,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
         sC[64 + tid] = q;
         sC[128 + tid] = pterm - q * mu;
     }
+    if (l > 0) load_prev_bn(T, L - 1, side, sPrm, tid);
     __syncthreads();
 
     float ga[16], gb[16];
@@ -1047,45 +1050,50 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
                 *reinterpret_cast<uint32_t*>(sEN + n * 64 + c) = __ldg(en + e);
                 *reinterpret_cast<float4*>(sDA + n * XS + c) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
-            if (tid < N) {
-                const uint8_t* gi = T.idx[L] + (sg * N + tid) * k;
-                uint32_t m[4] = {0u, 0u, 0u, 0u};
-                for (int e = 0; e < k; ++e) {
+            // neighbour bit masks, one warp per node (lanes = list entries, OR-reduced across the warp)
+            for (int i = warp; i < N; i += kWarps) {
+                const uint8_t* gi = T.idx[L] + (sg * N + i) * k;
+                uint32_t m[NPL];
+#pragma unroll
+                for (int w = 0; w < NPL; ++w) m[w] = 0u;
+                for (int e = lane; e < k; e += 32) {
                     const int j = gi[e];
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) m[w] |= (j >> 5) == w ? (1u << (j & 31)) : 0u;
+                    for (int w = 0; w < NPL; ++w) m[w] |= (j >> 5) == w ? (1u << (j & 31)) : 0u;
                 }
 #pragma unroll
-                for (int w = 0; w < 4; ++w) sAdj[4 * tid + w] = m[w];
+                for (int w = 0; w < NPL; ++w) {
+                    const uint32_t all = __reduce_or_sync(0xffffffffu, m[w]);
+                    if (lane == 0) sAdj[4 * i + w] = all;
+                }
             }
         }
         __syncthreads();
-        // ---- reverse neighbour lists (CSR): who lists node n, ascending ----
-        int deg_own = 0;
-        if (tid < N) {
-            const int w = tid >> 5;
-            const uint32_t bit = 1u << (tid & 31);
-            for (int i = 0; i < N; ++i) deg_own += (sAdj[4 * i + w] & bit) ? 1 : 0;
-            sOff[tid + 1] = deg_own;                         // counts first, scanned below
+        // ---- reverse neighbourhoods of own nodes (n = warp, warp + 8, ...) as warp-uniform bit masks: bit i of word q is set
+        // when node 32 q + i lists n.  Then S1 (scatter by the extreme neighbour, one thread per channel: fixed order)
+        // runs beside S2 (gather over the reverse neighbourhood, ascending node order). ----
+        uint32_t rmask[SLOTS][NPL];
+        float s2r[SLOTS][2], areg[SLOTS][2], syreg[SLOTS][2];
+        {
+            const float* ga_ = T.a[L] + o;
+            const float* gs_ = T.sumy[L] + o;
+#pragma unroll
+            for (int slot = 0; slot < SLOTS; ++slot) {
+                const int n = warp + kWarps * slot;
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                    const int i = 32 * q + lane;
+                    const bool lists = (n < N && i < N) ? ((sAdj[4 * i + (n >> 5)] >> (n & 31)) & 1u) != 0u : false;
+                    rmask[slot][q] = __ballot_sync(0xffffffffu, lists);
+                }
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {                   // operands of the per-node terms, in flight during S2
+                    const bool live = n < N && p < cpl;
+                    areg[slot][p] = live ? __ldg(ga_ + n * cout + lane * cpl + p) : 0.0f;
+                    syreg[slot][p] = live ? __ldg(gs_ + n * cout + lane * cpl + p) : 0.0f;
+                }
+            }
         }
-        if (tid == 0) sOff[0] = 0;
-        __syncthreads();
-        if (tid < N) {
-            int start = 0;
-            for (int m = 1; m <= tid; ++m) start += sOff[m];
-            const int w = tid >> 5;
-            const uint32_t bit = 1u << (tid & 31);
-            int pos = start;
-            for (int i = 0; i < N; ++i)
-                if (sAdj[4 * i + w] & bit) sRl[pos++] = static_cast<uint8_t>(i);
-            deg_own = start;                                 // reuse: own list start
-        }
-        __syncthreads();
-        if (tid < N) sOff[tid] = deg_own;                    // offsets (sOff[n+1] still holds deg_n until overwritten by n+1's start)
-        if (tid == N - 1) sOff[N] = N * k;
-        __syncthreads();
-        // ---- S1 (scatter by the extreme neighbour, one thread per channel: fixed order) || S2 (gather over reverse lists) ----
-        float s2r[SLOTS][2];
         if (tid < cout) {
             for (int i = 0; i < N; ++i) {
                 const int n = sEN[i * 64 + tid];
@@ -1094,38 +1102,39 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
         }
 #pragma unroll
         for (int slot = 0; slot < SLOTS; ++slot) {
-            const int n = warp + kWarps * slot;
-            s2r[slot][0] = 0.0f; s2r[slot][1] = 0.0f;
-            if (n < N) {
-                const int t0 = sOff[n], t1 = sOff[n + 1];
-                float a0 = 0.0f, a1 = 0.0f;
-                if (cpl == 2) {
-#pragma unroll 4
-                    for (int t = t0; t < t1; ++t) {
-                        const float2 dv = *reinterpret_cast<const float2*>(sD + sRl[t] * XS + 2 * lane);
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+                uint32_t mm = rmask[slot][q];
+                while (mm) {
+                    const int i = 32 * q + __ffs(static_cast<int>(mm)) - 1;
+                    mm &= mm - 1u;
+                    if (cpl == 2) {
+                        const float2 dv = *reinterpret_cast<const float2*>(sD + i * XS + 2 * lane);
                         a0 = __fadd_rn(a0, dv.x); a1 = __fadd_rn(a1, dv.y);
+                    } else {
+                        a0 = __fadd_rn(a0, sD[i * XS + lane]);
                     }
-                } else {
-#pragma unroll 4
-                    for (int t = t0; t < t1; ++t) a0 = __fadd_rn(a0, sD[sRl[t] * XS + lane]);
                 }
-                s2r[slot][0] = a0; s2r[slot][1] = a1;
             }
+            s2r[slot][0] = a0; s2r[slot][1] = a1;
         }
         __syncthreads();                                        // S1 complete (and every read of gz by the scatter)
-        {
-            const float* ga_ = T.a[L] + o;
-            const float* gs_ = T.sumy[L] + o;
 #pragma unroll
-            for (int slot = 0; slot < SLOTS; ++slot) {
-                const int n = warp + kWarps * slot;
-                if (n < N) {
-                    const float deg = static_cast<float>(sOff[n + 1] - sOff[n]);
-                    for (int p = 0; p < cpl; ++p) {
+        for (int slot = 0; slot < SLOTS; ++slot) {
+            const int n = warp + kWarps * slot;
+            if (n < N) {
+                int dg = 0;
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) dg += __popc(rmask[slot][q]);
+                const float deg = static_cast<float>(dg);
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    if (p < cpl) {
                         const int c = lane * cpl + p;
                         const float s = sC[c], q = sC[64 + c], r = sC[128 + c];
-                        const float t = s * sGZ[n * XS + c] - kf * r - q * gs_[n * cout + c];
-                        sDA[n * XS + c] = -t + s * sDA[n * XS + c] - deg * (r + q * ga_[n * cout + c]) - q * s2r[slot][p];
+                        const float t = s * sGZ[n * XS + c] - kf * r - q * syreg[slot][p];
+                        sDA[n * XS + c] = -t + s * sDA[n * XS + c] - deg * (r + q * areg[slot][p]) - q * s2r[slot][p];
                         sGZ[n * XS + c] = t;                    // dB
                     }
                 }

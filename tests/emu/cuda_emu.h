@@ -88,6 +88,14 @@ inline int __reduce_max_sync(unsigned, int v) {
     for (int d = 16; d >= 1; d >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, v, d); v = o > v ? o : v; }
     return v;
 }
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    for (int d = 16; d >= 1; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+inline unsigned __ballot_sync(unsigned, bool pred) {
+    unsigned v = pred ? (1u << (threadIdx.x & 31)) : 0u;
+    return __reduce_or_sync(0xffffffffu, v);
+}
 inline int __reduce_add_sync(unsigned, int v) {
     for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     return v;
