@@ -333,7 +333,7 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
     TRY_CUDA(cudaMemsetAsync(t->d_sums, 0, kSumDoubles * sizeof(double), st));
 
     const FwdSmem FS = fwd_layout(nmax, KS);
-    const BwdSmem BS = bwd_layout(nmax);
+    const BwdSmem BS = bwd_layout(nmax, KS);
     const size_t end_fwd_smem = (64 * 32 + 2 * static_cast<size_t>(nmax) * XS + 256) * 4 + kWarps * 128 * 8;
     const size_t end_bwd_smem = (32 * 64 + static_cast<size_t>(nmax) * XS + static_cast<size_t>(nmax) * 36 + 256 + 192) * 4 + 4 * 128 * 8;
 

