@@ -74,6 +74,23 @@ int sgpr_train_set_optimizer(sgpr_train* t, float lr, float weight_decay, float 
 int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, const float* target_dev, int B, int N, int k,
                     float* loss_dev, float* pred_dev, int flags, void* stream);
 
+/*
+ * Training-batch assembly + augmentation on the device, for graphs already resident in HBM.  Replaces the host loop of
+ * process_batch (sg_net.py:316-331) with transfer_to_torch's training branch (sg_net.py:286-295) and the augmentations
+ * of utils.py:91-178 (reference defaults; applied to all node_num rows, zero pads included; one x-flip decision per
+ * listed pair):
+ *   graphs_dev   : [M][15][N]  un-augmented padded blocks, exactly what transfer_to_torch(training=False) builds
+ *   pair_idx_dev : [P][2] int32  listed pairs (graph a, graph b), indices into graphs_dev
+ *   out_f1_dev   : [2P][15][N]  row 2p = augmented a, row 2p+1 = augmented b  == features_1 of the mirrored batch
+ *   draws_dev    : NULL or [2P][12]  the random draws of every slot (flip u, angle u, scale, 3 raw perturbation normals,
+ *                  3 shifts) and jitter_dev : NULL or [2P][N][3] raw jitter normals — parity taps: the tests feed them
+ *                  to the reference-shaped numpy functions and compare.
+ * Random numbers are Philox4x32-10 keyed by `seed` with counter (step, slot, node): reproducible from (seed, step), but
+ * not numpy's global stream (which the reference never seeds) — parity with the reference is distributional.
+ */
+int sgpr_train_assemble(sgpr_train* t, const float* graphs_dev, int M, int N, const int32_t* pair_idx_dev, int P,
+                        uint64_t seed, uint64_t step, float* out_f1_dev, float* draws_dev, float* jitter_dev, void* stream);
+
 /* Gradients of the last step w.r.t. the trainable parameters (before weight decay), flat layout, host pointer. */
 int sgpr_train_get_grads(sgpr_train* t, float* grads_host);
 

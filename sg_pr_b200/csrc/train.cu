@@ -374,6 +374,26 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
 #undef BY_NPL
 }
 
+int sgpr_train_assemble(sgpr_train* t, const float* graphs_dev, int M, int N, const int32_t* pair_idx_dev, int P,
+                        uint64_t seed, uint64_t step, float* out_f1_dev, float* draws_dev, float* jitter_dev, void* stream) {
+    if (!t) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_assemble: NULL context");
+    if (P < 0 || M < 1) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_assemble: bad sizes (M=%d, P=%d)", M, P);
+    if (N < 2 || N > SGPR_MAX_NODES) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_assemble: node_num %d outside [2,%d]", N, SGPR_MAX_NODES);
+    if (P == 0) return SGPR_OK;
+    if (!graphs_dev || !pair_idx_dev || !out_f1_dev) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_assemble: NULL pointer");
+    Guard guard(t->device);
+    AssembleArgs A{};
+    A.graphs = graphs_dev; A.pair_idx = pair_idx_dev; A.out = out_f1_dev; A.draws = draws_dev; A.jitter = jitter_dev;
+    A.M = M; A.N = N; A.P = P;
+    A.seed_lo = static_cast<uint32_t>(seed); A.seed_hi = static_cast<uint32_t>(seed >> 32);
+    A.step_lo = static_cast<uint32_t>(step); A.step_hi = static_cast<uint32_t>(step >> 32);
+    const int grid = 2 * P < 8 * t->sm_count ? 2 * P : 8 * t->sm_count;
+    SGPR_LAUNCH(sgpr_train_assemble_kernel, grid, kThreads, 0, static_cast<cudaStream_t>(stream), A);
+    t->launches += 1;
+    TRY_CUDA(cudaGetLastError());
+    return SGPR_OK;
+}
+
 int sgpr_train_get_grads(sgpr_train* t, float* grads_host) {
     if (!t || !grads_host) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_get_grads: NULL argument");
     Guard guard(t->device);

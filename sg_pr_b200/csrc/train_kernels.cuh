@@ -1331,5 +1331,105 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
     }
 }
 
+// =====================================================================================================================
+// Training-batch assembly + augmentation on the device.  Replaces, for graphs already resident in HBM, the host loop of
+// process_batch (sg_net.py:316-331) with transfer_to_torch's training branch (sg_net.py:286-295) and the point-cloud
+// augmentations of utils.py:91-178 (rotate about z, jitter sigma 0.01 clip 0.05, scale U[0.8, 1.25), rotation
+// perturbation sigma 0.015 clip 0.045, shift U[-0.3, 0.3) — the reference's defaults, applied in that order to all
+// node_num rows, zero pads included; one x-flip decision per listed pair shared by its two graphs, sg_net.py:288-291).
+// Random numbers: Philox4x32-10 keyed by the seed, counter = (step, slot, node, stream) — reproducible from
+// (seed, step), but NOT numpy's global Mersenne stream (the reference never seeds it).
+// Output row 2p / 2p+1 = augmented graph a / b of listed pair p: features_1 of the mirrored batch.
+// =====================================================================================================================
+struct Philox { uint32_t v[4]; };
+__host__ __device__ inline Philox philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0, n1 = static_cast<uint32_t>(p1);
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1, n3 = static_cast<uint32_t>(p0);
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox out;
+    out.v[0] = c0; out.v[1] = c1; out.v[2] = c2; out.v[3] = c3;
+    return out;
+}
+__host__ __device__ inline float u01(uint32_t x) { return static_cast<float>(x >> 8) * (1.0f / 16777216.0f); }         // [0, 1)
+__host__ __device__ inline float u01_open(uint32_t x) { return (static_cast<float>(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }  // (0, 1]
+// two standard normals from two words (Box-Muller)
+__device__ __forceinline__ void normal2(uint32_t a, uint32_t b, float& n0, float& n1) {
+    const float r = sqrtf(-2.0f * logf(u01_open(a)));
+    const float t = 6.283185307179586f * u01(b);
+    n0 = r * cosf(t);
+    n1 = r * sinf(t);
+}
+
+struct AssembleArgs {
+    const float* graphs;      // [M][15][N] un-augmented padded blocks
+    const int* pair_idx;      // [P][2]
+    float* out;               // [2P][15][N]
+    float* draws;             // optional [2P][12]: flip u, angle u, scale, 3 raw perturbation normals, 3 shifts (debug / tests)
+    float* jitter;            // optional [2P][N][3] raw jitter normals (debug / tests)
+    int M, N, P;
+    uint32_t seed_lo, seed_hi, step_lo, step_hi;
+};
+
+__global__ void __launch_bounds__(kThreads) sgpr_train_assemble_kernel(const AssembleArgs A) {
+    __shared__ float sPar[16];
+    const int tid = threadIdx.x, N = A.N;
+    for (int slot = blockIdx.x; slot < 2 * A.P; slot += gridDim.x) {
+        const int p = slot >> 1;
+        const int g = A.pair_idx[slot];
+        if (tid == 0) {
+            const Philox f = philox4x32(A.step_lo, A.step_hi, static_cast<uint32_t>(p), 0xF11Fu, A.seed_lo, A.seed_hi);
+            const Philox a = philox4x32(A.step_lo, A.step_hi, static_cast<uint32_t>(slot), 0xA001u, A.seed_lo, A.seed_hi);
+            const Philox b = philox4x32(A.step_lo, A.step_hi, static_cast<uint32_t>(slot), 0xA002u, A.seed_lo, A.seed_hi);
+            float n0, n1, n2, n3;
+            normal2(a.v[2], a.v[3], n0, n1);
+            normal2(b.v[0], b.v[1], n2, n3);
+            sPar[0] = u01(f.v[0]);                                   // flip when > 0.5 (random.random() > 0.5)
+            sPar[1] = u01(a.v[0]);                                   // rotation angle / 2 pi
+            sPar[2] = 0.8f + (1.25f - 0.8f) * u01(a.v[1]);           // scale
+            sPar[3] = n0; sPar[4] = n1; sPar[5] = n2;                // raw perturbation angles (x sigma, clipped below)
+            sPar[6] = -0.3f + 0.6f * u01(b.v[2]);                    // shifts
+            sPar[7] = -0.3f + 0.6f * u01(b.v[3]);
+            sPar[8] = -0.3f + 0.6f * u01(philox4x32(A.step_lo, A.step_hi, static_cast<uint32_t>(slot), 0xA003u, A.seed_lo, A.seed_hi).v[0]);
+            if (A.draws) for (int i = 0; i < 9; ++i) A.draws[slot * 12 + i] = sPar[i];
+        }
+        __syncthreads();
+        const float* src = A.graphs + static_cast<size_t>(g) * kInCh * N;
+        float* dst = A.out + static_cast<size_t>(slot) * kInCh * N;
+        for (int e = tid; e < kLabels * N; e += kThreads) dst[3 * N + e] = __ldg(src + 3 * N + e);     // label rows unchanged
+        const float flip = sPar[0] > 0.5f ? -1.0f : 1.0f;
+        const float ang = sPar[1] * 6.283185307179586f, c = cosf(ang), s = sinf(ang);
+        const float scale = sPar[2];
+        const float ax = fminf(fmaxf(0.015f * sPar[3], -0.045f), 0.045f), ay = fminf(fmaxf(0.015f * sPar[4], -0.045f), 0.045f),
+                    az = fminf(fmaxf(0.015f * sPar[5], -0.045f), 0.045f);
+        const float cx = cosf(ax), sx = sinf(ax), cy = cosf(ay), sy = sinf(ay), cz = cosf(az), sz = sinf(az);
+        // R = Rz (Ry Rx), applied to row vectors: out = p R   (utils.py rotate_perturbation_point_cloud)
+        const float r00 = cz * cy, r01 = cz * sy * sx - sz * cx, r02 = cz * sy * cx + sz * sx;
+        const float r10 = sz * cy, r11 = sz * sy * sx + cz * cx, r12 = sz * sy * cx - cz * sx;
+        const float r20 = -sy, r21 = cy * sx, r22 = cy * cx;
+        for (int n = tid; n < N; n += kThreads) {
+            float x = flip * __ldg(src + n), y = __ldg(src + N + n), z = __ldg(src + 2 * N + n);
+            const float xr = x * c + y * s, yr = -x * s + y * c;                      // p . Rot_z(angle)
+            const Philox q = philox4x32(A.step_lo, A.step_hi, static_cast<uint32_t>(slot), 0xB000u + static_cast<uint32_t>(n),
+                                        A.seed_lo, A.seed_hi);
+            float j0, j1, j2, j3;
+            normal2(q.v[0], q.v[1], j0, j1);
+            normal2(q.v[2], q.v[3], j2, j3);
+            if (A.jitter) { float* jd = A.jitter + (static_cast<size_t>(slot) * N + n) * 3; jd[0] = j0; jd[1] = j1; jd[2] = j2; }
+            x = (xr + fminf(fmaxf(0.01f * j0, -0.05f), 0.05f)) * scale;
+            y = (yr + fminf(fmaxf(0.01f * j1, -0.05f), 0.05f)) * scale;
+            z = (z + fminf(fmaxf(0.01f * j2, -0.05f), 0.05f)) * scale;
+            dst[n] = x * r00 + y * r10 + z * r20 + sPar[6];
+            dst[N + n] = x * r01 + y * r11 + z * r21 + sPar[7];
+            dst[2 * N + n] = x * r02 + y * r12 + z * r22 + sPar[8];
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace train
 }  // namespace sgpr

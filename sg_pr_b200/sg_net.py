@@ -196,6 +196,13 @@ class SGTrainer(object):
         self.embed_cache = True
         self._graph_store = None
         self._emb = None
+        # training-side pipeline switches.  `device_augment = True` moves batch assembly and the point-cloud augmentation
+        # onto the GPU (sgpr_train_assemble): graphs are parsed and uploaded once, a step sends only pair indices and
+        # targets.  Its random numbers are a Philox stream keyed by `augment_seed`, not numpy's global stream, so it is
+        # opt-in: the default keeps the reference's host code path and RNG call order.
+        self.device_augment = bool(getattr(args, "device_augment", False))
+        self.augment_seed = int(getattr(args, "augment_seed", 0))
+        self._dev_graphs = None
 
     # ---- construction ----------------------------------------------------------------------------------------
     def setup_model(self, train=True):
@@ -266,10 +273,12 @@ class SGTrainer(object):
         return nodes, centers
 
     def _one_hot(self, nodes):
+        """sg_net.py:270-275 / 281-286 without the Python loop: row r gets a 1 in column global_labels[nodes[r]]; pads
+        (label -1) stay all-zero."""
+        nodes = np.asarray(nodes)
         out = np.zeros((len(nodes), self.number_of_labels))
-        for row, node in enumerate(nodes):
-            if node != -1:
-                out[row, self.global_labels[int(node)]] = 1.0
+        real = np.nonzero(nodes != -1)[0]
+        out[real, [self.global_labels[int(v)] for v in nodes[real]]] = 1.0
         return out
 
     def transfer_to_torch(self, data, training=True):
@@ -333,17 +342,63 @@ class SGTrainer(object):
                     target.add_(2 * self._unsynced_steps)
         self._unsynced_steps = 0
 
+    def _device_graph_rows(self, paths):
+        """Row indices into the device-resident table of un-augmented graph blocks ([M, 15, node_num], what
+        transfer_to_torch(training=False) builds), uploading the graphs not seen yet.  None when a graph has more than
+        node_num nodes (the reference re-samples those on every use, sg_net.py:252-256: host path only)."""
+        store = self._store()
+        dev = self._device_trainer().device
+        tab = self._dev_graphs
+        if tab is None or tab["node_num"] != int(self.args.node_num):
+            tab = self._dev_graphs = {"node_num": int(self.args.node_num), "index": {}, "count": 0,
+                                      "blocks": torch.empty(1024, 15, int(self.args.node_num), device=dev)}
+        fresh = [p for p in dict.fromkeys(paths) if p not in tab["index"]]
+        if any(not store.is_static(p) for p in fresh):
+            return None
+        if fresh:
+            need = tab["count"] + len(fresh)
+            if need > tab["blocks"].shape[0]:
+                grown = torch.empty(max(need, 2 * tab["blocks"].shape[0]), 15, tab["node_num"], device=dev)
+                grown[:tab["count"]] = tab["blocks"][:tab["count"]]
+                tab["blocks"] = grown
+            tab["blocks"][tab["count"]:need] = torch.stack([store.block(p) for p in fresh]).to(dev)
+            for i, p in enumerate(fresh):
+                tab["index"][p] = tab["count"] + i
+            tab["count"] = need
+        return [tab["index"][p] for p in paths]
+
+    def _process_batch_on_device(self, batch):
+        """device_augment: pair indices + targets go up, sgpr_train_assemble builds the augmented mirrored batch in HBM,
+        sgpr_train_step trains on it.  Returns None when the batch needs the host path."""
+        rows = self._device_graph_rows([p for pair in batch for p in pair])
+        if rows is None:
+            return None
+        store, eng = self._store(), self._device_trainer()
+        targets = np.repeat(np.array([store.target(a, b, self.args.p_thresh) for a, b in batch], dtype=np.float32), 2)
+        idx = torch.tensor(rows, dtype=torch.int32).view(-1, 2).to(eng.device, non_blocking=True)
+        tgt = torch.from_numpy(targets).to(eng.device, non_blocking=True)
+        f1 = eng.assemble(self._dev_graphs["blocks"], idx, self.augment_seed, eng.step_count())
+        loss, prediction = eng.step(f1, None, tgt, int(self.args.K), apply=True, mirrored=True)
+        self._unsynced_steps += 1
+        return loss.item(), prediction.cpu().numpy().reshape(-1), targets.astype(np.float32)
+
     def process_batch(self, batch, training=True):
         """sg_net.py:312-345: every listed pair is fed in both orders; BCE; (training) backward + Adam step — the whole
         device part of a training step is ONE call into the C-ABI (sgpr_train_step)."""
         self.optimizer.zero_grad()
+        if training and self.device_augment and len(batch) > 0:
+            done = self._process_batch_on_device(batch)
+            if done is not None:
+                return done
         f1, f2, targets = [], [], []
+        if getattr(self, "_json_cache", None) is None:
+            self._json_cache = {}
         for graph_pair in batch:
-            data = self.transfer_to_torch(process_pair(graph_pair), training)
+            data = self.transfer_to_torch(process_pair(graph_pair, self._json_cache), training)
             f1 += [data["features_1"], data["features_2"]]
             f2 += [data["features_2"], data["features_1"]]
             targets += [data["target"], data["target"]]
-        data = self._stack(f1, f2, targets)
+        data = self._stack(f1, f2 if not training else f1[:1], targets)      # a training step reads features_1 only (mirrored)
         if training:
             eng = self._device_trainer()
             dev = eng.device

@@ -127,6 +127,28 @@ class TrainEngine:
                    "sgpr_train_step", self._lib)
         return loss, pred
 
+    def assemble(self, graphs: torch.Tensor, pair_idx: torch.Tensor, seed: int, step: int, want_draws: bool = False):
+        """Device batch assembly + augmentation: graphs [M,15,N] and pair_idx [P,2] int32 on the device -> features_1
+        [2P,15,N] of the mirrored batch (row 2p / 2p+1 = augmented graph a / b of listed pair p).  want_draws also
+        returns the random draws (draws [2P,12], raw jitter normals [2P,N,3]) for the parity tests."""
+        graphs = self._buf(graphs, "graphs")
+        if pair_idx.dtype != torch.int32 or pair_idx.device != self.device or pair_idx.dim() != 2 or pair_idx.shape[1] != 2:
+            raise ValueError("pair_idx must be an int32 [P, 2] tensor on the engine's device")
+        pair_idx = pair_idx.contiguous()
+        M, _, N = graphs.shape
+        P = int(pair_idx.shape[0])
+        if P and (int(pair_idx.min()) < 0 or int(pair_idx.max()) >= M) and want_draws:
+            raise IndexError("pair_idx out of range")
+        out = torch.empty(2 * P, 15, N, dtype=torch.float32, device=self.device)
+        draws = torch.zeros(2 * P, 12, dtype=torch.float32, device=self.device) if want_draws else None
+        jitter = torch.zeros(2 * P, N, 3, dtype=torch.float32, device=self.device) if want_draws else None
+        stream = None if self._emulated else C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self._lib.sgpr_train_assemble(self._h, graphs.data_ptr(), M, N, pair_idx.data_ptr(), P, int(seed), int(step),
+                                                 out.data_ptr(), draws.data_ptr() if want_draws else None,
+                                                 jitter.data_ptr() if want_draws else None, stream),
+                   "sgpr_train_assemble", self._lib)
+        return (out, draws, jitter) if want_draws else out
+
     def step_count(self) -> int:
         return int(self._lib.sgpr_train_step_count(self._h))
 

@@ -34,9 +34,19 @@ def _read_graph(path):
         return json.load(handle)
 
 
-def process_pair(path):
-    """Two graph JSON files -> one pair dict; `distance` is the planar pose distance (utils.py:21-38: pose[3], pose[11])."""
-    first, second = _read_graph(path[0]), _read_graph(path[1])
+def process_pair(path, cache=None):
+    """Two graph JSON files -> one pair dict; `distance` is the planar pose distance (utils.py:21-38: pose[3], pose[11]).
+    `cache` (a dict, optional): parsed files are kept and reused — the reference re-reads both files for every listed
+    pair of every epoch; the returned dict only references the parsed lists, nothing downstream mutates them."""
+    if cache is None:
+        first, second = _read_graph(path[0]), _read_graph(path[1])
+    else:
+        first = cache.get(path[0])
+        if first is None:
+            first = cache[path[0]] = _read_graph(path[0])
+        second = cache.get(path[1])
+        if second is None:
+            second = cache[path[1]] = _read_graph(path[1])
     dx = first["pose"][3] - second["pose"][3]
     dz = first["pose"][11] - second["pose"][11]
     return {"centers_1": first["centers"], "nodes_1": first["nodes"],

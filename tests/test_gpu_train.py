@@ -104,3 +104,20 @@ def test_loud_errors(eng, kitti_state):
     with pytest.raises(RuntimeError):
         fresh.step(f.cpu(), f.cpu(), t.cpu(), 10)
     fresh.close()
+
+
+def test_batch_assembly_matches_host_augmentation(eng, monkeypatch):
+    """sgpr_train_assemble vs the reference-shaped host path fed with the kernel's own random draws."""
+    from tests import assemble_checks as ac
+    ac.check_assemble(eng, "cuda", monkeypatch, M=12, N=64, P=9)
+    ac.check_assemble(eng, "cuda", monkeypatch, M=6, N=100, P=4, seed=99, step=2 ** 33 + 5)
+
+
+def test_batch_assembly_draw_statistics(eng):
+    from sg_pr_b200 import synth
+    from tests import assemble_checks as ac
+    a, b = synth.make_pair_batch(8, 64, 20, seed=2)
+    graphs = torch.cat([a, b]).cuda()
+    pair_idx = torch.randint(0, 16, (4096, 2), dtype=torch.int32).cuda()
+    _, draws, jitter = eng.assemble(graphs, pair_idx, seed=5, step=0, want_draws=True)
+    ac.check_draw_statistics(draws.cpu(), jitter.cpu())

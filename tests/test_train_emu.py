@@ -64,3 +64,10 @@ def test_emulated_errors_are_loud(emu_lib):
     with pytest.raises(_lib.SgprError, match="Adam"):
         eng.set_optimizer(-1.0)
     eng.close()
+
+
+def test_emulated_batch_assembly_matches_host_augmentation(emu_lib, monkeypatch):
+    from tests import assemble_checks as ac
+    eng = TrainEngine(lib=emu_lib)
+    ac.check_assemble(eng, "cpu", monkeypatch, M=8, N=32, P=5)
+    eng.close()

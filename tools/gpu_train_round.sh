@@ -12,3 +12,4 @@ tail -15 gpurun_out/pytest_train.log; cat gpurun_out/train_bench.jsonl; tail -3 
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sgpr_train_edge_fwd -s 1 -c 1 -f -o gpurun_out/prof_train_fwd python tools/train_bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full_fwd.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sgpr_train_edge_bwd -s 1 -c 1 -f -o gpurun_out/prof_train_bwd python tools/train_bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full_bwd.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+timeout 600 python tools/train_e2e_bench.py --graphs 1000 --pairs 2560 --cpu-steps 1 2> gpurun_out/train_e2e.err | grep -E "^\{" > gpurun_out/train_e2e.jsonl; cat gpurun_out/train_e2e.jsonl; tail -3 gpurun_out/train_e2e.err
