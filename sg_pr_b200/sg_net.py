@@ -350,7 +350,7 @@ class SGTrainer(object):
         dev = self._device_trainer().device
         tab = self._dev_graphs
         if tab is None or tab["node_num"] != int(self.args.node_num):
-            tab = self._dev_graphs = {"node_num": int(self.args.node_num), "index": {}, "count": 0,
+            tab = self._dev_graphs = {"node_num": int(self.args.node_num), "index": {}, "count": 0, "pairs": {},
                                       "blocks": torch.empty(1024, 15, int(self.args.node_num), device=dev)}
         fresh = [p for p in dict.fromkeys(paths) if p not in tab["index"]]
         if any(not store.is_static(p) for p in fresh):
@@ -370,11 +370,20 @@ class SGTrainer(object):
     def _process_batch_on_device(self, batch):
         """device_augment: pair indices + targets go up, sgpr_train_assemble builds the augmented mirrored batch in HBM,
         sgpr_train_step trains on it.  Returns None when the batch needs the host path."""
-        rows = self._device_graph_rows([p for pair in batch for p in pair])
-        if rows is None:
-            return None
         store, eng = self._store(), self._device_trainer()
-        targets = np.repeat(np.array([store.target(a, b, self.args.p_thresh) for a, b in batch], dtype=np.float32), 2)
+        cache = self._dev_graphs["pairs"] if self._dev_graphs is not None else {}
+        try:                                    # steady state: every listed pair has been seen (epoch 2 onwards)
+            known = [cache[(a, b)] for a, b in batch]
+        except KeyError:
+            rows = self._device_graph_rows([p for pair in batch for p in pair])
+            if rows is None:
+                return None
+            cache = self._dev_graphs.setdefault("pairs", {})
+            for i, (a, b) in enumerate(batch):
+                cache[(a, b)] = (rows[2 * i], rows[2 * i + 1], store.target(a, b, self.args.p_thresh))
+            known = [cache[(a, b)] for a, b in batch]
+        rows = [r for ia, ib, _ in known for r in (ia, ib)]
+        targets = np.repeat(np.array([t for _, _, t in known], dtype=np.float32), 2)
         idx = torch.tensor(rows, dtype=torch.int32).view(-1, 2).to(eng.device, non_blocking=True)
         tgt = torch.from_numpy(targets).to(eng.device, non_blocking=True)
         f1 = eng.assemble(self._dev_graphs["blocks"], idx, self.augment_seed, eng.step_count())

@@ -145,6 +145,59 @@ def test_training_step_runs_on_device(tree):
     assert not torch.equal(synced["dgcnn_s_conv2.0.weight"].cpu(), state0["dgcnn_s_conv2.0.weight"])
 
 
+def test_fit_runs_and_saves_reference_format_checkpoints(tree):
+    """fit() (sg_net.py:347-384): epochs of device training steps, eval pass, checkpoints loadable by the eval path."""
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SGTrainer
+    root, cfg = tree
+    os.makedirs(f"{root}/lists", exist_ok=True)
+    for seq in ("00", "08"):
+        with open(f"{root}/lists/{seq}.txt", "w") as f:
+            f.write("0.json 3.json\n0.json 250.json\n3.json 250.json\n0.json 0.json\n" * 3)
+    args = sgpr_args().load(cfg)
+    args.K, args.node_num, args.batch_size, args.epochs, args.logdir = 10, 64, 4, 1, f"{root}/fitlogs"
+    trainer = SGTrainer(args, True)
+    trainer.fit()
+    assert trainer._train_engine.step_count() == 3                       # 12 listed pairs / batch 4
+    saved = torch.load(f"{root}/fitlogs/0.pth", map_location="cpu", weights_only=False)
+    assert all(k.startswith("module.") for k in saved) and len(saved) == 50
+    assert int(saved["module.dgcnn_conv_end.1.num_batches_tracked"]) == 6      # two BatchNorm calls per step
+    assert os.path.isfile(f"{root}/fitlogs/0_best.pth")
+    args2 = sgpr_args().load(cfg)
+    args2.K, args2.node_num, args2.model = 10, 64, f"{root}/fitlogs/0.pth"
+    evaluator = SGTrainer(args2, False)                                  # strict load of what fit() wrote
+    evaluator.model.eval()
+    pred, gt = evaluator.eval_batch_pair([[f"{root}/data/0.json", f"{root}/data/250.json"]])
+    assert pred.shape == (1,) and 0.0 <= float(pred[0]) <= 1.0
+
+
+def test_device_augment_training_path(tree):
+    """device_augment: graphs uploaded once, batches assembled + augmented by sgpr_train_assemble, same training step."""
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SGTrainer, _DeviceAdam
+    root, cfg = tree
+    os.makedirs(f"{root}/lists", exist_ok=True)
+    for seq in ("00", "08"):
+        with open(f"{root}/lists/{seq}.txt", "w") as f:
+            f.write("0.json 3.json\n0.json 250.json\n3.json 250.json\n0.json 0.json\n")
+    args = sgpr_args().load(cfg)
+    args.K, args.node_num, args.batch_size, args.device_augment, args.augment_seed = 10, 64, 4, True, 11
+    trainer = SGTrainer(args, True)
+    trainer.optimizer = _DeviceAdam(trainer)
+    trainer.model.train()
+    loss0, pred, gt = trainer.process_batch(trainer.training_graphs, True)
+    assert pred.shape == (8,) and gt.tolist() == [1, 1, 0, 0, 0, 0, 1, 1] and np.isfinite(loss0)
+    assert trainer._dev_graphs["count"] == 3 and len(trainer._dev_graphs["pairs"]) == 4       # 3 files, uploaded once
+    launches = trainer._train_engine.launch_count()
+    for _ in range(8):
+        loss, _, _ = trainer.process_batch(trainer.training_graphs, True)
+    assert loss < loss0
+    assert trainer._train_engine.launch_count() == launches + 8 * 14                          # assemble + 13 per step
+    assert trainer._dev_graphs["count"] == 3
+    model_loss, f1 = trainer.score("eval")
+    assert np.isfinite(model_loss) and 0.0 <= f1 <= 1.0
+
+
 @pytest.mark.skipif(not os.path.isfile("/root/reference/eval_pair.py"), reason="reference tree not on this box")
 def test_unmodified_reference_script(tree):
     """The reference's own eval_pair.py, unmodified, with our modules first on sys.path."""

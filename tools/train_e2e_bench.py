@@ -63,8 +63,11 @@ def make_trainer(**kw):
     return t
 
 
-def run(label, trainer, fn):
+def run(label, trainer, fn, warm=False):
     fn(batches[0])                                     # warm-up: context, workspace, first upload
+    if warm:                                           # epoch 2 onwards: every file parsed / every graph uploaded already
+        for b in batches:
+            fn(b)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     losses = [fn(b)[0] for b in batches]
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
@@ -103,10 +106,12 @@ def reference_shaped(batch):                           # host side exactly as sg
 run("reference-shaped host prep (re-read JSON, python one-hot, both sides) + device step", t1, reference_shaped)
 
 t2 = make_trainer()
-run("default: cached parse + vectorised one-hot + mirrored device step (reference RNG order)", t2, lambda b: t2.process_batch(b, True))
+run("default, first epoch: cached parse + vectorised one-hot + mirrored device step (reference RNG order)", t2, lambda b: t2.process_batch(b, True))
+run("default, later epochs", t2, lambda b: t2.process_batch(b, True), warm=True)
 
 t3 = make_trainer(device_augment=True, augment_seed=1)
-run("device_augment: sgpr_train_assemble + mirrored device step", t3, lambda b: t3.process_batch(b, True))
+run("device_augment, first epoch (parses + uploads every graph once): sgpr_train_assemble + mirrored device step", t3, lambda b: t3.process_batch(b, True))
+run("device_augment, later epochs", t3, lambda b: t3.process_batch(b, True), warm=True)
 
 if args.cpu_steps:
     from oracle import sgpr_oracle_train as ort
