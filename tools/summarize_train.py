@@ -46,5 +46,5 @@ for which in ("fwd", "bwd"):
     lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "12"], capture_output=True, text=True).stdout
     k["hot_lines"] = lines.strip().splitlines()
     summary[f"edge_{which}_layer2"] = k
-json.dump(summary, open(os.path.join(prof, f"{tag}_train_ncu_summary.json"), "w"), indent=1)
+json.dump(summary, open(os.path.join(prof, f"{tag}_train_summary.json"), "w"), indent=1)
 print(json.dumps(summary["kernel_us_per_step"], indent=1), summary["sum_us_per_step"])

@@ -57,6 +57,7 @@ def make_trainer(**kw):
     a.graph_pairs_dir, a.pair_list_dir = f"{root}/seq", f"{root}/lists"
     for k, v in kw.items():
         setattr(a, k, v)
+    torch.manual_seed(0)                               # every arm starts from the same random initialisation
     with contextlib.redirect_stdout(io.StringIO()):
         t = SGTrainer(a, True)
     t.optimizer = _DeviceAdam(t)
