@@ -269,12 +269,13 @@ def main():
         achieved = BATCH * ALG_BYTES_PER_PAIR / kernel_s / 1e9
         traffic, traffic_src = None, None       # dram__bytes_read+write per launch from the committed `ncu --set full` summary
         try:
-            import glob
-            latest = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), key=os.path.getmtime)[-1]
+            # profiles/current.json names the ncu summary captured from the build that is checked in
+            with open(os.path.join(ROOT, "profiles", "current.json")) as f:
+                latest = os.path.join(ROOT, "profiles", json.load(f)["embed_ncu_summary"])
             with open(latest) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
             traffic_src = os.path.relpath(latest, ROOT)
-        except (IndexError, OSError, ValueError):
+        except (KeyError, OSError, ValueError):
             pass
         line = {
             "metric": METRIC, "value": value, "unit": "graph-pairs/s", "n_gpus": world, "steps": args.steps,
