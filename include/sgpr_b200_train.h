@@ -75,6 +75,25 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
                     float* loss_dev, float* pred_dev, int flags, void* stream);
 
 /*
+ * The same step split at the loss, for callers that drive autograd themselves (model(data) in train mode, their own
+ * loss, loss.backward(), their own optimiser — the general use of SG.forward, sg_net.py:112-138):
+ *   sgpr_train_forward : train-mode forward only.  pred_dev [B]; att1_dev / att2_dev [B][N] attention scores or NULL
+ *                        (att2 is not written for a mirrored batch: it is att1 with adjacent rows swapped).
+ *                        With SGPR_TRAIN_APPLY the BatchNorm running statistics are updated, as nn.BatchNorm does in
+ *                        forward; parameters are never touched.  Everything the backward needs stays in the context.
+ *   sgpr_train_backward: backward of the LAST sgpr_train_forward from dpred_dev [B] = d loss / d prediction; the flat
+ *                        gradient vector (sgpr_train_param_count floats) is left readable through sgpr_train_get_grads
+ *                        and, if grads_dev != NULL, copied there (device pointer).
+ *   sgpr_train_set_state_dev / _get_state_dev : the flat state vector from / to DEVICE memory (sgpr_train_state_count
+ *                        floats), for modules whose parameters already live on the GPU.
+ */
+int sgpr_train_forward(sgpr_train* t, const float* f1_dev, const float* f2_dev, int B, int N, int k, float* pred_dev,
+                       float* att1_dev, float* att2_dev, int flags, void* stream);
+int sgpr_train_backward(sgpr_train* t, const float* dpred_dev, float* grads_dev, void* stream);
+int sgpr_train_set_state_dev(sgpr_train* t, const float* state_dev, void* stream);
+int sgpr_train_get_state_dev(sgpr_train* t, float* state_dev, void* stream);
+
+/*
  * Training-batch assembly + augmentation on the device, for graphs already resident in HBM.  Replaces the host loop of
  * process_batch (sg_net.py:316-331) with transfer_to_torch's training branch (sg_net.py:286-295) and the augmentations
  * of utils.py:91-178 (reference defaults; applied to all node_num rows, zero pads included; one x-flip decision per

@@ -63,6 +63,11 @@ TRAIN_SYMBOLS = {
     "sgpr_train_set_optimizer": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
     "sgpr_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "sgpr_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p]),
+    "sgpr_train_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sgpr_train_set_state_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sgpr_train_get_state_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgpr_train_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgpr_train_get_grads": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -91,6 +91,17 @@ void build_layout() {
 
 }  // namespace
 
+struct Plan {
+    bool valid = false, backward_ready = false;
+    TrainWs W{};
+    int npl = 2, grid4 = 0, grid2 = 0, grid_att = 0, head_grid = 0;
+    size_t fwd_smem = 0, bwd_smem = 0, end_fwd_smem = 0, end_bwd_smem = 0;
+    float* part_head = nullptr;
+    float* part_att = nullptr;
+    float* part_end = nullptr;
+    float* part_conv[6] = {};
+};
+
 struct sgpr_train {
     int device = 0;
     int sm_count = 0;
@@ -108,6 +119,7 @@ struct sgpr_train {
     long long launches = 0;
     TrainWs last{};                // pointers of the last step (debug taps)
     bool has_last = false;
+    Plan plan;
 };
 
 namespace {
@@ -231,25 +243,28 @@ int sgpr_train_set_optimizer(sgpr_train* t, float lr, float weight_decay, float 
     return SGPR_OK;
 }
 
-int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, const float* target_dev, int B, int N, int k,
-                    float* loss_dev, float* pred_dev, int flags, void* stream) {
-    if (!t) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: NULL context");
-    if (!t->has_state) return sgpr_fail(SGPR_E_NOWEIGHTS, "sgpr_train_step: call sgpr_train_set_state first");
-    if (B < 1) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: batch %d < 1", B);
-    if (N < 2 || N > SGPR_MAX_NODES) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: node_num %d outside [2,%d]", N, SGPR_MAX_NODES);
+}  // extern "C"
+
+namespace {
+
+// Everything one batch needs: workspace carve-out, grids, partial buffers.  Kept in the context after a forward so that a
+// separate backward call (sgpr_train_backward) finds the same tensors.
+int make_plan(sgpr_train* t, const float* f1_dev, const float* f2_dev, const float* target_dev, int B, int N, int k,
+              int mirrored, const char* who) {
+    if (!t->has_state) return sgpr_fail(SGPR_E_NOWEIGHTS, "%s: call sgpr_train_set_state first", who);
+    if (B < 1) return sgpr_fail(SGPR_E_INVALID, "%s: batch %d < 1", who, B);
+    if (N < 2 || N > SGPR_MAX_NODES) return sgpr_fail(SGPR_E_INVALID, "%s: node_num %d outside [2,%d]", who, N, SGPR_MAX_NODES);
     if (k < 1 || k > N)
-        return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: k=%d must satisfy 1 <= k <= node_num=%d (topk raises in the reference, dgcnn.py:19)", k, N);
-    const int apply = (flags & SGPR_TRAIN_APPLY) ? 1 : 0, mirrored = (flags & SGPR_TRAIN_MIRRORED) ? 1 : 0;
-    if (!f1_dev || (!f2_dev && !mirrored) || !target_dev) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: NULL feature/target pointer");
-    if (mirrored && (B & 1)) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: a mirrored batch holds every pair in both orders, B=%d is odd", B);
-    Guard guard(t->device);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+        return sgpr_fail(SGPR_E_INVALID, "%s: k=%d must satisfy 1 <= k <= node_num=%d (topk raises in the reference, dgcnn.py:19)", who, k, N);
+    if (!f1_dev || (!f2_dev && !mirrored)) return sgpr_fail(SGPR_E_INVALID, "%s: NULL feature pointer", who);
+    if (mirrored && (B & 1)) return sgpr_fail(SGPR_E_INVALID, "%s: a mirrored batch holds every pair in both orders, B=%d is odd", who, B);
     const int G = B, S = mirrored ? 1 : 2, SG = S * B;
-    const int npl = (N <= 32) ? 1 : (N <= 64) ? 2 : 4;
-    const int nmax = 32 * npl;
+    Plan& P = t->plan;
+    P.valid = false;
+    P.npl = (N <= 32) ? 1 : (N <= 64) ? 2 : 4;
+    const int nmax = 32 * P.npl;
     const int KS = (k + 3) & ~3;
 
-    // ---- workspace ----
     size_t need = 0;
     for (int L = 0; L < 6; ++L) {
         const size_t per = static_cast<size_t>(SG) * N * layer_cout(L);
@@ -265,17 +280,17 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
         TRY_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->d_ws), want));
         t->ws_cap = want;
     }
-    const int per_sm = (npl <= 2) ? 2 : 1;
+    const int per_sm = (P.npl <= 2) ? 2 : 1;
     const int cap = t->sm_count * per_sm;
-    int grid4 = 2 * S * G < cap ? 2 * S * G : (cap / (2 * S)) * (2 * S);        // (branch, side) x graphs
-    if (grid4 < 2 * S) grid4 = 2 * S;
-    int grid2 = S * G < cap ? S * G : (cap / S) * S;                            // side x graphs
-    if (grid2 < S) grid2 = S;
-    int grid_att = SG < 4 * t->sm_count ? SG : 4 * t->sm_count;
-    const int head_grid = G < kMaxHeadGrid ? G : kMaxHeadGrid;
-    const int nb = grid4 / 2;                                // partial rows per branch in the EdgeConv backward
-    size_t part_need = static_cast<size_t>(head_grid) * kHeadFloats + static_cast<size_t>(grid2) * 1024 +
-                       static_cast<size_t>(grid2) * 2048;
+    P.grid4 = 2 * S * G < cap ? 2 * S * G : (cap / (2 * S)) * (2 * S);        // (branch, side) x graphs
+    if (P.grid4 < 2 * S) P.grid4 = 2 * S;
+    P.grid2 = S * G < cap ? S * G : (cap / S) * S;                            // side x graphs
+    if (P.grid2 < S) P.grid2 = S;
+    P.grid_att = SG < 4 * t->sm_count ? SG : 4 * t->sm_count;
+    P.head_grid = G < kMaxHeadGrid ? G : kMaxHeadGrid;
+    const int nb = P.grid4 / 2;                                // partial rows per branch in the EdgeConv backward
+    size_t part_need = static_cast<size_t>(P.head_grid) * kHeadFloats + static_cast<size_t>(P.grid2) * 1024 +
+                       static_cast<size_t>(P.grid2) * 2048;
     for (int L = 0; L < 6; ++L) part_need += static_cast<size_t>(nb) * conv_size(L);
     if (part_need > t->part_cap) {
         if (t->d_part) cudaFree(t->d_part);
@@ -286,7 +301,7 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
 
     TrainWs W{};
     W.G = G; W.S = S; W.mirrored = mirrored; W.N = N; W.k = k; W.KS = KS; W.eps = 1e-5f;
-    W.f[0] = f1_dev; W.f[1] = f2_dev; W.target = target_dev;
+    W.f[0] = f1_dev; W.f[1] = f2_dev; W.target = target_dev; W.dpred = nullptr;
     W.state = t->d_state; W.wpk = t->d_wpk;
     unsigned char* p = t->d_ws;
     for (int L = 0; L < 6; ++L) {
@@ -314,64 +329,168 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
     W.grads = t->d_grads;
     W.adam_m = t->d_adam;
     W.adam_v = t->d_adam + P_TOTAL;
-    W.head_grid = head_grid;
+    W.head_grid = P.head_grid;
 
     // gradient partials and the segment table the optimiser sums them by
     float* pp = t->d_part;
-    float* part_head = pp; pp += static_cast<size_t>(head_grid) * kHeadFloats;
-    float* part_att = pp;  pp += static_cast<size_t>(grid2) * 1024;
-    float* part_end = pp;  pp += static_cast<size_t>(grid2) * 2048;
-    float* part_conv[6];
-    for (int L = 0; L < 6; ++L) { part_conv[L] = pp; pp += static_cast<size_t>(nb) * conv_size(L); }
+    P.part_head = pp; pp += static_cast<size_t>(P.head_grid) * kHeadFloats;
+    P.part_att = pp;  pp += static_cast<size_t>(P.grid2) * 1024;
+    P.part_end = pp;  pp += static_cast<size_t>(P.grid2) * 2048;
+    for (int L = 0; L < 6; ++L) { P.part_conv[L] = pp; pp += static_cast<size_t>(nb) * conv_size(L); }
     int ns = 0;
-    for (int L = 0; L < 6; ++L) W.seg[ns++] = Segment{conv_off(L), conv_size(L), nb, conv_size(L), part_conv[L]};
-    W.seg[ns++] = Segment{P_ENDW, 2048, grid2, 2048, part_end};
-    W.seg[ns++] = Segment{P_ATT, 1024, grid2, 1024, part_att};
-    W.seg[ns++] = Segment{P_NTNW, kHeadFloats, head_grid, kHeadFloats, part_head};
+    for (int L = 0; L < 6; ++L) W.seg[ns++] = Segment{conv_off(L), conv_size(L), nb, conv_size(L), P.part_conv[L]};
+    W.seg[ns++] = Segment{P_ENDW, 2048, P.grid2, 2048, P.part_end};
+    W.seg[ns++] = Segment{P_ATT, 1024, P.grid2, 1024, P.part_att};
+    W.seg[ns++] = Segment{P_NTNW, kHeadFloats, P.head_grid, kHeadFloats, P.part_head};
     W.nseg = ns;
+    P.W = W;
+    P.fwd_smem = fwd_layout(nmax, KS).total;
+    P.bwd_smem = bwd_layout(nmax, KS).total;
+    P.end_fwd_smem = (64 * 32 + 2 * static_cast<size_t>(nmax) * XS + 256) * 4 + kWarps * 128 * 8;
+    P.end_bwd_smem = (32 * 64 + static_cast<size_t>(nmax) * XS + static_cast<size_t>(nmax) * 36 + 256 + 192) * 4 + 4 * 128 * 8;
+    P.valid = true;
+    return SGPR_OK;
+}
 
-    TRY_CUDA(cudaMemsetAsync(t->d_sums, 0, kSumDoubles * sizeof(double), st));
-
-    const FwdSmem FS = fwd_layout(nmax, KS);
-    const BwdSmem BS = bwd_layout(nmax, KS);
-    const size_t end_fwd_smem = (64 * 32 + 2 * static_cast<size_t>(nmax) * XS + 256) * 4 + kWarps * 128 * 8;
-    const size_t end_bwd_smem = (32 * 64 + static_cast<size_t>(nmax) * XS + static_cast<size_t>(nmax) * 36 + 256 + 192) * 4 + 4 * 128 * 8;
-
-#define BY_NPL(KERN, GRID, SMEM, ...)                                                                  \
-    do {                                                                                               \
-        if (npl == 1) { SGPR_LAUNCH(KERN<1>, GRID, kThreads, SMEM, st, __VA_ARGS__); }                 \
-        else if (npl == 2) { SGPR_LAUNCH(KERN<2>, GRID, kThreads, SMEM, st, __VA_ARGS__); }            \
-        else { SGPR_LAUNCH(KERN<4>, GRID, kThreads, SMEM, st, __VA_ARGS__); }                          \
-        t->launches += 1;                                                                              \
+#define BY_NPL(KERN, GRID, SMEM, ...)                                                                    \
+    do {                                                                                                 \
+        if (P.npl == 1) { SGPR_LAUNCH(KERN<1>, GRID, kThreads, SMEM, st, __VA_ARGS__); }                 \
+        else if (P.npl == 2) { SGPR_LAUNCH(KERN<2>, GRID, kThreads, SMEM, st, __VA_ARGS__); }            \
+        else { SGPR_LAUNCH(KERN<4>, GRID, kThreads, SMEM, st, __VA_ARGS__); }                            \
+        t->launches += 1;                                                                                \
     } while (0)
 
+// pack | EdgeConv fwd x3 | conv_end fwd | attention fwd  (statistics zeroed first)
+int launch_forward(sgpr_train* t, cudaStream_t st) {
+    Plan& P = t->plan;
+    const TrainWs& W = P.W;
+    TRY_CUDA(cudaMemsetAsync(t->d_sums, 0, kSumDoubles / 2 * sizeof(double), st));
     SGPR_LAUNCH(sgpr_train_pack_kernel, 32, kThreads, 0, st, W);
     t->launches += 1;
-    for (int l = 0; l < 3; ++l) BY_NPL(sgpr_train_edge_fwd, grid4, FS.total, W, l);
-    BY_NPL(sgpr_train_end_fwd, grid2, end_fwd_smem, W);
-    SGPR_LAUNCH(sgpr_train_att_fwd, grid_att, kThreads, 0, st, W);
-    SGPR_LAUNCH(sgpr_train_head_kernel, head_grid, kThreads, 0, st, W, part_head);
-    SGPR_LAUNCH(sgpr_train_att_bwd, grid2, kThreads, 0, st, W, part_att);
-    t->launches += 3;
-    BY_NPL(sgpr_train_end_bwd, grid2, end_bwd_smem, W, part_end);
-    for (int l = 2; l >= 0; --l) BY_NPL(sgpr_train_edge_bwd, grid4, BS.total, W, l, part_conv[l], part_conv[3 + l]);
+    for (int l = 0; l < 3; ++l) BY_NPL(sgpr_train_edge_fwd, P.grid4, P.fwd_smem, W, l);
+    BY_NPL(sgpr_train_end_fwd, P.grid2, P.end_fwd_smem, W);
+    SGPR_LAUNCH(sgpr_train_att_fwd, P.grid_att, kThreads, 0, st, W);
+    t->launches += 1;
+    return SGPR_OK;
+}
 
+// head (mode: kHeadFused / kHeadForward / kHeadBackward)
+void launch_head(sgpr_train* t, cudaStream_t st, int mode) {
+    Plan& P = t->plan;
+    SGPR_LAUNCH(sgpr_train_head_kernel, P.head_grid, kThreads, 0, st, P.W, P.part_head, mode);
+    t->launches += 1;
+}
+
+// attention bwd | conv_end bwd | EdgeConv bwd x3   (dbeta / dgamma sums zeroed first)
+int launch_backward(sgpr_train* t, cudaStream_t st) {
+    Plan& P = t->plan;
+    const TrainWs& W = P.W;
+    SGPR_LAUNCH(sgpr_train_att_bwd, P.grid2, kThreads, 0, st, W, P.part_att);
+    t->launches += 1;
+    BY_NPL(sgpr_train_end_bwd, P.grid2, P.end_bwd_smem, W, P.part_end);
+    for (int l = 2; l >= 0; --l) BY_NPL(sgpr_train_edge_bwd, P.grid4, P.bwd_smem, W, l, P.part_conv[l], P.part_conv[3 + l]);
+    return SGPR_OK;
+}
+#undef BY_NPL
+
+void launch_adam(sgpr_train* t, cudaStream_t st, int apply) {
     AdamArgs A{};
     A.lr = t->lr; A.wd = t->wd; A.b1 = t->b1; A.b2 = t->b2; A.eps = t->eps;
     const long long step = t->steps + 1;
     A.bc1 = static_cast<float>(1.0 - std::pow(static_cast<double>(t->b1), static_cast<double>(step)));
     A.bc2_sqrt = static_cast<float>(std::sqrt(1.0 - std::pow(static_cast<double>(t->b2), static_cast<double>(step))));
     A.apply = apply;
-    SGPR_LAUNCH(sgpr_train_adam_kernel, (STATE_TOTAL + 31) / 32, kThreads, 0, st, W, A);
+    SGPR_LAUNCH(sgpr_train_adam_kernel, (STATE_TOTAL + 31) / 32, kThreads, 0, st, t->plan.W, A);
     t->launches += 1;
-    if (apply) t->steps = step;
+    if (apply == kApplyAll) t->steps = step;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, const float* target_dev, int B, int N, int k,
+                    float* loss_dev, float* pred_dev, int flags, void* stream) {
+    if (!t) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: NULL context");
+    const int apply = (flags & SGPR_TRAIN_APPLY) ? 1 : 0, mirrored = (flags & SGPR_TRAIN_MIRRORED) ? 1 : 0;
+    if (!target_dev) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_step: NULL target pointer");
+    Guard guard(t->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = make_plan(t, f1_dev, f2_dev, target_dev, B, N, k, mirrored, "sgpr_train_step");
+    if (rc) return rc;
+    TRY_CUDA(cudaMemsetAsync(t->d_sums + kSumDoubles / 2, 0, kSumDoubles / 2 * sizeof(double), st));
+    rc = launch_forward(t, st);
+    if (rc) return rc;
+    launch_head(t, st, kHeadFused);
+    rc = launch_backward(t, st);
+    if (rc) return rc;
+    launch_adam(t, st, apply ? kApplyAll : kApplyNone);
+    const TrainWs& W = t->plan.W;
     if (loss_dev) TRY_CUDA(cudaMemcpyAsync(loss_dev, W.loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (pred_dev) TRY_CUDA(cudaMemcpyAsync(pred_dev, W.pred, static_cast<size_t>(G) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (pred_dev) TRY_CUDA(cudaMemcpyAsync(pred_dev, W.pred, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRY_CUDA(cudaGetLastError());
     t->last = W;
     t->has_last = true;
+    t->plan.backward_ready = false;
     return SGPR_OK;
-#undef BY_NPL
+}
+
+int sgpr_train_forward(sgpr_train* t, const float* f1_dev, const float* f2_dev, int B, int N, int k, float* pred_dev,
+                       float* att1_dev, float* att2_dev, int flags, void* stream) {
+    if (!t) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_forward: NULL context");
+    const int apply = (flags & SGPR_TRAIN_APPLY) ? 1 : 0, mirrored = (flags & SGPR_TRAIN_MIRRORED) ? 1 : 0;
+    Guard guard(t->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = make_plan(t, f1_dev, f2_dev, nullptr, B, N, k, mirrored, "sgpr_train_forward");
+    if (rc) return rc;
+    rc = launch_forward(t, st);
+    if (rc) return rc;
+    launch_head(t, st, kHeadForward);
+    if (apply) launch_adam(t, st, kApplyRunning);             // nn.BatchNorm updates its running statistics in forward
+    const TrainWs& W = t->plan.W;
+    if (pred_dev) TRY_CUDA(cudaMemcpyAsync(pred_dev, W.pred, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const size_t att_bytes = static_cast<size_t>(B) * N * sizeof(float);
+    if (att1_dev) TRY_CUDA(cudaMemcpyAsync(att1_dev, W.att, att_bytes, cudaMemcpyDeviceToDevice, st));
+    if (att2_dev && !mirrored) TRY_CUDA(cudaMemcpyAsync(att2_dev, W.att + static_cast<size_t>(B) * N, att_bytes, cudaMemcpyDeviceToDevice, st));
+    TRY_CUDA(cudaGetLastError());
+    t->last = W;
+    t->has_last = true;
+    t->plan.backward_ready = true;
+    return SGPR_OK;
+}
+
+int sgpr_train_backward(sgpr_train* t, const float* dpred_dev, float* grads_dev, void* stream) {
+    if (!t || !dpred_dev) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_backward: NULL argument");
+    if (!t->plan.valid || !t->plan.backward_ready)
+        return sgpr_fail(SGPR_E_INVALID, "sgpr_train_backward: no sgpr_train_forward to differentiate (or another call used the workspace since)");
+    Guard guard(t->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    t->plan.W.dpred = dpred_dev;
+    TRY_CUDA(cudaMemsetAsync(t->d_sums + kSumDoubles / 2, 0, kSumDoubles / 2 * sizeof(double), st));
+    launch_head(t, st, kHeadBackward);
+    int rc = launch_backward(t, st);
+    if (rc) return rc;
+    launch_adam(t, st, kApplyNone);                            // sums the partials into the flat gradient vector
+    if (grads_dev) TRY_CUDA(cudaMemcpyAsync(grads_dev, t->d_grads, P_TOTAL * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRY_CUDA(cudaGetLastError());
+    t->last = t->plan.W;
+    return SGPR_OK;
+}
+
+int sgpr_train_set_state_dev(sgpr_train* t, const float* state_dev, void* stream) {
+    if (!t || !state_dev) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_set_state_dev: NULL argument");
+    Guard guard(t->device);
+    TRY_CUDA(cudaMemcpyAsync(t->d_state, state_dev, STATE_TOTAL * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    t->has_state = true;
+    return SGPR_OK;
+}
+
+int sgpr_train_get_state_dev(sgpr_train* t, float* state_dev, void* stream) {
+    if (!t || !state_dev) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_get_state_dev: NULL argument");
+    if (!t->has_state) return sgpr_fail(SGPR_E_NOWEIGHTS, "sgpr_train_get_state_dev: no state has been set");
+    Guard guard(t->device);
+    TRY_CUDA(cudaMemcpyAsync(state_dev, t->d_state, STATE_TOTAL * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return SGPR_OK;
 }
 
 int sgpr_train_assemble(sgpr_train* t, const float* graphs_dev, int M, int N, const int32_t* pair_idx_dev, int P,

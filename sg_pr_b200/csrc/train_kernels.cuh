@@ -72,7 +72,14 @@ constexpr int WT_S2 = WPK_TOTAL, WT_S3 = WT_S2 + 2 * 64 * 64, WT_F2 = WT_S3 + 2 
               WPK_ALL = WT_F3 + 2 * 32 * 64;
 __host__ __device__ inline int wt_off(int L) { return L == 1 ? WT_S2 : (L == 2 ? WT_S3 : (L == 4 ? WT_F2 : WT_F3)); }
 
-constexpr float kMomentum = 0.1f;           // nn.BatchNorm default (sg_net.py:52)
+constexpr float kMomentum = 0.1f;
+// head kernel modes / optimiser kernel modes
+constexpr int kHeadFused = 0;       // forward + mean BCE + backward (sgpr_train_step)
+constexpr int kHeadForward = 1;     // predictions only (sgpr_train_forward)
+constexpr int kHeadBackward = 2;    // forward recomputed, backward from T.dpred (sgpr_train_backward)
+constexpr int kApplyNone = 0;       // gradients only
+constexpr int kApplyAll = 1;        // Adam update + running statistics
+constexpr int kApplyRunning = 2;    // running statistics only (a train-mode forward without an optimiser step)           // nn.BatchNorm default (sg_net.py:52)
 
 // layer index L: 0-2 xyz EdgeConv 1-3, 3-5 sem EdgeConv 1-3, 6 conv_end
 __host__ __device__ inline int layer_cin(int L) { return L == 0 ? 3 : (L == 3 ? 12 : 64); }
@@ -112,7 +119,8 @@ struct TrainWs {
     int N, k, KS;
     float eps;
     const float* f[2];      // features_1 / features_2   [G][15][N]
-    const float* target;    // [G]
+    const float* target;    // [G]  (fused step)
+    const float* dpred;     // [G]  d loss / d prediction handed in by the caller's autograd (sgpr_train_backward)
     float* state;           // [STATE_TOTAL] parameters | running statistics
     float* wpk;             // [WPK_TOTAL]
     // per EdgeConv layer L = 0..5, every tensor [2*G][N][cout]  (side-major: sg = side*G + g)
@@ -586,7 +594,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_att_fwd(const TrainWs T) 
 // Pair head forward (layers_batch.py:70-83, sg_net.py:131-136), mean BCE (sg_net.py:335) and the head's backward.
 // Persistent CTAs; parameter gradients in registers, written as one partial row of kHeadFloats per CTA.
 // =====================================================================================================================
-__global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs T, float* __restrict__ part) {
+__global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs T, float* __restrict__ part, int mode) {
     __shared__ float e12[64];              // e1 | e2 (the V-block input cat(e1, e2), layers_batch.py:80)
     __shared__ float sP[512], sQ[512];
     __shared__ float sS[16], sNt[16], sHpre[16], sH[16], sDh[16], sDs[16];
@@ -651,14 +659,19 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs
             z = warp_sum(z);
             if (lane == 0) {
                 const float pr = sigmoidf_acc(__fadd_rn(z, b2[0]));
-                const float tg = T.target[p];
                 T.pred[p] = pr;
-                // torch.nn.functional.binary_cross_entropy clamps both logs at -100
-                loss += -(tg * fmaxf(logf(pr), -100.0f) + (1.0f - tg) * fmaxf(logf(1.0f - pr), -100.0f));
-                sDz = (pr - tg) / static_cast<float>(G);
+                if (mode == kHeadFused) {
+                    const float tg = T.target[p];
+                    // torch.nn.functional.binary_cross_entropy clamps both logs at -100
+                    loss += -(tg * fmaxf(logf(pr), -100.0f) + (1.0f - tg) * fmaxf(logf(1.0f - pr), -100.0f));
+                    sDz = (pr - tg) / static_cast<float>(G);           // d mean-BCE / d (pre-sigmoid score)
+                } else if (mode == kHeadBackward) {
+                    sDz = T.dpred[p] * pr * (1.0f - pr);               // through the sigmoid (sg_net.py:136)
+                }
             }
         }
         __syncthreads();
+        if (mode == kHeadForward) continue;                            // uniform: every thread of the CTA skips the backward
         const float dz = sDz;
         if (tid < 16) sDh[tid] = sHpre[tid] > 0.0f ? dz * w2[tid] : 0.0f;
         __syncthreads();
@@ -705,6 +718,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs
         }
         __syncthreads();
     }
+    if (mode == kHeadForward) return;
     float* row = part + static_cast<size_t>(blockIdx.x) * kHeadFloats;
 #pragma unroll
     for (int m = 0; m < 64; ++m) row[tid + 256 * m] = gW[m];
@@ -1256,7 +1270,7 @@ struct AdamArgs {
     float lr, wd, b1, b2, eps;
     float bc1;          // 1 - b1^t
     float bc2_sqrt;     // sqrt(1 - b2^t)
-    int apply;          // 0: gradients only (no parameter, moment or running-statistics update)
+    int apply;          // kApplyNone / kApplyAll / kApplyRunning
 };
 
 // One block per 32 consecutive state elements: lane = element, the 8 warps split the partial rows (j = warp, warp + 8,
@@ -1267,7 +1281,8 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
     const int e = blockIdx.x * 32 + lane;
     const bool is_bn = e >= P_BN && e < P_BN + kBnFloats;
     float g = 0.0f;
-    if (e < P_TOTAL && !is_bn) {
+    if (A.apply == kApplyRunning && blockIdx.x * 32 + 31 < P_TOTAL) return;      // only the running-statistics blocks work
+    if (e < P_TOTAL && !is_bn && A.apply != kApplyRunning) {
         for (int s = 0; s < T.nseg; ++s) {
             const Segment& sg = T.seg[s];
             if (e >= sg.off && e < sg.off + sg.size) {
@@ -1281,12 +1296,13 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
     sPart[warp][lane] = g;
     __syncthreads();
     if (warp != 0) return;
-    if (blockIdx.x == 0 && lane == 0) {
+    if (blockIdx.x == 0 && lane == 0 && A.apply != kApplyRunning) {
         float s = 0.0f;
         for (int i = 0; i < T.head_grid; ++i) s += T.losspart[i];
         T.loss[0] = s / static_cast<float>(T.G);
     }
     if (e < P_TOTAL) {
+        if (A.apply == kApplyRunning) return;
         if (is_bn) {
             int L = 6;
             while (bn_off(L) > e - P_BN) --L;
@@ -1301,7 +1317,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
             for (int w = 0; w < kWarps; ++w) g += sPart[w][lane];
         }
         T.grads[e] = g;
-        if (A.apply) {
+        if (A.apply == kApplyAll) {
             const float p = T.state[e];
             g = fmaf(A.wd, p, g);
             const float m = A.b1 * T.adam_m[e] + (1.0f - A.b1) * g;
@@ -1311,7 +1327,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
             const float denom = sqrtf(v) / A.bc2_sqrt + A.eps;
             T.state[e] = p - (A.lr / A.bc1) * (m / denom);
         }
-    } else if (e < STATE_TOTAL && A.apply) {
+    } else if (e < STATE_TOTAL && A.apply != kApplyNone) {
         int L = 6;
         const int r0 = e - R_OFF;
         while (bn_off(L) > r0) --L;

@@ -7,9 +7,11 @@ device tensors, like the reference (sg_net.py:112-138).  In eval mode the whole 
 fused sm_100a kernel (csrc/embed_kernel.cuh) through `sg_pr_b200.engine.Engine`; there is no CPU or eager-PyTorch
 fallback for it — without the built library or without a CUDA device the call raises.
 
-Train mode (`fit`, BASELINE config 3) needs batch-statistics BatchNorm and a backward pass, which are a "next" row
-of the scope table: it runs the same math as differentiable stock PyTorch ops on the device
-(`SG._forward_autograd`).  It is never used for, or counted in, the measured eval hot path.
+Train mode (BASELINE config 3) runs in the same library (csrc/train_kernels.cuh, include/
+sgpr_b200_train.h): `SGTrainer.process_batch(batch, training=True)` is one fused optimiser step per call
+(`sgpr_train_step`), and `SG.forward(data)` on a module in train mode is an autograd node whose forward and backward
+are `sgpr_train_forward` / `sgpr_train_backward`, so a caller's own `loss.backward()` + torch optimiser work unchanged.
+The path as stock PyTorch ops lives in `torch_baseline.py` for benchmarks and tests only.
 """
 import os
 import random
@@ -20,7 +22,6 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import dgcnn
 from . import utils as _utils
 from .graph_store import GraphStore
 from .layers_batch import AttentionModule, TenorNetworkModule
@@ -58,6 +59,44 @@ def _edge_block(cin, cout):
     """Conv2d(1x1, no bias) + BatchNorm2d + LeakyReLU(0.2): the EdgeConv MLP of sg_net.py:50-73."""
     return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=1, bias=False), nn.BatchNorm2d(cout),
                          nn.LeakyReLU(negative_slope=0.2))
+
+
+class _TrainForward(torch.autograd.Function):
+    """Train-mode SG.forward as one autograd node: forward = sgpr_train_forward (batch-statistics BatchNorm, running
+    statistics updated), backward = sgpr_train_backward.  The parameters are inputs so that `loss.backward()` leaves
+    their `.grad` exactly where a torch optimiser expects it."""
+
+    @staticmethod
+    def forward(ctx, module, f1, f2, *params):
+        eng = module._train_engine_for_autograd()
+        names = [n for n, _, _ in eng.layout]
+        sd = module.state_dict(keep_vars=True)
+        flat = torch.cat([sd[n].detach().reshape(-1).to(torch.float32) for n in names])
+        eng.set_state_flat(flat)
+        pred, att1, att2 = eng.forward(f1, f2, int(module.args.K), update_running=True)
+        new = eng.get_state_flat()
+        with torch.no_grad():                         # what nn.BatchNorm does in a train-mode forward
+            for name, off, size in eng.layout[eng.n_param_tensors:]:
+                sd[name].copy_(new[off:off + size].view(sd[name].shape))
+            for name, buf in sd.items():
+                if name.endswith("num_batches_tracked"):
+                    buf.add_(2)                       # one BatchNorm call per side (sg_net.py:123-124)
+        ctx.eng = eng
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.mark_non_differentiable(att1, att2)
+        return pred, att1, att2
+
+    @staticmethod
+    def backward(ctx, dpred, _datt1, _datt2):
+        flat = ctx.eng.backward(dpred.contiguous().to(torch.float32))
+        grads, off = [], 0
+        for shape in ctx.shapes:
+            n = 1
+            for d in shape:
+                n *= d
+            grads.append(flat[off:off + n].view(shape))
+            off += n
+        return (None, None, None, *grads)
 
 
 class SG(torch.nn.Module):
@@ -117,25 +156,17 @@ class SG(torch.nn.Module):
             self._packed_version = version
         return self._engine
 
-    # ---- differentiable device path, training only (sg_net.py:79-138 as stock PyTorch ops) -------------------
-    def _edge_layer(self, x, block):
-        return block(dgcnn.get_graph_feature(x, k=self.args.K)).max(dim=-1)[0]     # sg_net.py:84-86
+    # ---- train mode: the same C-ABI kernels as SGTrainer.process_batch, split at the loss ----------------------------
+    def _train_engine_for_autograd(self):
+        from .train_engine import TrainEngine
+        if getattr(self, "_autograd_engine", None) is None:
+            self._autograd_engine = TrainEngine(self._device())
+        return self._autograd_engine
 
-    def dgcnn_conv_pass(self, x):
-        xyz, sem = x[:, :3, :], x[:, 3:, :]
-        for block in (self.dgcnn_s_conv1, self.dgcnn_s_conv2, self.dgcnn_s_conv3):
-            xyz = self._edge_layer(xyz, block)
-        for block in (self.dgcnn_f_conv1, self.dgcnn_f_conv2, self.dgcnn_f_conv3):
-            sem = self._edge_layer(sem, block)
-        return self.dgcnn_conv_end(torch.cat((xyz, sem), dim=1)).permute(0, 2, 1)
-
-    def _forward_autograd(self, f1, f2):
-        e1, e2 = self.dgcnn_conv_pass(f1), self.dgcnn_conv_pass(f2)
-        p1, a1 = self.attention(e1)
-        p2, a2 = self.attention(e2)
-        s = self.tensor_network(p1, p2).permute(0, 2, 1)
-        s = torch.nn.functional.relu(self.fully_connected_first(s))
-        return torch.sigmoid(self.scoring_layer(s)).reshape(-1), a1, a2
+    def _train_params_in_layout_order(self):
+        eng = self._train_engine_for_autograd()
+        own = dict(self.named_parameters())
+        return [own[name] for name, _, _ in eng.layout[:eng.n_param_tensors]]
 
     # ---- the boundary ----------------------------------------------------------------------------------------
     def forward(self, data):
@@ -143,7 +174,9 @@ class SG(torch.nn.Module):
         dev = self._device()
         f1, f2 = data["features_1"], data["features_2"]
         if self.training:
-            return self._forward_autograd(f1.to(dev, dtype=torch.float32), f2.to(dev, dtype=torch.float32))
+            # batch-statistics BatchNorm, differentiable: forward and backward both run in csrc/train_kernels.cuh
+            return _TrainForward.apply(self, f1.to(dev, dtype=torch.float32).contiguous(),
+                                       f2.to(dev, dtype=torch.float32).contiguous(), *self._train_params_in_layout_order())
         # pinned fp32 host tensors are read in place by the kernel (zero-copy over PCIe); anything else is moved first
         ok = (f1.dim() == 3 and f1.shape[1] == 15 and f2.shape == f1.shape and f1.dtype == torch.float32
               and f2.dtype == torch.float32 and f1.is_contiguous() and f2.is_contiguous())

@@ -127,6 +127,52 @@ class TrainEngine:
                    "sgpr_train_step", self._lib)
         return loss, pred
 
+    def _stream(self):
+        return None if self._emulated else C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- the step split at the loss (caller-driven autograd) -----------------------------------------------------------
+    def set_state_flat(self, flat: torch.Tensor):
+        """Flat state vector [n_state] already on the engine's device (layout order)."""
+        flat = self._buf(flat, "state")
+        if flat.numel() != self.n_state:
+            raise ValueError(f"state vector has {flat.numel()} values, expected {self.n_state}")
+        _lib.check(self._lib.sgpr_train_set_state_dev(self._h, flat.data_ptr(), self._stream()), "sgpr_train_set_state_dev",
+                   self._lib)
+
+    def get_state_flat(self) -> torch.Tensor:
+        flat = torch.empty(self.n_state, dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.sgpr_train_get_state_dev(self._h, flat.data_ptr(), self._stream()), "sgpr_train_get_state_dev",
+                   self._lib)
+        return flat
+
+    def forward(self, f1: torch.Tensor, f2: Optional[torch.Tensor], k: int, update_running: bool = True,
+                mirrored: bool = False, want_att: bool = True):
+        """Train-mode forward only -> (prediction [B], att_1 [B,N,1] | None, att_2 [B,N,1] | None)."""
+        f1 = self._buf(f1, "features_1")
+        f2 = f1 if (mirrored and f2 is None) else self._buf(f2, "features_2")
+        if f1.dim() != 3 or f1.shape[1] != 15 or f2.shape != f1.shape:
+            raise ValueError(f"expected features [B,15,N] x2, got {tuple(f1.shape)}, {tuple(f2.shape)}")
+        B, _, N = f1.shape
+        pred = torch.empty(B, dtype=torch.float32, device=self.device)
+        att1 = torch.empty(B, N, 1, dtype=torch.float32, device=self.device) if want_att else None
+        att2 = torch.empty(B, N, 1, dtype=torch.float32, device=self.device) if (want_att and not mirrored) else None
+        _lib.check(self._lib.sgpr_train_forward(self._h, f1.data_ptr(), f2.data_ptr(), B, N, int(k), pred.data_ptr(),
+                                                att1.data_ptr() if att1 is not None else None,
+                                                att2.data_ptr() if att2 is not None else None,
+                                                int(bool(update_running)) | (2 if mirrored else 0), self._stream()),
+                   "sgpr_train_forward", self._lib)
+        if want_att and mirrored:
+            att2 = att1.view(B // 2, 2, N, 1).flip(1).reshape(B, N, 1)
+        return pred, att1, att2
+
+    def backward(self, dpred: torch.Tensor) -> torch.Tensor:
+        """d loss / d prediction [B] -> flat gradient vector [n_params] of the last forward()."""
+        dpred = self._buf(dpred, "dpred")
+        grads = torch.empty(self.n_params, dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.sgpr_train_backward(self._h, dpred.data_ptr(), grads.data_ptr(), self._stream()),
+                   "sgpr_train_backward", self._lib)
+        return grads
+
     def assemble(self, graphs: torch.Tensor, pair_idx: torch.Tensor, seed: int, step: int, want_draws: bool = False):
         """Device batch assembly + augmentation: graphs [M,15,N] and pair_idx [P,2] int32 on the device -> features_1
         [2P,15,N] of the mirrored batch (row 2p / 2p+1 = augmented graph a / b of listed pair p).  want_draws also

@@ -121,3 +121,48 @@ def test_batch_assembly_draw_statistics(eng):
     pair_idx = torch.randint(0, 16, (4096, 2), dtype=torch.int32).cuda()
     _, draws, jitter = eng.assemble(graphs, pair_idx, seed=5, step=0, want_draws=True)
     ac.check_draw_statistics(draws.cpu(), jitter.cpu())
+
+
+def test_split_forward_backward_matches_reference(eng):
+    g, sd = tc.load_case("n64_k20")
+    tc.check_split_forward_backward(eng, g, sd, "cuda", pred_tol=5e-5)
+    g, sd = tc.load_case("n32_k10")
+    tc.check_split_forward_backward(eng, g, sd, "cuda", pred_tol=1e-5, mirrored=True)
+
+
+def test_module_forward_in_train_mode_is_an_autograd_node(kitti_state):
+    """model.train(); model(data); loss.backward(); torch.optim.Adam.step() — the reference's own training idiom
+    (sg_net.py:332-338) on the drop-in module, against the golden gradients and the state after one step."""
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SG
+    g, sd = tc.load_case("n32_k10")
+    args = sgpr_args()
+    args.K, args.node_num, args.gpu = int(g["K"]), int(g["N"]), 0
+    model = SG(args, 12)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["weight_decay"]))
+    data = {"features_1": torch.from_numpy(g["features_1"]), "features_2": torch.from_numpy(g["features_2"]),
+            "target": torch.from_numpy(g["target"])}
+    opt.zero_grad()
+    pred, a1, a2 = model(data)
+    assert pred.requires_grad and not a1.requires_grad and a1.shape == (8, 32, 1)
+    loss = torch.mean(torch.nn.functional.binary_cross_entropy(pred, data["target"].cuda()))
+    loss.backward()
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), g["pred1"], rtol=0, atol=1e-5)
+    assert abs(float(loss) - float(g["loss1"])) < 1e-5
+    for name, p in model.named_parameters():
+        ref = g["grad1." + name]
+        scale = max(float(np.abs(ref).max()), 1e-8)
+        assert float(np.abs(p.grad.cpu().numpy() - ref).max()) <= 1e-3 * scale, name
+    opt.step()
+    state = model.state_dict()
+    assert int(state["dgcnn_s_conv1.1.num_batches_tracked"]) == int(g["state1.dgcnn_s_conv1.1.num_batches_tracked"])
+    for name in ("dgcnn_s_conv2.1.running_mean", "dgcnn_conv_end.1.running_var"):
+        ref = g["state1." + name]
+        assert float(np.abs(state[name].cpu().numpy() - ref).max()) <= 1e-4 * max(1.0, float(np.abs(ref).max())), name
+    # eval mode afterwards: the fused eval kernel sees the stepped weights (re-packed on version change)
+    model.eval()
+    with torch.no_grad():
+        s, _, _ = model(data)
+    assert s.shape == (8,) and bool(torch.isfinite(s).all())

@@ -136,7 +136,8 @@ def test_checkpoint_contract(tree, kitti_state):
 
 
 def test_training_path_matches_oracle_in_eval_math(kitti_state):
-    """The differentiable PyTorch path used by fit() computes the same function as the oracle (CPU, eval BN)."""
+    """The stock-PyTorch baseline form (benchmarks/tests only) computes the same function as the oracle (CPU, eval BN)."""
+    from sg_pr_b200.torch_baseline import forward_torch
     from oracle import sgpr_oracle as orc
     from sg_pr_b200 import synth
     from sg_pr_b200.parser_sg import sgpr_args
@@ -148,7 +149,7 @@ def test_training_path_matches_oracle_in_eval_math(kitti_state):
     model.eval()
     f1, f2 = synth.make_pair_batch(4, 64, 20, seed=8)
     with torch.no_grad():
-        score, a1, a2 = model._forward_autograd(f1, f2)
+        score, a1, a2 = forward_torch(model, f1, f2)
     want = orc.forward_pairs(f1, f2, 20, kitti_state)
     assert float((score - want["score"]).abs().max()) <= 1e-5
     assert float((a1 - want["att_1"]).abs().max()) <= 1e-5

@@ -48,6 +48,18 @@ def test_emulated_two_optimiser_steps_match_reference(emu_lib):
     eng.close()
 
 
+def test_emulated_split_forward_backward(emu_lib):
+    g, sd = tc.load_case("n32_k10")
+    eng = TrainEngine(lib=emu_lib)
+    tc.check_split_forward_backward(eng, g, sd, "cpu", pred_tol=1e-5)
+    import torch
+    f1, t = torch.from_numpy(g["features_1"]), torch.from_numpy(g["target"])
+    eng.step(f1, None, t, int(g["K"]), apply=False, mirrored=True)       # a fused step reuses the workspace ...
+    with pytest.raises(_lib.SgprError, match="no sgpr_train_forward"):
+        eng.backward(torch.zeros(8))                                      # ... so the old forward can no longer be differentiated
+    eng.close()
+
+
 def test_emulated_errors_are_loud(emu_lib):
     import torch
     g, sd = tc.load_case("n32_k10")

@@ -73,3 +73,40 @@ def check_two_steps(eng, g, sd, device, pred_tol, mirrored=False):
             else:
                 assert tight.mean() >= 0.85, (name, step, float(tight.mean()))
     assert eng.step_count() == 2
+
+
+def check_split_forward_backward(eng, g, sd, device, pred_tol, mirrored=False):
+    """sgpr_train_forward + sgpr_train_backward (the step split at the loss, autograd driven by the caller): feeding
+    d mean-BCE / d prediction computed by torch must reproduce the reference's gradients, and the forward alone must
+    update the running statistics the way the reference's first forward did."""
+    f1 = torch.from_numpy(g["features_1"]).to(device)
+    f2 = torch.from_numpy(g["features_2"]).to(device)
+    target = torch.from_numpy(g["target"]).to(device)
+    eng.set_state(sd)
+    pred, att1, att2 = eng.forward(f1, None if mirrored else f2, int(g["K"]), update_running=True, mirrored=mirrored)
+    np.testing.assert_allclose(pred.cpu().numpy(), g["pred1"], rtol=0, atol=pred_tol)
+    assert att1.shape == (f1.shape[0], f1.shape[2], 1) and att2.shape == att1.shape
+    leaf = pred.detach().clone().requires_grad_(True)
+    loss = torch.mean(torch.nn.functional.binary_cross_entropy(leaf, target))
+    loss.backward()
+    flat = eng.backward(leaf.grad)
+    assert abs(float(loss) - float(g["loss1"])) < pred_tol
+    grads = eng.grads()
+    off = 0
+    for name, got in grads.items():
+        ref = g["grad1." + name]
+        scale = max(float(np.abs(ref).max()), 1e-8)
+        err = float(np.abs(got.numpy().reshape(ref.shape) - ref).max())
+        assert err <= 1e-3 * scale, (name, err, scale)
+        assert torch.equal(flat[off:off + got.numel()].cpu(), got.reshape(-1))           # the device copy is the same vector
+        off += got.numel()
+    state = eng.get_state()
+    for name, value in state.items():
+        ref = g["state1." + name]
+        if "running_" in name:                       # updated by the forward, both sides
+            assert float(np.abs(value.numpy().reshape(ref.shape) - ref).max()) <= 1e-4 * max(1.0, float(np.abs(ref).max())), name
+        else:                                        # parameters untouched
+            assert torch.equal(value, sd[name].reshape(value.shape)), name
+    flat_state = eng.get_state_flat()
+    eng.set_state_flat(flat_state)
+    assert torch.equal(eng.get_state_flat(), flat_state)

@@ -74,6 +74,7 @@ out["configs"].append(run(64, 20, int(os.environ.get("PAIRS", "10240")), 10_000)
 try:
     from sg_pr_b200.parser_sg import sgpr_args
     from sg_pr_b200.sg_net import SG
+    from sg_pr_b200.torch_baseline import forward_torch
     margs = sgpr_args(); margs.K, margs.node_num, margs.gpu, margs.cuda = 20, 64, 0, "0"
     model = SG(margs, 12); model.load_state_dict(sd); model.cuda(0).eval()
     for tf32 in (True, False):
@@ -83,7 +84,7 @@ try:
             f1, f2 = synth.make_pair_batch(256, 64, 20, seed=10_000 + c0)
             want = orc.forward_pairs(f1, f2, 20, sd)["score"]
             with torch.no_grad():
-                got, _, _ = model._forward_autograd(f1.cuda(), f2.cuda())
+                got, _, _ = forward_torch(model, f1.cuda(), f2.cuda())
             err = (got.cpu() - want).abs()
             off += int((err > 1e-5).sum()); worst = max(worst, float(err.max())); tot += 256
         out.setdefault("reference_modules_on_gpu_vs_cpu", []).append(

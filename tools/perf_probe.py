@@ -32,20 +32,21 @@ for n, k, B in ((16, 10, 512), (32, 10, 512), (64, 10, 512), (64, 20, 512), (100
     us = timeit(f1.cuda(), f2.cuda(), k, iters=50)
     out.append({"N": n, "k": k, "B": B, "kind": "kitti", "us": round(us, 2), "pairs_per_s": round(B / us * 1e6)})
 # second baseline (BASELINE.md §3 "optional"): the same math as ~200 stock PyTorch launches per forward ON THE B200 — the
-# unfused path the reference would run on this GPU (our differentiable eval-mode path: SG._forward_autograd under no_grad)
+# unfused path the reference would run on this GPU (our differentiable eval-mode path: sg_pr_b200.torch_baseline.forward_torch under no_grad)
 try:
     from sg_pr_b200.parser_sg import sgpr_args
     from sg_pr_b200.sg_net import SG
+    from sg_pr_b200.torch_baseline import forward_torch
     margs = sgpr_args(); margs.K, margs.node_num, margs.gpu, margs.cuda = 20, 64, 0, "0"
     model = SG(margs, 12); model.load_state_dict(sd); model.cuda(0).eval()
     f1, f2 = synth.make_pair_batch(128, 64, 20, seed=1)
     f1, f2 = f1.cuda(), f2.cuda()
     with torch.no_grad():
-        for _ in range(5): ref_score, _, _ = model._forward_autograd(f1, f2)
+        for _ in range(5): ref_score, _, _ = forward_torch(model, f1, f2)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(20): model._forward_autograd(f1, f2)
+        for _ in range(20): forward_torch(model, f1, f2)
         e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1e3
     fused, _, _ = eng.forward_pairs(f1, f2, 20)

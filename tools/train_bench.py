@@ -1,7 +1,7 @@
 """Training-step benchmark (BASELINE config 3): `listed` synthetic KITTI-shape pairs -> 2*listed forward pairs (both
 orders, sg_net.py:324-331), N nodes, k neighbours.  Times the device step (sgpr_train_step: 13 launches) with CUDA
 events, inputs resident in HBM, and — optionally — the same step as stock PyTorch ops on the same GPU (the reference's
-own module code path: SG._forward_autograd + loss.backward() + torch.optim.Adam).
+own module code path: sg_pr_b200.torch_baseline.forward_torch + loss.backward() + torch.optim.Adam).
 
     python tools/train_bench.py [--listed 128] [--nodes 64] [--k 20] [--steps 50] [--warmup 5] [--torch-baseline]
 """
@@ -58,6 +58,7 @@ def main():
     if a.torch_baseline:
         from sg_pr_b200.parser_sg import sgpr_args
         from sg_pr_b200.sg_net import SG
+        from sg_pr_b200.torch_baseline import forward_torch
         args = sgpr_args()
         args.K, args.node_num, args.gpu, args.cuda = a.k, a.nodes, 0, "0"
         model = SG(args, 12)
@@ -67,7 +68,7 @@ def main():
 
         def step():
             opt.zero_grad()
-            pred, _, _ = model._forward_autograd(f1, f2)
+            pred, _, _ = forward_torch(model, f1, f2)
             loss = torch.mean(torch.nn.functional.binary_cross_entropy(pred, target))
             loss.backward()
             opt.step()
