@@ -80,7 +80,8 @@ int sgpr_train_step(sgpr_train* t, const float* f1_dev, const float* f2_dev, con
  *   sgpr_train_forward : train-mode forward only.  pred_dev [B]; att1_dev / att2_dev [B][N] attention scores or NULL
  *                        (att2 is not written for a mirrored batch: it is att1 with adjacent rows swapped).
  *                        With SGPR_TRAIN_APPLY the BatchNorm running statistics are updated, as nn.BatchNorm does in
- *                        forward; parameters are never touched.  Everything the backward needs stays in the context.
+ *                        forward; parameters are never touched.  Everything the backward needs stays in the context,
+ *                        except the input blocks themselves: f1_dev / f2_dev must stay valid until sgpr_train_backward.
  *   sgpr_train_backward: backward of the LAST sgpr_train_forward from dpred_dev [B] = d loss / d prediction; the flat
  *                        gradient vector (sgpr_train_param_count floats) is left readable through sgpr_train_get_grads
  *                        and, if grads_dev != NULL, copied there (device pointer).

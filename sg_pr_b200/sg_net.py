@@ -82,6 +82,7 @@ class _TrainForward(torch.autograd.Function):
                 if name.endswith("num_batches_tracked"):
                     buf.add_(2)                       # one BatchNorm call per side (sg_net.py:123-124)
         ctx.eng = eng
+        ctx.save_for_backward(f1, f2)                 # the layer-1 backward re-reads the input blocks: keep them alive
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.mark_non_differentiable(att1, att2)
         return pred, att1, att2

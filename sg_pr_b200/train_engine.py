@@ -147,7 +147,8 @@ class TrainEngine:
 
     def forward(self, f1: torch.Tensor, f2: Optional[torch.Tensor], k: int, update_running: bool = True,
                 mirrored: bool = False, want_att: bool = True):
-        """Train-mode forward only -> (prediction [B], att_1 [B,N,1] | None, att_2 [B,N,1] | None)."""
+        """Train-mode forward only -> (prediction [B], att_1 [B,N,1] | None, att_2 [B,N,1] | None).
+        The caller keeps f1 / f2 alive until backward(): the first EdgeConv layers' backward re-reads them."""
         f1 = self._buf(f1, "features_1")
         f2 = f1 if (mirrored and f2 is None) else self._buf(f2, "features_2")
         if f1.dim() != 3 or f1.shape[1] != 15 or f2.shape != f1.shape:
