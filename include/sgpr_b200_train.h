@@ -120,7 +120,7 @@ int64_t sgpr_train_launch_count(const sgpr_train* t);
 
 /*
  * Debug/parity tap: copy an internal tensor of the LAST step to the host.  what: "yext","a","d","sumy","gz","enode",
- * "idx" (layer = 0..5: xyz 1-3, sem 1-3), "yend","gzend","pooled","att","ctx","dpooled","stats","bsum" (layer ignored).
+ * "idx" (layer = 0..5: xyz 1-3, sem 1-3), "yend","gzend","pooled","att","dpooled","stats","bsum" (layer ignored).
  * Returns the number of bytes copied (<= cap_bytes) or a negative error.
  */
 int64_t sgpr_train_debug_read(sgpr_train* t, const char* what, int layer, void* host, int64_t cap_bytes);

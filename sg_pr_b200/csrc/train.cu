@@ -94,8 +94,8 @@ void build_layout() {
 struct Plan {
     bool valid = false, backward_ready = false;
     TrainWs W{};
-    int npl = 2, grid4 = 0, grid2 = 0, grid_att = 0, head_grid = 0;
-    size_t fwd_smem = 0, bwd_smem = 0, end_fwd_smem = 0, end_bwd_smem = 0;
+    int npl = 2, grid4 = 0, grid2 = 0, head_grid = 0;
+    size_t fwd_smem = 0, bwd_smem = 0, end_fwd_smem = 0, end_bwd_smem = 0, pool_smem = 0;
     float* part_head = nullptr;
     float* part_att = nullptr;
     float* part_end = nullptr;
@@ -124,7 +124,7 @@ struct sgpr_train {
 
 namespace {
 
-constexpr int kMaxHeadGrid = 148;
+constexpr int kMaxHeadGrid = 1024;
 constexpr size_t kSumDoubles = 2 * 2 * 7 * 128;
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
@@ -181,6 +181,7 @@ int sgpr_train_create(sgpr_train** out, int device) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_state), STATE_TOTAL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_adam), 2 * P_TOTAL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_grads), P_TOTAL * sizeof(float));
@@ -270,7 +271,7 @@ int make_plan(sgpr_train* t, const float* f1_dev, const float* f2_dev, const flo
         const size_t per = static_cast<size_t>(SG) * N * layer_cout(L);
         need += 5 * align256(per * 4) + align256(per) + align256(static_cast<size_t>(SG) * N * k);
     }
-    need += 2 * align256(static_cast<size_t>(SG) * N * 32 * 4) + 3 * align256(static_cast<size_t>(SG) * 32 * 4) +
+    need += 2 * align256(static_cast<size_t>(SG) * N * 32 * 4) + align256(static_cast<size_t>(SG) * 32 * 4) +
             align256(static_cast<size_t>(2) * G * 32 * 4) +
             align256(static_cast<size_t>(SG) * N * 4) + align256(static_cast<size_t>(G) * 4);
     if (need > t->ws_cap) {
@@ -286,10 +287,12 @@ int make_plan(sgpr_train* t, const float* f1_dev, const float* f2_dev, const flo
     if (P.grid4 < 2 * S) P.grid4 = 2 * S;
     P.grid2 = S * G < cap ? S * G : (cap / S) * S;                            // side x graphs
     if (P.grid2 < S) P.grid2 = S;
-    P.grid_att = SG < 4 * t->sm_count ? SG : 4 * t->sm_count;
-    P.head_grid = G < kMaxHeadGrid ? G : kMaxHeadGrid;
+    const int groups = mirrored ? G / 2 : G;                  // pool_head: one group = the two graphs of a pair
+    P.head_grid = groups < 2 * t->sm_count ? groups : 2 * t->sm_count;
+    if (P.head_grid > kMaxHeadGrid) P.head_grid = kMaxHeadGrid;
+    P.pool_smem = static_cast<size_t>(4) * N * 33 * sizeof(float);
     const int nb = P.grid4 / 2;                                // partial rows per branch in the EdgeConv backward
-    size_t part_need = static_cast<size_t>(P.head_grid) * kHeadFloats + static_cast<size_t>(P.grid2) * 1024 +
+    size_t part_need = static_cast<size_t>(P.head_grid) * kHeadFloats + static_cast<size_t>(P.head_grid) * 1024 +
                        static_cast<size_t>(P.grid2) * 2048;
     for (int L = 0; L < 6; ++L) part_need += static_cast<size_t>(nb) * conv_size(L);
     if (part_need > t->part_cap) {
@@ -317,8 +320,6 @@ int make_plan(sgpr_train* t, const float* f1_dev, const float* f2_dev, const flo
     W.yend = carve<float>(p, static_cast<size_t>(SG) * N * 32);
     W.gzend = carve<float>(p, static_cast<size_t>(SG) * N * 32);
     W.pooled = carve<float>(p, static_cast<size_t>(SG) * 32);
-    W.actx = carve<float>(p, static_cast<size_t>(SG) * 32);
-    W.esum = carve<float>(p, static_cast<size_t>(SG) * 32);
     W.dpooled = carve<float>(p, static_cast<size_t>(2) * G * 32);        // d/d e1 of pair p | d/d e2 of pair p
     W.att = carve<float>(p, static_cast<size_t>(SG) * N);
     W.pred = carve<float>(p, static_cast<size_t>(G));
@@ -334,13 +335,13 @@ int make_plan(sgpr_train* t, const float* f1_dev, const float* f2_dev, const flo
     // gradient partials and the segment table the optimiser sums them by
     float* pp = t->d_part;
     P.part_head = pp; pp += static_cast<size_t>(P.head_grid) * kHeadFloats;
-    P.part_att = pp;  pp += static_cast<size_t>(P.grid2) * 1024;
+    P.part_att = pp;  pp += static_cast<size_t>(P.head_grid) * 1024;
     P.part_end = pp;  pp += static_cast<size_t>(P.grid2) * 2048;
     for (int L = 0; L < 6; ++L) { P.part_conv[L] = pp; pp += static_cast<size_t>(nb) * conv_size(L); }
     int ns = 0;
     for (int L = 0; L < 6; ++L) W.seg[ns++] = Segment{conv_off(L), conv_size(L), nb, conv_size(L), P.part_conv[L]};
     W.seg[ns++] = Segment{P_ENDW, 2048, P.grid2, 2048, P.part_end};
-    W.seg[ns++] = Segment{P_ATT, 1024, P.grid2, 1024, P.part_att};
+    W.seg[ns++] = Segment{P_ATT, 1024, P.head_grid, 1024, P.part_att};
     W.seg[ns++] = Segment{P_NTNW, kHeadFloats, P.head_grid, kHeadFloats, P.part_head};
     W.nseg = ns;
     P.W = W;
@@ -360,7 +361,7 @@ int make_plan(sgpr_train* t, const float* f1_dev, const float* f2_dev, const flo
         t->launches += 1;                                                                                \
     } while (0)
 
-// pack | EdgeConv fwd x3 | conv_end fwd | attention fwd  (statistics zeroed first)
+// pack | EdgeConv fwd x3 | conv_end fwd  (statistics zeroed first)
 int launch_forward(sgpr_train* t, cudaStream_t st) {
     Plan& P = t->plan;
     const TrainWs& W = P.W;
@@ -369,24 +370,20 @@ int launch_forward(sgpr_train* t, cudaStream_t st) {
     t->launches += 1;
     for (int l = 0; l < 3; ++l) BY_NPL(sgpr_train_edge_fwd, P.grid4, P.fwd_smem, W, l);
     BY_NPL(sgpr_train_end_fwd, P.grid2, P.end_fwd_smem, W);
-    SGPR_LAUNCH(sgpr_train_att_fwd, P.grid_att, kThreads, 0, st, W);
-    t->launches += 1;
     return SGPR_OK;
 }
 
-// head (mode: kHeadFused / kHeadForward / kHeadBackward)
+// conv_end BN + attention + pair head (+ loss, head bwd, attention bwd); mode: kHeadFused / kHeadForward / kHeadBackward
 void launch_head(sgpr_train* t, cudaStream_t st, int mode) {
     Plan& P = t->plan;
-    SGPR_LAUNCH(sgpr_train_head_kernel, P.head_grid, kThreads, 0, st, P.W, P.part_head, mode);
+    SGPR_LAUNCH(sgpr_train_pool_head_kernel, P.head_grid, kThreads, P.pool_smem, st, P.W, P.part_head, P.part_att, mode);
     t->launches += 1;
 }
 
-// attention bwd | conv_end bwd | EdgeConv bwd x3   (dbeta / dgamma sums zeroed first)
+// conv_end bwd | EdgeConv bwd x3   (the caller zeroes the dbeta / dgamma sums before launch_head)
 int launch_backward(sgpr_train* t, cudaStream_t st) {
     Plan& P = t->plan;
     const TrainWs& W = P.W;
-    SGPR_LAUNCH(sgpr_train_att_bwd, P.grid2, kThreads, 0, st, W, P.part_att);
-    t->launches += 1;
     BY_NPL(sgpr_train_end_bwd, P.grid2, P.end_bwd_smem, W, P.part_end);
     for (int l = 2; l >= 0; --l) BY_NPL(sgpr_train_edge_bwd, P.grid4, P.bwd_smem, W, l, P.part_conv[l], P.part_conv[3 + l]);
     return SGPR_OK;
@@ -546,7 +543,6 @@ int64_t sgpr_train_debug_read(sgpr_train* t, const char* what, int layer, void* 
     } else if (!strcmp(what, "yend")) { src = W.yend; bytes = SG * W.N * 32 * 4; }
     else if (!strcmp(what, "gzend")) { src = W.gzend; bytes = SG * W.N * 32 * 4; }
     else if (!strcmp(what, "pooled")) { src = W.pooled; bytes = SG * 32 * 4; }
-    else if (!strcmp(what, "ctx")) { src = W.actx; bytes = SG * 32 * 4; }
     else if (!strcmp(what, "dpooled")) { src = W.dpooled; bytes = 2 * static_cast<size_t>(W.G) * 32 * 4; }
     else if (!strcmp(what, "att")) { src = W.att; bytes = SG * W.N * 4; }
     else if (!strcmp(what, "stats")) { src = W.stats; bytes = kSumDoubles / 2 * 8; }

@@ -8,8 +8,9 @@
 // path's single fused kernel — a layer cannot start before the previous layer's statistics are complete.  The step is a
 // short chain of launches with a grid-wide dependency (the kernel boundary) exactly where BatchNorm puts one:
 //
-//   pack | edge_fwd l=0,1,2 (xyz and sem branches of both sides in one grid) | end_fwd | att_fwd | head (fwd+loss+bwd)
-//        | att_bwd | end_bwd | edge_bwd l=2,1,0 | adam (+ running statistics, loss)
+//   pack | edge_fwd l=0,1,2 (xyz and sem branches of both sides in one grid) | end_fwd
+//        | pool_head (conv_end BN, attention fwd, pair head fwd + loss + bwd, attention bwd)
+//        | end_bwd | edge_bwd l=2,1,0 | adam (+ running statistics, loss)
 //
 // Arithmetic form (tests/train_model.py holds the same algebra in torch, checked against autograd on the CPU):
 //   forward   y_ij = (A_j - A_i) + B_i,  A = Wa x, B = Wb x per node; BN+LeakyReLU is monotone per channel, so the max over
@@ -134,9 +135,7 @@ struct TrainWs {
     float* yend;            // [2*G][N][32] conv_end pre-BN
     float* gzend;           // [2*G][N][32]
     float* pooled;          // [2*G][32]
-    float* actx;            // [2*G][32]  tanh context
     float* att;             // [2*G][N]
-    float* esum;            // [2*G][32]  sum_n emb
     float* dpooled;         // [2*G][32]
     double* stats;          // [2][7][2][64]  sum y | sum y^2
     double* bsum;           // [2][7][2][64]  dbeta | dgamma
@@ -532,75 +531,37 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_f
 }
 
 // =====================================================================================================================
-// conv_end BatchNorm + LeakyReLU, then attention pooling (layers_batch.py:28-39).  One CTA per (side, g) item.
+// conv_end BatchNorm + LeakyReLU -> attention pooling (layers_batch.py:28-39) -> pair head (layers_batch.py:70-83,
+// sg_net.py:131-136) -> loss -> head backward -> attention backward -> LeakyReLU of conv_end, in ONE kernel: after the
+// conv_end statistics nothing on this stretch depends on another pair.  A CTA works on a GROUP = the two graphs of a
+// pair: thread half h (128 threads) owns graph h for the attention stages, the whole CTA runs the head.
+//   two-sided: group p = graphs (side 0, p) and (side 1, p), one ordered pair p
+//   mirrored : group q = graphs 2q and 2q+1 of side 0, the two ordered pairs 2q = (2q, 2q+1) and 2q+1 = (2q+1, 2q);
+//              each graph's pooled-vector gradient is the sum over its two roles.
+// mode kHeadForward stops after the predictions (sgpr_train_forward); kHeadBackward takes d loss / d prediction from
+// T.dpred instead of the BCE (sgpr_train_backward; the attention forward is simply recomputed from yend).
+// Outputs: pred, att, pooled, dpooled (taps), gz_end = d loss / d (conv_end BN output) with its dbeta / dgamma sums;
+// partial rows: part_head [grid][kHeadFloats], part_att [grid][1024].
 // =====================================================================================================================
-__global__ void __launch_bounds__(kThreads) sgpr_train_att_fwd(const TrainWs T) {
-    __shared__ float sE[SGPR_MAX_NODES * 33];
-    __shared__ float sPrm[4 * 32];
-    __shared__ float sSum[32], sCtx[32], sAtt[SGPR_MAX_NODES];
-    const int tid = threadIdx.x;
-    const int N = T.N;
-    const float* watt = T.state + P_ATT;
-    for (int item = blockIdx.x; item < T.S * T.G; item += gridDim.x) {
-        const int side = item / T.G;
-        if (tid < 32) {
-            float mu, istd;
-            bn_coef(stat_ptr(T.stats, side, 6), tid, static_cast<double>(T.G) * N, T.eps, mu, istd);
-            sPrm[tid] = mu;
-            sPrm[32 + tid] = istd;
-            sPrm[64 + tid] = T.state[P_BN + bn_off(6) + tid];
-            sPrm[96 + tid] = T.state[P_BN + bn_off(6) + 32 + tid];
-        }
-        __syncthreads();
-        const float* y = T.yend + static_cast<size_t>(item) * N * 32;
-        for (int e = tid; e < N * 32; e += kThreads) {
-            const int n = e >> 5, c = e & 31;
-            sE[n * 33 + c] = bn_act(y[e], sPrm[c], sPrm[32 + c], sPrm[64 + c], sPrm[96 + c]);
-        }
-        __syncthreads();
-        if (tid < 32) {
-            float s = 0.0f;
-            for (int n = 0; n < N; ++n) s = __fadd_rn(s, sE[n * 33 + tid]);
-            sSum[tid] = s;
-            T.esum[static_cast<size_t>(item) * 32 + tid] = s;
-        }
-        __syncthreads();
-        if (tid < 32) {          // context = tanh(mean_n(E W)) = tanh((sum_n E) W / N)
-            float s = 0.0f;
-            for (int a = 0; a < 32; ++a) s = fmaf(sSum[a], watt[a * 32 + tid], s);
-            const float c = tanhf(s / static_cast<float>(N));
-            sCtx[tid] = c;
-            T.actx[static_cast<size_t>(item) * 32 + tid] = c;
-        }
-        __syncthreads();
-        if (tid < N) {
-            float s = 0.0f;
-            for (int a = 0; a < 32; ++a) s = fmaf(sE[tid * 33 + a], sCtx[a], s);
-            const float av = sigmoidf_acc(s);
-            sAtt[tid] = av;
-            T.att[static_cast<size_t>(item) * N + tid] = av;
-        }
-        __syncthreads();
-        if (tid < 32) {
-            float s = 0.0f;
-            for (int n = 0; n < N; ++n) s = fmaf(sAtt[n], sE[n * 33 + tid], s);
-            T.pooled[static_cast<size_t>(item) * 32 + tid] = s;
-        }
-        __syncthreads();
-    }
-}
-
-// =====================================================================================================================
-// Pair head forward (layers_batch.py:70-83, sg_net.py:131-136), mean BCE (sg_net.py:335) and the head's backward.
-// Persistent CTAs; parameter gradients in registers, written as one partial row of kHeadFloats per CTA.
-// =====================================================================================================================
-__global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs T, float* __restrict__ part, int mode) {
+__global__ void __launch_bounds__(kThreads, 2) sgpr_train_pool_head_kernel(const TrainWs T, float* __restrict__ part_head,
+                                                                         float* __restrict__ part_att, int mode) {
+    SGPR_DYN_SMEM(smem);
+    const int N = T.N, G = T.G;
+    float* sE = reinterpret_cast<float*>(smem);            // [2][N][33]  node embeddings
+    float* sYh = sE + 2 * N * 33;                          // [2][N][33]  conv_end BN-normalised pre-activations
+    __shared__ float sPrm[2][4 * 32];
+    __shared__ float sSum[2][32], sCtx[2][32], sPool[2][32], sDp[2][32], sDcbar[2][32], sV[2][32];
+    __shared__ float sAtt[2][SGPR_MAX_NODES], sDsig[2][SGPR_MAX_NODES];
     __shared__ float e12[64];              // e1 | e2 (the V-block input cat(e1, e2), layers_batch.py:80)
     __shared__ float sP[512], sQ[512];
     __shared__ float sS[16], sNt[16], sHpre[16], sH[16], sDh[16], sDs[16];
     __shared__ float sDz;
+    __shared__ double sRed[kWarps * 64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = tid >> 7, lt = tid & 127;
     const int t16 = tid >> 4, part16 = tid & 15;
+    const int side = T.mirrored ? 0 : half;
+    const float* watt = T.state + P_ATT;
     const float* W = T.state + P_NTNW;
     const float* V = T.state + P_NTNV;
     const float* nb = T.state + P_NTNB;
@@ -608,118 +569,218 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs
     const float* b1 = T.state + P_FC1B;
     const float* w2 = T.state + P_FC2W;
     const float* b2 = T.state + P_FC2B;
-    const int G = T.G;
-    float gW[64], gV[4], gW1 = 0.0f, gNb = 0.0f, gB1 = 0.0f, gW2 = 0.0f, gB2 = 0.0f, loss = 0.0f;
+    float gW[64], gV[4], gA[4], gW1 = 0.0f, gNb = 0.0f, gB1 = 0.0f, gW2 = 0.0f, gB2 = 0.0f, loss = 0.0f;
 #pragma unroll
     for (int m = 0; m < 64; ++m) gW[m] = 0.0f;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) gV[m] = 0.0f;
-    const float* e1 = e12;
-    const float* e2 = e12 + 32;
+    for (int m = 0; m < 4; ++m) { gV[m] = 0.0f; gA[m] = 0.0f; }
+    double accb = 0.0, accg = 0.0;                     // conv_end channel lt & 31 of this half's side
+    if (lt < 32) {
+        float mu, istd;
+        bn_coef(stat_ptr(T.stats, side, 6), lt, static_cast<double>(G) * N, T.eps, mu, istd);
+        sPrm[half][lt] = mu;
+        sPrm[half][32 + lt] = istd;
+        sPrm[half][64 + lt] = T.state[P_BN + bn_off(6) + lt];
+        sPrm[half][96 + lt] = T.state[P_BN + bn_off(6) + 32 + lt];
+    }
+    __syncthreads();
+    const int groups = T.mirrored ? G / 2 : G;
+    const int npairs = T.mirrored ? 2 : 1;
+    const float* prm = sPrm[half];
+    float* hE = sE + half * N * 33;
+    float* hYh = sYh + half * N * 33;
 
-    for (int p = blockIdx.x; p < G; p += gridDim.x) {
-        if (tid < 64) {          // e2 of pair p: the graph of side 2 — in mirrored mode that is graph p ^ 1 of side 1
-            const size_t row = (tid < 32) ? static_cast<size_t>(p) : (T.mirrored ? static_cast<size_t>(p ^ 1) : static_cast<size_t>(G) + p);
-            e12[tid] = T.pooled[row * 32 + (tid & 31)];
-        }
-        __syncthreads();
-        for (int m = 0; m < 2; ++m) {                       // P[b*16+t] = sum_a e1[a] W[a][b][t]
-            const int bt = tid + 256 * m;
-            float acc = 0.0f;
-#pragma unroll 8
-            for (int a = 0; a < 32; ++a) acc = fmaf(e1[a], W[a * 512 + bt], acc);
-            sP[bt] = acc;
-        }
-        __syncthreads();
-        {   // s[t] = sum_b P[b][t] e2[b] + V[t] . cat + bias[t];  thread (t16, part16) sums a slice
-            float bil = fmaf(sP[(2 * part16 + 1) * 16 + t16], e2[2 * part16 + 1], __fmul_rn(sP[(2 * part16) * 16 + t16], e2[2 * part16]));
-            float blk = 0.0f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) blk = fmaf(V[t16 * 64 + part16 * 4 + q], e12[part16 * 4 + q], blk);
-            bil = group16_sum(bil);
-            blk = group16_sum(blk);
-            if (part16 == 0) {
-                const float s = __fadd_rn(__fadd_rn(bil, blk), nb[t16]);
-                sS[t16] = s;
-                sNt[t16] = fmaxf(s, 0.0f);
+    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+        const size_t sg = T.mirrored ? static_cast<size_t>(2 * grp + half) : static_cast<size_t>(half) * G + grp;
+        // ---- conv_end BN + LeakyReLU ----
+        {
+            const float* y = T.yend + sg * N * 32;
+            for (int e = lt; e < N * 32; e += 128) {
+                const int n = e >> 5, c = e & 31;
+                const float yh = __fmul_rn(__fsub_rn(__ldg(y + e), prm[c]), prm[32 + c]);
+                hYh[n * 33 + c] = yh;
+                hE[n * 33 + c] = lrelu(fmaf(yh, prm[64 + c], prm[96 + c]));
             }
+        }
+        __syncthreads();
+        // ---- attention forward (layers_batch.py:35-38), one graph per thread half ----
+        if (lt < 32) {
+            float s = 0.0f;
+            for (int n = 0; n < N; ++n) s = __fadd_rn(s, hE[n * 33 + lt]);
+            sSum[half][lt] = s;
+        }
+        __syncthreads();
+        if (lt < 32) {          // context = tanh(mean_n(E W)) = tanh((sum_n E) W / N)
+            float s = 0.0f;
+            for (int a = 0; a < 32; ++a) s = fmaf(sSum[half][a], watt[a * 32 + lt], s);
+            sCtx[half][lt] = tanhf(s / static_cast<float>(N));
+        }
+        __syncthreads();
+        if (lt < N) {
+            float s = 0.0f;
+            for (int a = 0; a < 32; ++a) s = fmaf(hE[lt * 33 + a], sCtx[half][a], s);
+            const float av = sigmoidf_acc(s);
+            sAtt[half][lt] = av;
+            T.att[sg * N + lt] = av;
+        }
+        __syncthreads();
+        if (lt < 32) {
+            float s = 0.0f;
+            for (int n = 0; n < N; ++n) s = fmaf(sAtt[half][n], hE[n * 33 + lt], s);
+            sPool[half][lt] = s;
+            sDp[half][lt] = 0.0f;
+            T.pooled[sg * 32 + lt] = s;
+        }
+        __syncthreads();
+        // ---- pair head: forward, loss, backward ----
+        for (int q = 0; q < npairs; ++q) {
+            const int p = T.mirrored ? 2 * grp + q : grp;       // pair index
+            const int g1 = q, g2 = q ^ 1;                       // which half holds e1 / e2 of this pair
+            if (tid < 64) e12[tid] = tid < 32 ? sPool[g1][tid] : sPool[g2][tid - 32];
+            __syncthreads();
+            const float* e1 = e12;
+            const float* e2 = e12 + 32;
+            for (int m = 0; m < 2; ++m) {                       // P[b*16+t] = sum_a e1[a] W[a][b][t]
+                const int bt = tid + 256 * m;
+                float acc = 0.0f;
+#pragma unroll 8
+                for (int a = 0; a < 32; ++a) acc = fmaf(e1[a], W[a * 512 + bt], acc);
+                sP[bt] = acc;
+            }
+            __syncthreads();
+            {   // s[t] = sum_b P[b][t] e2[b] + V[t] . cat + bias[t];  thread (t16, part16) sums a slice
+                float bil = fmaf(sP[(2 * part16 + 1) * 16 + t16], e2[2 * part16 + 1], __fmul_rn(sP[(2 * part16) * 16 + t16], e2[2 * part16]));
+                float blk = 0.0f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) blk = fmaf(V[t16 * 64 + part16 * 4 + u], e12[part16 * 4 + u], blk);
+                bil = group16_sum(bil);
+                blk = group16_sum(blk);
+                if (part16 == 0) {
+                    const float s = __fadd_rn(__fadd_rn(bil, blk), nb[t16]);
+                    sS[t16] = s;
+                    sNt[t16] = fmaxf(s, 0.0f);
+                }
+            }
+            __syncthreads();
+            {
+                float h = group16_sum(__fmul_rn(sNt[part16], w1[t16 * 16 + part16]));
+                if (part16 == 0) {
+                    h = __fadd_rn(h, b1[t16]);
+                    sHpre[t16] = h;
+                    sH[t16] = fmaxf(h, 0.0f);
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                float z = lane < 16 ? __fmul_rn(sH[lane], w2[lane]) : 0.0f;
+                z = warp_sum(z);
+                if (lane == 0) {
+                    const float pr = sigmoidf_acc(__fadd_rn(z, b2[0]));
+                    T.pred[p] = pr;
+                    if (mode == kHeadFused) {
+                        const float tg = T.target[p];
+                        // torch.nn.functional.binary_cross_entropy clamps both logs at -100
+                        loss += -(tg * fmaxf(logf(pr), -100.0f) + (1.0f - tg) * fmaxf(logf(1.0f - pr), -100.0f));
+                        sDz = (pr - tg) / static_cast<float>(G);           // d mean-BCE / d (pre-sigmoid score)
+                    } else if (mode == kHeadBackward) {
+                        sDz = T.dpred[p] * pr * (1.0f - pr);               // through the sigmoid (sg_net.py:136)
+                    }
+                }
+            }
+            __syncthreads();
+            if (mode == kHeadForward) continue;                            // uniform: the whole CTA skips the backward
+            const float dz = sDz;
+            if (tid < 16) sDh[tid] = sHpre[tid] > 0.0f ? dz * w2[tid] : 0.0f;
+            __syncthreads();
+            if (tid < 16) {
+                float s = 0.0f;
+                for (int u = 0; u < 16; ++u) s = fmaf(sDh[u], w1[u * 16 + tid], s);
+                sDs[tid] = sS[tid] > 0.0f ? s : 0.0f;
+            }
+            __syncthreads();
+            const float q0 = e2[tid >> 4] * sDs[part16];               // q[b*16+t] = e2[b] ds[t], bt = tid
+            const float q1 = e2[16 + (tid >> 4)] * sDs[part16];        // bt = tid + 256
+            sQ[tid] = q0;
+            sQ[256 + tid] = q1;
+            // ---- head parameter gradients ----
+#pragma unroll
+            for (int m = 0; m < 64; ++m) gW[m] = fmaf(e1[m >> 1], (m & 1) ? q1 : q0, gW[m]);    // flat index tid + 256 m
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { const int e = tid + 256 * m; gV[m] = fmaf(sDs[e >> 6], e12[e & 63], gV[m]); }
+            gW1 = fmaf(sDh[t16], sNt[part16], gW1);
+            if (tid < 16) {
+                gNb += sDs[tid];
+                gB1 += sDh[tid];
+                gW2 = fmaf(dz, sH[tid], gW2);
+            }
+            if (tid == 0) gB2 += dz;
+            __syncthreads();
+            // ---- d loss / d pooled vectors, added to the graph that played the role ----
+            for (int u = 0; u < 4; ++u) {                        // de1[a] = sum_bt W[a][bt] q[bt] + sum_t ds[t] V[t][a]
+                const int a = warp * 4 + u;
+                float s = 0.0f;
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) s = fmaf(W[a * 512 + lane + 32 * i], sQ[lane + 32 * i], s);
+                s = warp_sum(s);
+                if (lane == 0) {
+                    for (int t = 0; t < 16; ++t) s = fmaf(sDs[t], V[t * 64 + a], s);
+                    T.dpooled[static_cast<size_t>(p) * 32 + a] = s;
+                    sDp[g1][a] = __fadd_rn(sDp[g1][a], s);
+                }
+            }
+            __syncthreads();                                     // (mirrored: g2 of this pair was g1's array a moment ago)
+            if (tid < 32) {                                      // de2[b] = sum_t P[b][t] ds[t] + sum_t ds[t] V[t][32+b]
+                float s = 0.0f;
+                for (int t = 0; t < 16; ++t) s = fmaf(sP[tid * 16 + t], sDs[t], s);
+                for (int t = 0; t < 16; ++t) s = fmaf(sDs[t], V[t * 64 + 32 + tid], s);
+                T.dpooled[(static_cast<size_t>(G) + p) * 32 + tid] = s;
+                sDp[g2][tid] = __fadd_rn(sDp[g2][tid], s);
+            }
+            __syncthreads();
+        }
+        if (mode == kHeadForward) continue;
+        // ---- attention backward, one graph per thread half ----
+        if (lt < N) {
+            float s = 0.0f;
+            for (int a = 0; a < 32; ++a) s = fmaf(hE[lt * 33 + a], sDp[half][a], s);
+            const float av = sAtt[half][lt];
+            sDsig[half][lt] = s * av * (1.0f - av);
+        }
+        __syncthreads();
+        if (lt < 32) {
+            float s = 0.0f;
+            for (int n = 0; n < N; ++n) s = fmaf(sDsig[half][n], hE[n * 33 + lt], s);
+            const float c = sCtx[half][lt];
+            sDcbar[half][lt] = s * (1.0f - c * c) / static_cast<float>(N);
+        }
+        __syncthreads();
+        if (lt < 32) {
+            float s = 0.0f;
+            for (int b = 0; b < 32; ++b) s = fmaf(sDcbar[half][b], watt[lt * 32 + b], s);
+            sV[half][lt] = s;
         }
         __syncthreads();
         {
-            float h = group16_sum(__fmul_rn(sNt[part16], w1[t16 * 16 + part16]));
-            if (part16 == 0) {
-                h = __fadd_rn(h, b1[t16]);
-                sHpre[t16] = h;
-                sH[t16] = fmaxf(h, 0.0f);
+            float* gzo = T.gzend + sg * N * 32;
+            for (int e = lt; e < N * 32; e += 128) {
+                const int n = e >> 5, c = e & 31;
+                const float de = fmaf(sAtt[half][n], sDp[half][c], fmaf(sDsig[half][n], sCtx[half][c], sV[half][c]));
+                const float gzv = de * slope_of(hE[n * 33 + c]);
+                gzo[e] = gzv;
+                accb += static_cast<double>(gzv);
+                accg += static_cast<double>(gzv) * static_cast<double>(hYh[n * 33 + c]);
             }
         }
-        __syncthreads();
-        if (warp == 0) {
-            float z = lane < 16 ? __fmul_rn(sH[lane], w2[lane]) : 0.0f;
-            z = warp_sum(z);
-            if (lane == 0) {
-                const float pr = sigmoidf_acc(__fadd_rn(z, b2[0]));
-                T.pred[p] = pr;
-                if (mode == kHeadFused) {
-                    const float tg = T.target[p];
-                    // torch.nn.functional.binary_cross_entropy clamps both logs at -100
-                    loss += -(tg * fmaxf(logf(pr), -100.0f) + (1.0f - tg) * fmaxf(logf(1.0f - pr), -100.0f));
-                    sDz = (pr - tg) / static_cast<float>(G);           // d mean-BCE / d (pre-sigmoid score)
-                } else if (mode == kHeadBackward) {
-                    sDz = T.dpred[p] * pr * (1.0f - pr);               // through the sigmoid (sg_net.py:136)
-                }
-            }
-        }
-        __syncthreads();
-        if (mode == kHeadForward) continue;                            // uniform: every thread of the CTA skips the backward
-        const float dz = sDz;
-        if (tid < 16) sDh[tid] = sHpre[tid] > 0.0f ? dz * w2[tid] : 0.0f;
-        __syncthreads();
-        if (tid < 16) {
-            float s = 0.0f;
-            for (int u = 0; u < 16; ++u) s = fmaf(sDh[u], w1[u * 16 + tid], s);
-            sDs[tid] = sS[tid] > 0.0f ? s : 0.0f;
-        }
-        __syncthreads();
-        const float q0 = e2[tid >> 4] * sDs[part16];               // q[b*16+t] = e2[b] ds[t], bt = tid
-        const float q1 = e2[16 + (tid >> 4)] * sDs[part16];        // bt = tid + 256
-        sQ[tid] = q0;
-        sQ[256 + tid] = q1;
-        // ---- parameter gradients ----
 #pragma unroll
-        for (int m = 0; m < 64; ++m) gW[m] = fmaf(e1[m >> 1], (m & 1) ? q1 : q0, gW[m]);    // flat index tid + 256 m
-#pragma unroll
-        for (int m = 0; m < 4; ++m) { const int e = tid + 256 * m; gV[m] = fmaf(sDs[e >> 6], e12[e & 63], gV[m]); }
-        gW1 = fmaf(sDh[t16], sNt[part16], gW1);
-        if (tid < 16) {
-            gNb += sDs[tid];
-            gB1 += sDh[tid];
-            gW2 = fmaf(dz, sH[tid], gW2);
-        }
-        if (tid == 0) gB2 += dz;
-        __syncthreads();
-        // ---- d loss / d pooled vectors ----
-        for (int u = 0; u < 4; ++u) {                        // de1[a] = sum_bt W[a][bt] q[bt] + sum_t ds[t] V[t][a]
-            const int a = warp * 4 + u;
-            float s = 0.0f;
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) s = fmaf(W[a * 512 + lane + 32 * i], sQ[lane + 32 * i], s);
-            s = warp_sum(s);
-            if (lane == 0) {
-                for (int t = 0; t < 16; ++t) s = fmaf(sDs[t], V[t * 64 + a], s);
-                T.dpooled[static_cast<size_t>(p) * 32 + a] = s;
-            }
-        }
-        if (tid < 32) {                                      // de2[b] = sum_t P[b][t] ds[t] + sum_t ds[t] V[t][32+b]
-            float s = 0.0f;
-            for (int t = 0; t < 16; ++t) s = fmaf(sP[tid * 16 + t], sDs[t], s);
-            for (int t = 0; t < 16; ++t) s = fmaf(sDs[t], V[t * 64 + 32 + tid], s);
-            T.dpooled[(static_cast<size_t>(G) + p) * 32 + tid] = s;
+        for (int m = 0; m < 4; ++m) {                            // d attention.weight_matrix[a][b] += esum[a] dcbar[b], both graphs
+            const int e = tid + 256 * m;
+            gA[m] = fmaf(sSum[0][e >> 5], sDcbar[0][e & 31], gA[m]);
+            gA[m] = fmaf(sSum[1][e >> 5], sDcbar[1][e & 31], gA[m]);
         }
         __syncthreads();
     }
     if (mode == kHeadForward) return;
-    float* row = part + static_cast<size_t>(blockIdx.x) * kHeadFloats;
+    float* row = part_head + static_cast<size_t>(blockIdx.x) * kHeadFloats;
 #pragma unroll
     for (int m = 0; m < 64; ++m) row[tid + 256 * m] = gW[m];
 #pragma unroll
@@ -734,95 +795,26 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_head_kernel(const TrainWs
         row[kHeadFloats - 1] = gB2;
         T.losspart[blockIdx.x] = loss;
     }
-}
-
-// =====================================================================================================================
-// Attention backward + the LeakyReLU of conv_end: gz_end = d loss / d (conv_end BN output), dbeta/dgamma sums.
-// grid = multiple of 2, CTA -> side, loops g.  part: [grid][1024] attention.weight_matrix partials.
-// =====================================================================================================================
-__global__ void __launch_bounds__(kThreads) sgpr_train_att_bwd(const TrainWs T, float* __restrict__ part) {
-    __shared__ float sE[SGPR_MAX_NODES * 33];
-    __shared__ float sYh[SGPR_MAX_NODES * 33];
-    __shared__ float sPrm[4 * 32];
-    __shared__ float sDp[32], sCtx[32], sSum[32], sDcbar[32], sV[32], sAtt[SGPR_MAX_NODES], sDsig[SGPR_MAX_NODES];
-    __shared__ double sRed[8 * 64];
-    const int tid = threadIdx.x;
-    const int side = blockIdx.x % T.S;
-    const int N = T.N;
-    const float* watt = T.state + P_ATT;
-    float gA[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    double accb = 0.0, accg = 0.0;                     // channel tid & 31
-    if (tid < 32) {
-        float mu, istd;
-        bn_coef(stat_ptr(T.stats, side, 6), tid, static_cast<double>(T.G) * N, T.eps, mu, istd);
-        sPrm[tid] = mu;
-        sPrm[32 + tid] = istd;
-        sPrm[64 + tid] = T.state[P_BN + bn_off(6) + tid];
-        sPrm[96 + tid] = T.state[P_BN + bn_off(6) + 32 + tid];
-    }
-    __syncthreads();
-    for (int g = blockIdx.x / T.S; g < T.G; g += gridDim.x / T.S) {
-        const size_t sg = static_cast<size_t>(side) * T.G + g;
-        const float* y = T.yend + sg * N * 32;
-        for (int e = tid; e < N * 32; e += kThreads) {
-            const int n = e >> 5, c = e & 31;
-            const float yh = __fmul_rn(__fsub_rn(y[e], sPrm[c]), sPrm[32 + c]);
-            sYh[n * 33 + c] = yh;
-            sE[n * 33 + c] = lrelu(fmaf(yh, sPrm[64 + c], sPrm[96 + c]));
-        }
-        if (tid < 32) {
-            // mirrored: graph g is e1 of pair g and e2 of pair g ^ 1 — its gradient is the sum over both roles
-            sDp[tid] = T.mirrored ? __fadd_rn(T.dpooled[static_cast<size_t>(g) * 32 + tid],
-                                              T.dpooled[(static_cast<size_t>(T.G) + (g ^ 1)) * 32 + tid])
-                                  : T.dpooled[sg * 32 + tid];
-            sCtx[tid] = T.actx[sg * 32 + tid];
-            sSum[tid] = T.esum[sg * 32 + tid];
-        }
-        if (tid < N) sAtt[tid] = T.att[sg * N + tid];
-        __syncthreads();
-        if (tid < N) {
-            float s = 0.0f;
-            for (int a = 0; a < 32; ++a) s = fmaf(sE[tid * 33 + a], sDp[a], s);
-            const float av = sAtt[tid];
-            sDsig[tid] = s * av * (1.0f - av);
-        }
-        __syncthreads();
-        if (tid < 32) {
-            float s = 0.0f;
-            for (int n = 0; n < N; ++n) s = fmaf(sDsig[n], sE[n * 33 + tid], s);
-            const float c = sCtx[tid];
-            sDcbar[tid] = s * (1.0f - c * c) / static_cast<float>(N);
-        }
-        __syncthreads();
-        if (tid < 32) {
-            float s = 0.0f;
-            for (int b = 0; b < 32; ++b) s = fmaf(sDcbar[b], watt[tid * 32 + b], s);
-            sV[tid] = s;
-        }
-        __syncthreads();
-        float* gzo = T.gzend + sg * N * 32;
-        for (int e = tid; e < N * 32; e += kThreads) {
-            const int n = e >> 5, c = e & 31;
-            const float de = fmaf(sAtt[n], sDp[c], fmaf(sDsig[n], sCtx[c], sV[c]));
-            const float gzv = de * slope_of(sE[n * 33 + c]);
-            gzo[e] = gzv;
-            accb += static_cast<double>(gzv);
-            accg += static_cast<double>(gzv) * static_cast<double>(sYh[n * 33 + c]);
-        }
+    float* arow = part_att + static_cast<size_t>(blockIdx.x) * 1024;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) { const int e = tid + 256 * m; gA[m] = fmaf(sSum[e >> 5], sDcbar[e & 31], gA[m]); }
-        __syncthreads();
-    }
-    float* row = part + static_cast<size_t>(blockIdx.x) * 1024;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) row[tid + 256 * m] = gA[m];
-    sRed[(tid >> 5) * 64 + (tid & 31)] = accb;
-    sRed[(tid >> 5) * 64 + 32 + (tid & 31)] = accg;
+    for (int m = 0; m < 4; ++m) arow[tid + 256 * m] = gA[m];
+    // dbeta / dgamma of the conv_end BatchNorm: warps 0-3 hold graph half 0, warps 4-7 half 1
+    sRed[warp * 64 + lane] = accb;
+    sRed[warp * 64 + 32 + lane] = accg;
     __syncthreads();
-    if (tid < 64) {
-        double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += sRed[w * 64 + tid];
-        atomicAdd(stat_ptr(T.bsum, side, 6) + (tid >> 5) * 64 + (tid & 31), s);
+    if (tid < 128) {
+        const int sd = tid >> 6, which = (tid >> 5) & 1, c = tid & 31;
+        if (T.mirrored) {
+            if (sd == 0) {
+                double s = 0.0;
+                for (int w = 0; w < kWarps; ++w) s += sRed[w * 64 + which * 32 + c];
+                atomicAdd(stat_ptr(T.bsum, 0, 6) + which * 64 + c, s);
+            }
+        } else {
+            double s = 0.0;
+            for (int w = 4 * sd; w < 4 * sd + 4; ++w) s += sRed[w * 64 + which * 32 + c];
+            atomicAdd(stat_ptr(T.bsum, sd, 6) + which * 64 + c, s);
+        }
     }
 }
 
