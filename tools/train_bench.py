@@ -1,5 +1,5 @@
 """Training-step benchmark (BASELINE config 3): `listed` synthetic KITTI-shape pairs -> 2*listed forward pairs (both
-orders, sg_net.py:324-331), N nodes, k neighbours.  Times the device step (sgpr_train_step: 13 launches) with CUDA
+orders, sg_net.py:324-331), N nodes, k neighbours.  Times the device step (sgpr_train_step: 11 launches) with CUDA
 events, inputs resident in HBM, and — optionally — the same step as stock PyTorch ops on the same GPU (the reference's
 own module code path: sg_pr_b200.torch_baseline.forward_torch + loss.backward() + torch.optim.Adam).
 
