@@ -433,25 +433,27 @@ class SGTrainer(object):
             done = self._process_batch_on_device(batch)
             if done is not None:
                 return done
-        f1, f2, targets = [], [], []
+        f1, targets = [], []
         if getattr(self, "_json_cache", None) is None:
             self._json_cache = {}
         for graph_pair in batch:
             data = self.transfer_to_torch(process_pair(graph_pair, self._json_cache), training)
             f1 += [data["features_1"], data["features_2"]]
-            f2 += [data["features_2"], data["features_1"]]
             targets += [data["target"], data["target"]]
-        data = self._stack(f1, f2 if not training else f1[:1], targets)      # a training step reads features_1 only (mirrored)
         if training:
+            # the batch holds every listed pair in both orders (features_2[p] == features_1[p ^ 1] by construction), so
+            # both sides are the same BatchNorm batch: one EdgeConv pass per graph serves both (mirrored step) and
+            # features_2 is never materialised
             eng = self._device_trainer()
             dev = eng.device
-            # the batch holds every listed pair in both orders (features_2[p] == features_1[p ^ 1] by construction just
-            # above), so both sides are the same BatchNorm batch: one EdgeConv pass per graph serves both (mirrored step)
-            loss, prediction = eng.step(data["features_1"].to(dev, non_blocking=True), None,
-                                        data["target"].to(dev, non_blocking=True), int(self.args.K), apply=True,
-                                        mirrored=True)
+            feats = torch.from_numpy(np.asarray(f1, dtype=np.float32))
+            target = torch.from_numpy(np.asarray(targets, dtype=np.float32))
+            loss, prediction = eng.step(feats.to(dev, non_blocking=True), None, target.to(dev, non_blocking=True),
+                                        int(self.args.K), apply=True, mirrored=True)
             self._unsynced_steps += 1
-            return (loss.item(), prediction.cpu().numpy().reshape(-1), data["target"].numpy().reshape(-1))
+            return (loss.item(), prediction.cpu().numpy().reshape(-1), target.numpy().reshape(-1))
+        f2 = [f1[i ^ 1] for i in range(len(f1))]
+        data = self._stack(f1, f2, targets)
         self.sync_model_from_device()
         prediction, _, _ = self.model(data)
         losses = torch.mean(torch.nn.functional.binary_cross_entropy(prediction, data["target"].to(prediction.device)))
