@@ -106,6 +106,7 @@ struct sgpr_train {
     int device = 0;
     int sm_count = 0;
     bool has_state = false;
+    bool wpk_valid = false;        // the packed GEMM copies match d_state (kept current by the optimiser kernel)
     float* d_state = nullptr;      // [STATE_TOTAL]
     float* d_adam = nullptr;       // m | v  [2][P_TOTAL]
     float* d_grads = nullptr;      // [P_TOTAL]
@@ -224,6 +225,7 @@ int sgpr_train_set_state(sgpr_train* t, const float* state_host, int reset_optim
         t->steps = 0;
     }
     t->has_state = true;
+    t->wpk_valid = false;
     return SGPR_OK;
 }
 
@@ -366,8 +368,11 @@ int launch_forward(sgpr_train* t, cudaStream_t st) {
     Plan& P = t->plan;
     const TrainWs& W = P.W;
     TRY_CUDA(cudaMemsetAsync(t->d_sums, 0, kSumDoubles / 2 * sizeof(double), st));
-    SGPR_LAUNCH(sgpr_train_pack_kernel, 32, kThreads, 0, st, W);
-    t->launches += 1;
+    if (!t->wpk_valid) {
+        SGPR_LAUNCH(sgpr_train_pack_kernel, 32, kThreads, 0, st, W);
+        t->launches += 1;
+        t->wpk_valid = true;
+    }
     for (int l = 0; l < 3; ++l) BY_NPL(sgpr_train_edge_fwd, P.grid4, P.fwd_smem, W, l);
     BY_NPL(sgpr_train_end_fwd, P.grid2, P.end_fwd_smem, W);
     return SGPR_OK;
@@ -479,6 +484,7 @@ int sgpr_train_set_state_dev(sgpr_train* t, const float* state_dev, void* stream
     Guard guard(t->device);
     TRY_CUDA(cudaMemcpyAsync(t->d_state, state_dev, STATE_TOTAL * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     t->has_state = true;
+    t->wpk_valid = false;
     return SGPR_OK;
 }
 

@@ -173,26 +173,29 @@ __device__ __forceinline__ int pair_index_dev(int ci, int co, int CO) {       //
 }
 
 // ---- pack: natural conv weights -> channel-pair GEMM layout [cin][A half | B half] ------------------------------------
+// element e of layer L's natural matrix (value v) -> its slots in the packed copies the GEMMs read
+__device__ __forceinline__ void pack_element(float* __restrict__ wpk, int L, int e, float v) {
+    if (L == 6) {                                   // conv_end [32][64]: out f, in c
+        const int f = e >> 6, c = e & 63;
+        wpk[wpk_off(6) + pair_index_dev(c, f, 32)] = v;
+        return;
+    }
+    const int cin = layer_cin(L), cout = layer_cout(L);
+    const int c = e / (2 * cin), col = e % (2 * cin);
+    const int ci = col < cin ? col : col - cin;
+    const int co = col < cin ? c : cout + c;
+    wpk[wpk_off(L) + pair_index_dev(ci, co, 2 * cout)] = v;
+    if (cin == 64)      // transposed halves for the backward: MA[c][ci] = Wa[c][ci], MB[c][ci] = Wb[c][ci]
+        wpk[wt_off(L) + (col < cin ? 0 : cout * 64) + pair_index_dev(c, ci, 64)] = v;
+}
+
+// whole-state pack (after sgpr_train_set_state*); during training the optimiser kernel keeps the copies current
 __global__ void __launch_bounds__(kThreads) sgpr_train_pack_kernel(const TrainWs T) {
     const int stride = gridDim.x * blockDim.x;
     for (int L = 1; L <= 6; ++L) {
-        const int cin = layer_cin(L), cout = layer_cout(L);
         const float* w = T.state + conv_off(L);
-        float* dst = T.wpk + wpk_off(L);
         const int total = conv_size(L);
-        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-            if (L == 6) {                               // conv_end [32][64]: out f, in c
-                const int f = e >> 6, c = e & 63;
-                dst[pair_index_dev(c, f, 32)] = w[e];
-            } else {
-                const int c = e / (2 * cin), col = e % (2 * cin);
-                const int ci = col < cin ? col : col - cin;
-                const int co = col < cin ? c : cout + c;
-                dst[pair_index_dev(ci, co, 2 * cout)] = w[e];
-                if (cin == 64)      // transposed halves: MA[c][ci] = Wa[c][ci], MB[c][ci] = Wb[c][ci]
-                    T.wpk[wt_off(L) + (col < cin ? 0 : cout * 64) + pair_index_dev(c, ci, 64)] = w[e];
-            }
-        }
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) pack_element(T.wpk, L, e, w[e]);
     }
 }
 
@@ -243,6 +246,7 @@ __device__ __forceinline__ void fill_layer_input(const TrainWs& T, int l, int br
         }
     } else {
         const float4* yp = reinterpret_cast<const float4*>(T.yext[L - 1] + (static_cast<size_t>(side) * T.G + g) * N * 64);
+#pragma unroll 4
         for (int e = tid; e < N * 16; e += kThreads) {
             const int n = e >> 4, c = (e & 15) * 4;
             const float4 y = __ldg(yp + e);
@@ -507,6 +511,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_f
         const size_t sg = static_cast<size_t>(side) * T.G + g;
         const float* y2 = T.yext[2] + sg * N * 32;
         const float* y5 = T.yext[5] + sg * N * 32;
+#pragma unroll 4
         for (int e = tid; e < N * 64; e += kThreads) {
             const int n = e >> 6, c = e & 63;
             const float y = c < 32 ? y2[n * 32 + c] : y5[n * 32 + c - 32];
@@ -595,6 +600,7 @@ __global__ void __launch_bounds__(kThreads, 2) sgpr_train_pool_head_kernel(const
         // ---- conv_end BN + LeakyReLU ----
         {
             const float* y = T.yend + sg * N * 32;
+#pragma unroll 4
             for (int e = lt; e < N * 32; e += 128) {
                 const int n = e >> 5, c = e & 31;
                 const float yh = __fmul_rn(__fsub_rn(__ldg(y + e), prm[c]), prm[32 + c]);
@@ -868,6 +874,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_b
         const size_t sg = static_cast<size_t>(side) * T.G + g;
         const float* y2 = T.yext[2] + sg * N * 32;
         const float* y5 = T.yext[5] + sg * N * 32;
+#pragma unroll 4
         for (int e = tid; e < N * 64; e += kThreads) {
             const int n = e >> 6, c = e & 63;
             const float y = c < 32 ? y2[n * 32 + c] : y5[n * 32 + c - 32];
@@ -875,6 +882,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_b
         }
         const float* ye = T.yend + sg * N * 32;
         const float* gze = T.gzend + sg * N * 32;
+#pragma unroll 4
         for (int e = tid; e < N * 32; e += kThreads) {
             const int n = e >> 5, c = e & 31;
             const float yh = __fmul_rn(__fsub_rn(ye[e], sEnd[c]), sEnd[32 + c]);
@@ -883,17 +891,36 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_b
         __syncthreads();
         float* gz2 = T.gz[2] + sg * N * 32;
         float* gz5 = T.gz[5] + sg * N * 32;
-        for (int e = tid; e < N * 64; e += kThreads) {             // d cat[n][c] = sum_f dy[n][f] W[f][c]
-            const int n = e >> 6, c = e & 63;
-            float s = 0.0f;
-#pragma unroll 8
-            for (int f = 0; f < 32; ++f) s = fmaf(sDy[n * DS + f], sWn[f * 64 + c], s);
-            const float gzv = s * slope_of(sX[n * XS + c]);
-            const float yprev = c < 32 ? y2[n * 32 + c] : y5[n * 32 + c - 32];
-            const float yh = __fmul_rn(__fsub_rn(yprev, sPrm[c]), sPrm[64 + c]);
-            if (c < 32) gz2[n * 32 + c] = gzv; else gz5[n * 32 + c - 32] = gzv;
-            accb += static_cast<double>(gzv);
-            accg += static_cast<double>(gzv) * static_cast<double>(yh);
+        {   // d cat[n][c] = sum_f dy[n][f] W[f][c]: a thread owns channel c = tid & 63 and walks nodes four at a time
+            const int c = tid & 63;
+            for (int n0 = (tid >> 6) * 4; n0 < N; n0 += 16) {
+                float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                int nn[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) nn[u] = min(n0 + u, N - 1);
+#pragma unroll
+                for (int f4 = 0; f4 < 8; ++f4) {
+                    const float w0 = sWn[(4 * f4) * 64 + c], w1 = sWn[(4 * f4 + 1) * 64 + c];
+                    const float w2 = sWn[(4 * f4 + 2) * 64 + c], w3 = sWn[(4 * f4 + 3) * 64 + c];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 dy = *reinterpret_cast<const float4*>(sDy + nn[u] * DS + 4 * f4);
+                        s[u] = fmaf(dy.w, w3, fmaf(dy.z, w2, fmaf(dy.y, w1, fmaf(dy.x, w0, s[u]))));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = n0 + u;
+                    if (n < N) {
+                        const float gzv = s[u] * slope_of(sX[n * XS + c]);
+                        const float yprev = c < 32 ? y2[n * 32 + c] : y5[n * 32 + c - 32];
+                        const float yh = __fmul_rn(__fsub_rn(yprev, sPrm[c]), sPrm[64 + c]);
+                        if (c < 32) gz2[n * 32 + c] = gzv; else gz5[n * 32 + c - 32] = gzv;
+                        accb += static_cast<double>(gzv);
+                        accg += static_cast<double>(gzv) * static_cast<double>(yh);
+                    }
+                }
+            }
         }
         for (int n = 0; n < N; ++n) {                              // dW_end[f][c] += dy[n][f] cat[n][c]
             const float2 dy = *reinterpret_cast<const float2*>(sDy + n * DS + f0);
@@ -1053,6 +1080,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
             const float4* gd = reinterpret_cast<const float4*>(T.d[L] + o);
             const uint32_t* en = reinterpret_cast<const uint32_t*>(T.enode[L] + o);
             const int q4 = cout >> 2;                        // float4 groups per node
+#pragma unroll 4
             for (int e = tid; e < N * q4; e += kThreads) {
                 const int n = e / q4, c = (e - n * q4) * 4;
                 *reinterpret_cast<float4*>(sGZ + n * XS + c) = __ldg(gz + e);
@@ -1317,7 +1345,13 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
             T.adam_m[e] = m;
             T.adam_v[e] = v;
             const float denom = sqrtf(v) / A.bc2_sqrt + A.eps;
-            T.state[e] = p - (A.lr / A.bc1) * (m / denom);
+            const float pn = p - (A.lr / A.bc1) * (m / denom);
+            T.state[e] = pn;
+            if (e >= P_S2W && e < P_BN) {               // a GEMM weight: refresh its packed copies (xyz layer 1 is read natural)
+                int L = 6;
+                while (conv_off(L) > e) --L;
+                pack_element(T.wpk, L, e - conv_off(L), pn);
+            }
         }
     } else if (e < STATE_TOTAL && A.apply != kApplyNone) {
         int L = 6;

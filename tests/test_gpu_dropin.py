@@ -194,7 +194,7 @@ def test_device_augment_training_path(tree):
     # a fresh augmentation every step on 4 listed pairs: the loss is noisy, so only finiteness and movement are asserted
     assert all(np.isfinite(l) for l in losses) and len(set(round(l, 6) for l in losses)) > 1
     assert not torch.equal(before, trainer._train_engine.get_state()["dgcnn_s_conv2.0.weight"])
-    assert trainer._train_engine.launch_count() == launches + 8 * 12                          # assemble + 11 per step
+    assert trainer._train_engine.launch_count() == launches + 8 * 11                          # assemble + 10 per step
     assert trainer._dev_graphs["count"] == 3
     model_loss, f1 = trainer.score("eval")
     assert np.isfinite(model_loss) and 0.0 <= f1 <= 1.0
