@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_pack_kernel(const TrainWs
 }
 
 // ---- shared-memory carve-outs ----------------------------------------------------------------------------------------
-struct FwdSmem { int w, x, y, xx, idx, cnt, deg, prm, stat, total; };
+struct FwdSmem { int w, x, y, xx, idx, cnt, prm, stat, total; };
 __host__ __device__ inline FwdSmem fwd_layout(int nmax, int ks) {
     FwdSmem L;
     int o = 0;
@@ -210,7 +210,6 @@ __host__ __device__ inline FwdSmem fwd_layout(int nmax, int ks) {
     L.xx = o;   o += nmax * 4;
     L.idx = o;  o += ((nmax * ks * 2 + 15) / 16) * 16;
     L.cnt = o;  o += ((nmax + 15) / 16) * 16;
-    L.deg = o;  o += nmax * 4;                           // how many neighbour lists hold each node
     L.prm = o;  o += 4 * 64 * 4;
     L.stat = o; o += kWarps * 128 * 8;
     L.total = o;
@@ -262,17 +261,16 @@ __device__ __forceinline__ void fill_layer_input(const TrainWs& T, int l, int br
 }
 
 // gather over the neighbour lists for own rows: extreme / arg-extreme of A_j and the sums of y_ij = (A_j - A_i) + B_i.
-// The A half of the tile is SIGN-FOLDED (sign bit flipped where gamma < 0, done once per row after the GEMM): the extreme
-// is then always a max (min == max of the negated values, exact), and sum_j A_j is the negated sum of the folded values
-// (exact as well).  List entries are the neighbours' word offsets j*YS.  With D = B_i - A_i
-//     sum_j y = SA + k D,      sum_ij y^2 = sum_n deg_n A_n^2 + sum_i (2 D_i SA_i + k D_i^2)
-// where deg_n counts the lists that hold n — so the per-edge work is one add and one max/arg-max per channel.
+// Per edge and channel only sum A_j and sum A_j^2 are accumulated; with D = B_i - A_i
+//     sum_j y = SA + k D,      sum_j y^2 = SA2 + 2 D SA + k D^2
+// (all terms are O(k) for BatchNorm-scaled features, so the expansion costs ~3 ulp of the sum).  The extreme is a max of
+// sign-folded values (sign bit flipped where gamma < 0: min == max of the negated values, exact).
 template <int COUT>
 __device__ __forceinline__ void train_gather_rows(const float* __restrict__ sY, const uint16_t* __restrict__ sIdx, int KS,
-                                                  int k, const int* __restrict__ sDeg, const float* __restrict__ gamma,
-                                                  float* __restrict__ yext, float* __restrict__ ga, float* __restrict__ gd,
-                                                  float* __restrict__ gsum, uint8_t* __restrict__ enode, int r0, int r1,
-                                                  int lane, double (&acc1)[2], double (&acc2)[2]) {
+                                                  int k, const float* __restrict__ gamma, float* __restrict__ yext,
+                                                  float* __restrict__ ga, float* __restrict__ gd, float* __restrict__ gsum,
+                                                  uint8_t* __restrict__ enode, int r0, int r1, int lane,
+                                                  double (&acc1)[2], double (&acc2)[2]) {
     constexpr int CPL = COUT / 32;
     uint32_t flip[CPL];
 #pragma unroll
@@ -280,43 +278,43 @@ __device__ __forceinline__ void train_gather_rows(const float* __restrict__ sY, 
     const float kf = static_cast<float>(k);
     const float* base = sY + lane * CPL;
     for (int i = r0; i < r1; ++i) {
-        float best[CPL], sa[CPL];
-        int bo[CPL];
+        float best[CPL], sa[CPL], sa2[CPL];
+        int bj[CPL];
 #pragma unroll
-        for (int p = 0; p < CPL; ++p) { best[p] = -INFINITY; sa[p] = 0.0f; bo[p] = 0; }
+        for (int p = 0; p < CPL; ++p) { best[p] = -INFINITY; sa[p] = 0.0f; sa2[p] = 0.0f; bj[p] = 0; }
         const uint16_t* list = sIdx + i * KS;
 #pragma unroll 4
         for (int e = 0; e < k; ++e) {
-            const int off = list[e];
+            const int j = list[e];
             float v[CPL];
             if constexpr (CPL == 2) {
-                const float2 t = *reinterpret_cast<const float2*>(base + off);
+                const float2 t = *reinterpret_cast<const float2*>(base + j * YS);
                 v[0] = t.x; v[1] = t.y;
             } else {
-                v[0] = base[off];
+                v[0] = base[j * YS];
             }
 #pragma unroll
             for (int p = 0; p < CPL; ++p) {
                 sa[p] = __fadd_rn(sa[p], v[p]);
-                bo[p] = v[p] > best[p] ? off : bo[p];
-                best[p] = fmaxf(best[p], v[p]);
+                sa2[p] = fmaf(v[p], v[p], sa2[p]);
+                const float vs = __uint_as_float(__float_as_uint(v[p]) ^ flip[p]);
+                bj[p] = vs > best[p] ? j : bj[p];
+                best[p] = fmaxf(best[p], vs);
             }
         }
-        const float degf = static_cast<float>(sDeg[i]);
 #pragma unroll
         for (int p = 0; p < CPL; ++p) {
             const size_t o = static_cast<size_t>(i) * COUT + lane * CPL + p;
-            const float ai = __uint_as_float(__float_as_uint(base[i * YS + p]) ^ flip[p]), bi = base[i * YS + COUT + p];
+            const float ai = base[i * YS + p], bi = base[i * YS + COUT + p];
             const float dv = __fsub_rn(bi, ai);
             const float ext = __uint_as_float(__float_as_uint(best[p]) ^ flip[p]);
-            const float sav = __uint_as_float(__float_as_uint(sa[p]) ^ flip[p]);
-            const float s1 = fmaf(kf, dv, sav);
-            const float s2 = fmaf(degf * ai, ai, fmaf(kf * dv, dv, 2.0f * dv * sav));
+            const float s1 = fmaf(kf, dv, sa[p]);
+            const float s2 = fmaf(kf * dv, dv, fmaf(2.0f * dv, sa[p], sa2[p]));
             yext[o] = __fadd_rn(__fsub_rn(ext, ai), bi);
             ga[o] = ai;
             gd[o] = dv;
             gsum[o] = s1;
-            enode[o] = static_cast<uint8_t>(bo[p] / YS);
+            enode[o] = static_cast<uint8_t>(bj[p]);
             acc1[p] += static_cast<double>(s1);
             acc2[p] += static_cast<double>(s2);
         }
@@ -350,8 +348,8 @@ __device__ __forceinline__ void train_xyz_rows(const float* __restrict__ sX, con
         const uint16_t* list = sIdx + i * KS;
 #pragma unroll 4
         for (int e = 0; e < k; ++e) {
-            const int j = list[e];                                   // word offset of the neighbour's row (node * XS)
-            const float4 xj = *reinterpret_cast<const float4*>(sX + j);
+            const int j = list[e];
+            const float4 xj = *reinterpret_cast<const float4*>(sX + j * XS);
             const float d0 = __fsub_rn(xj.x, xi.x), d1 = __fsub_rn(xj.y, xi.y), d2 = __fsub_rn(xj.z, xi.z);
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
@@ -375,7 +373,7 @@ __device__ __forceinline__ void train_xyz_rows(const float* __restrict__ sX, con
             ga[o] = av;
             gd[o] = __fsub_rn(cb, av);
             gsum[o] = s1;
-            enode[o] = static_cast<uint8_t>(bj[p] / XS);
+            enode[o] = static_cast<uint8_t>(bj[p]);
             acc1[p] += static_cast<double>(s1);
             acc2[p] += static_cast<double>(s2);
         }
@@ -415,7 +413,6 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     float* sXX = reinterpret_cast<float*>(smem + S.xx);
     uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + S.idx);
     uint8_t* sCnt = smem + S.cnt;
-    int* sDeg = reinterpret_cast<int*>(smem + S.deg);
     float* sPrm = reinterpret_cast<float*>(smem + S.prm);
     double* sStat = reinterpret_cast<double*>(smem + S.stat);
 
@@ -439,35 +436,24 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
     const int rpw = (N + kWarps - 1) / kWarps;
     const int w0 = min(N, warp * rpw), w1 = min(N, w0 + rpw);
     const float* gamma = T.state + P_BN + bn_off(L);
-    const int cpl = cout >> 5;                                   // channels per lane: lane*cpl, lane*cpl + 1
-    const bool neg0 = gamma[lane * cpl] < 0.0f, neg1 = cpl == 2 && gamma[lane * cpl + 1] < 0.0f;
     double acc1[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};
 
     for (int g = (blockIdx.x >> 1) / T.S; g < T.G; g += (gridDim.x >> 1) / T.S) {
         const size_t sg = static_cast<size_t>(side) * T.G + g;
         fill_layer_input(T, l, br, side, g, sX, sPrm, tid);
-        for (int e = tid; e < N; e += kThreads) sDeg[e] = 0;
         __syncthreads();
         norms_rows(sX, sXX, cin4, w0, w1, lane);
         __syncthreads();
         // ---- front: distance rows -> k-NN selection -> per-node GEMM rows, for own rows ----
-        const int scale = direct ? XS : YS;                  // list entries = word offset of the neighbour's row in the gathered tile
         for (int r0 = w0; r0 < w1; r0 += 8) {
             const int nr = min(8, w1 - r0);
             SGPR_NR_SWITCH(nr, (gram_rows<NPL, NPL, NR>(sX, sXX, sY, cin4, N, N, r0, lane)))
             __syncwarp();
-            select_rows<NPL>(sY, sIdx, sCnt, nullptr, N, N, k, KS, scale, r0, nr, lane);
+            select_rows<NPL>(sY, sIdx, sCnt, nullptr, N, N, k, KS, 1, r0, nr, lane);
             __syncwarp();
             if (!direct) {
                 if (cout == 64) { SGPR_NR_SWITCH(nr, (gemm_rows<NR, 4, 0>(sX, sW, sY, YS, nullptr, cin4, r0, lane))) }
                 else            { SGPR_NR_SWITCH(nr, (gemm_rows<NR, 2, 0>(sX, sW, sY, YS, nullptr, cin4, r0, lane))) }
-                __syncwarp();
-                // sign-fold the A half of own rows (a lane flips exactly the entries it wrote) and count list memberships
-                for (int r = r0; r < r0 + nr; ++r) {
-                    if (neg0) sY[r * YS + lane * cpl] = -sY[r * YS + lane * cpl];
-                    if (neg1) sY[r * YS + lane * cpl + 1] = -sY[r * YS + lane * cpl + 1];
-                    for (int e = lane; e < k; e += 32) atomicAdd(&sDeg[sIdx[r * KS + e] / YS], 1);
-                }
             }
         }
         __syncthreads();
@@ -477,15 +463,14 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
             train_xyz_rows(sX, sIdx, KS, k, sW, gamma, T.yext[L] + o, T.a[L] + o, T.d[L] + o, T.sumy[L] + o, T.enode[L] + o,
                            w0, w1, lane, acc1, acc2);
         else if (cout == 64)
-            train_gather_rows<64>(sY, sIdx, KS, k, sDeg, gamma, T.yext[L] + o, T.a[L] + o, T.d[L] + o, T.sumy[L] + o,
+            train_gather_rows<64>(sY, sIdx, KS, k, gamma, T.yext[L] + o, T.a[L] + o, T.d[L] + o, T.sumy[L] + o,
                                   T.enode[L] + o, w0, w1, lane, acc1, acc2);
         else
-            train_gather_rows<32>(sY, sIdx, KS, k, sDeg, gamma, T.yext[L] + o, T.a[L] + o, T.d[L] + o, T.sumy[L] + o,
+            train_gather_rows<32>(sY, sIdx, KS, k, gamma, T.yext[L] + o, T.a[L] + o, T.d[L] + o, T.sumy[L] + o,
                                   T.enode[L] + o, w0, w1, lane, acc1, acc2);
         uint8_t* gi = T.idx[L] + sg * N * k;
         for (int i = w0; i < w1; ++i)
-            for (int e = lane; e < k; e += 32)
-                gi[i * k + e] = static_cast<uint8_t>(direct ? sIdx[i * KS + e] / XS : sIdx[i * KS + e] / YS);
+            for (int e = lane; e < k; e += 32) gi[i * k + e] = static_cast<uint8_t>(sIdx[i * KS + e]);
         __syncthreads();
     }
     flush_channel_sums(sStat, stat_ptr(T.stats, side, L), acc1, acc2, cout / 32, cout, tid);
