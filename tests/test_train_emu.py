@@ -83,3 +83,11 @@ def test_emulated_batch_assembly_matches_host_augmentation(emu_lib, monkeypatch)
     eng = TrainEngine(lib=emu_lib)
     ac.check_assemble(eng, "cpu", monkeypatch, M=8, N=32, P=5)
     eng.close()
+
+
+def test_emulated_gradients_match_reference_at_64_nodes(emu_lib):
+    """The headline shape (N = 64, k = 20: two 32-column blocks per distance row, the NPL = 2 kernels), mirrored step."""
+    g, sd = tc.load_case("n64_k20")
+    eng = TrainEngine(lib=emu_lib)
+    tc.check_gradients(eng, g, sd, "cpu", pred_tol=5e-5, mirrored=True)
+    eng.close()
