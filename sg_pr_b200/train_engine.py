@@ -45,8 +45,15 @@ class TrainEngine:
     def __init__(self, device=0, lib=None):
         self._lib = lib or _lib.load()
         self._emulated = lib is not None           # tests/emu only: buffers are host memory
-        self.device = torch.device("cpu") if self._emulated else torch.device("cuda", int(torch.device(device).index or 0)
-                                                                              if not isinstance(device, int) else device)
+        if self._emulated:
+            self.device = torch.device("cpu")
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError("sg_pr_b200 needs a CUDA device (B200, sm_100a); the training step has no CPU path")
+            dev = torch.device(f"cuda:{device}" if isinstance(device, int) else device)
+            if dev.type != "cuda":
+                raise RuntimeError(f"sg_pr_b200 training engine cannot run on {dev}")
+            self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.layout, self.n_param_tensors = layout(self._lib)
         self.n_params = int(self._lib.sgpr_train_param_count())
         self.n_state = int(self._lib.sgpr_train_state_count())

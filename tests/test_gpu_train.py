@@ -48,7 +48,7 @@ def test_mirrored_equals_two_sided(eng, kitti_state):
         eng.step(f1[:3].cuda(), None, target[:3].cuda(), 20, mirrored=True)
 
 
-@pytest.mark.parametrize("N,k,listed", [(100, 10, 6), (30, 7, 5), (128, 20, 3)])
+@pytest.mark.parametrize("N,k,listed", [(100, 10, 6), (30, 7, 5), (128, 20, 3), (64, 40, 3)])
 def test_step_matches_live_oracle(eng, kitti_state, N, k, listed):
     """Shapes without golden vectors (the shipped config N=100/k=10, ragged N, the largest N): one full step vs the
     oracle's autograd + Adam on the CPU."""
@@ -166,3 +166,8 @@ def test_module_forward_in_train_mode_is_an_autograd_node(kitti_state):
     with torch.no_grad():
         s, _, _ = model(data)
     assert s.shape == (8,) and bool(torch.isfinite(s).all())
+
+
+@pytest.mark.parametrize("B,N,k", [(5, 32, 10), (7, 64, 20)])
+def test_general_two_sided_batch(eng, kitti_state, B, N, k):
+    tc.check_general_two_sided_batch(eng, kitti_state, "cuda", B=B, N=N, k=k)

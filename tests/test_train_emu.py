@@ -91,3 +91,9 @@ def test_emulated_gradients_match_reference_at_64_nodes(emu_lib):
     eng = TrainEngine(lib=emu_lib)
     tc.check_gradients(eng, g, sd, "cpu", pred_tol=5e-5, mirrored=True)
     eng.close()
+
+
+def test_emulated_general_two_sided_batch(emu_lib, kitti_state):
+    eng = TrainEngine(lib=emu_lib)
+    tc.check_general_two_sided_batch(eng, kitti_state, "cpu", B=3, N=32, k=10)
+    eng.close()

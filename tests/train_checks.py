@@ -110,3 +110,29 @@ def check_split_forward_backward(eng, g, sd, device, pred_tol, mirrored=False):
     flat_state = eng.get_state_flat()
     eng.set_state_flat(flat_state)
     assert torch.equal(eng.get_state_flat(), flat_state)
+
+
+def check_general_two_sided_batch(eng, sd, device, B=5, N=32, k=10, seed=31):
+    """features_2 unrelated to features_1 (odd batch, different graphs per side): each side is its own BatchNorm batch
+    with its own statistics.  One applied step vs the oracle's autograd + Adam."""
+    from oracle import sgpr_oracle_train as ort
+    from sg_pr_b200 import synth
+    f1, _ = synth.make_pair_batch(B, N, k, seed=seed)
+    f2, _ = synth.make_pair_batch(B, N, k, seed=seed + 1)
+    target = (torch.arange(B) % 2).float()
+    work = {n: v.clone() for n, v in sd.items()}
+    want = ort.train_step(work, f1, f2, target, k, ort.new_adam_state(work), 1e-3, 5e-4)
+    eng.set_state(sd, reset_optimizer=True)
+    eng.set_optimizer(1e-3, 5e-4)
+    loss, pred = eng.step(f1.to(device), f2.to(device), target.to(device), k, apply=True)
+    np.testing.assert_allclose(pred.cpu().numpy(), want["pred"].numpy(), rtol=0, atol=5e-5)
+    assert abs(float(loss) - want["loss"]) < 5e-5
+    grads = eng.grads()
+    for name, ref in want["grads"].items():
+        scale = max(float(ref.abs().max()), 1e-8)
+        assert float((grads[name].reshape(ref.shape) - ref).abs().max()) <= 2e-3 * scale, name
+    state = eng.get_state()
+    for name, value in state.items():
+        if "running_" in name:            # side 1 then side 2, each with its own batch statistics
+            ref = work[name]
+            assert float((value.reshape(ref.shape) - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), name
