@@ -1,7 +1,5 @@
 // C-ABI implementation (include/sgpr_b200.h): context, weight packing/upload, kernel launches.
 // No torch types, links only cudart.  There is deliberately no CPU path: every entry point needs the device.
-#include <cuda_runtime.h>
-
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -254,16 +252,16 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
         const int resident = (a.G <= capacity) ? 1 : 0;
         int ogrid = (a.G + kWarps - 1) / kWarps;
         if (ogrid > 4 * ctx->sm_count) ogrid = 4 * ctx->sm_count;
-        sgpr_order_kernel<<<ogrid, kThreads, 0, st>>>(a.g0, a.g1, a.pairs, a.G, a.N, a.dedup, ctx->sm_count, resident,
-                                                     ctx->d_order, ctx->d_order + a.G, ctx->d_ctrs, ctx->d_ctrs + 1);
+        SGPR_LAUNCH(sgpr_order_kernel, ogrid, kThreads, 0, st, a.g0, a.g1, a.pairs, a.G, a.N, a.dedup, ctx->sm_count, resident,
+                    ctx->d_order, ctx->d_order + a.G, ctx->d_ctrs, ctx->d_ctrs + 1);
         ctx->launches += 1;
         a.order = ctx->d_order + a.G;
         if (!resident) a.work_ctr = ctx->d_ctrs + 1;
     }
     switch (npl) {
-        case 1: sgpr_embed_kernel<1><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
-        case 2: sgpr_embed_kernel<2><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
-        default: sgpr_embed_kernel<4><<<grid, kThreads, L.total, st>>>(a, ctx->pw, ctx->hp); break;
+        case 1: SGPR_LAUNCH(sgpr_embed_kernel<1>, grid, kThreads, L.total, st, a, ctx->pw, ctx->hp); break;
+        case 2: SGPR_LAUNCH(sgpr_embed_kernel<2>, grid, kThreads, L.total, st, a, ctx->pw, ctx->hp); break;
+        default: SGPR_LAUNCH(sgpr_embed_kernel<4>, grid, kThreads, L.total, st, a, ctx->pw, ctx->hp); break;
     }
     ctx->launches += 1;
     cudaError_t e = cudaGetLastError();
@@ -379,8 +377,8 @@ int sgpr_score_pairs(sgpr_ctx* ctx, const float* pooled_dev, const int32_t* pair
     if (!pooled_dev || !pair_idx_dev || !score_dev) return fail(SGPR_E_INVALID, "sgpr_score_pairs: NULL pointer");
     DeviceGuard guard(ctx->device);
     const int grid = P < ctx->sm_count * 8 ? P : ctx->sm_count * 8;
-    sgpr_score_pairs_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(pooled_dev, pair_idx_dev, P, score_dev,
-                                                                                      ctx->pw, ctx->hp);
+    SGPR_LAUNCH(sgpr_score_pairs_kernel, grid, kThreads, 0, static_cast<cudaStream_t>(stream), pooled_dev, pair_idx_dev, P,
+                score_dev, ctx->pw, ctx->hp);
     ctx->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return SGPR_OK;
@@ -403,12 +401,13 @@ int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const 
     float* rowblk = ctx->d_blk;
     float* colblk = ctx->d_blk + static_cast<size_t>(R) * kT;
     const int cap = ctx->sm_count * 8;
-    sgpr_ntn_prep_kernel<<<R < cap ? R : cap, kThreads, 0, st>>>(pooled_rows_dev, R, ctx->d_proj, rowblk, nullptr, ctx->pw);
-    sgpr_ntn_prep_kernel<<<M < cap ? M : cap, kThreads, 0, st>>>(pooled_cols_dev, M, nullptr, nullptr, colblk, ctx->pw);
+    float* const no_out = nullptr;
+    SGPR_LAUNCH(sgpr_ntn_prep_kernel, R < cap ? R : cap, kThreads, 0, st, pooled_rows_dev, R, ctx->d_proj, rowblk, no_out, ctx->pw);
+    SGPR_LAUNCH(sgpr_ntn_prep_kernel, M < cap ? M : cap, kThreads, 0, st, pooled_cols_dev, M, no_out, no_out, colblk, ctx->pw);
     const dim3 grid((M + kSmTJ - 1) / kSmTJ, (R + kSmTI - 1) / kSmTI);
     const size_t smem = (kSmTI * 512 + kSmTI * kT) * sizeof(float);
-    sgpr_score_matrix_kernel<<<grid, kThreads, smem, st>>>(ctx->d_proj, rowblk, pooled_cols_dev, colblk, R, M, scores_dev,
-                                                           static_cast<long long>(ld_scores), ctx->pw.ntn_b, ctx->hp);
+    SGPR_LAUNCH(sgpr_score_matrix_kernel, grid, kThreads, smem, st, ctx->d_proj, rowblk, pooled_cols_dev, colblk, R, M, scores_dev,
+                static_cast<long long>(ld_scores), ctx->pw.ntn_b, ctx->hp);
     ctx->launches += 3;
     CUDA_TRY(cudaGetLastError());
     return SGPR_OK;

@@ -62,7 +62,34 @@ struct HeadParams {
     float fc2_b;
 };
 
-#ifndef SGPR_EMU
+// Kernel launch / dynamic shared memory spelled once for nvcc and for the host-compiler emulator build of tests/emu
+#ifdef SGPR_EMU
+#define SGPR_LAUNCH(kern, grid, block, smem, st, ...) emu::launch((grid), (block), (smem), [=] { kern(__VA_ARGS__); })
+#define SGPR_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#else
+#define SGPR_LAUNCH(kern, grid, block, smem, st, ...) kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__)
+#define SGPR_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
+#ifdef SGPR_EMU
+// tests/emu: an mbarrier is one 64-bit word (bit 0 = phase parity, the rest = bytes still expected); a bulk copy is a
+// memcpy by the issuing thread that completes the transaction count.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { std::atomic_ref<uint64_t>(*bar).store(0); }
+__device__ __forceinline__ void fence_mbar_init() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    std::atomic_ref<uint64_t>(*bar).fetch_add(static_cast<uint64_t>(bytes) << 1);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    std::memcpy(dst_smem, src_gmem, bytes);
+    std::atomic_ref<uint64_t> b(*bar);
+    const uint64_t left = b.fetch_sub(static_cast<uint64_t>(bytes) << 1) - (static_cast<uint64_t>(bytes) << 1);
+    if ((left >> 1) == 0) b.fetch_xor(1);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    std::atomic_ref<uint64_t> b(*bar);
+    while ((b.load() & 1u) == parity) std::this_thread::yield();
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

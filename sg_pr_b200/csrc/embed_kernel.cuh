@@ -716,7 +716,6 @@ struct FrontCtx {
         default: { constexpr int NR = 8; CALL; } break;                                            \
     }
 
-#ifndef SGPR_EMU   // everything below stages data with bulk TMA + mbarriers: device builds only
 // front of one pass (up to 8 own rows): distance rows -> selection -> GEMM rows.  Only the row-tiled pieces are
 // specialised on the row count; the selection network exists once.
 template <int NPL>
@@ -753,7 +752,7 @@ template <int NPL>
 __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? SGPR_MINBLOCKS_SMALL : 1)
 sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) {
     constexpr int NMAX = 32 * NPL;
-    extern __shared__ __align__(128) unsigned char smem[];
+    SGPR_DYN_SMEM(smem);
     const SmemLayout L = make_layout(NMAX, A.KS);
     float* sW = reinterpret_cast<float*>(smem + L.w);
     float* sIn = reinterpret_cast<float*>(smem + L.in);
@@ -1019,7 +1018,5 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
     }
 #endif
 }
-
-#endif  // !SGPR_EMU
 
 }  // namespace sgpr

@@ -135,7 +135,8 @@ sgpr_score_matrix_kernel(const float* __restrict__ proj, const float* __restrict
                          const float* __restrict__ pooled_cols, const float* __restrict__ colblk, int R, int M,
                          float* __restrict__ scores, long long ld, const float* __restrict__ ntn_b,
                          const HeadParams H) {
-    extern __shared__ __align__(16) float sm[];
+    SGPR_DYN_SMEM(sm_raw);
+    float* sm = reinterpret_cast<float*>(sm_raw);
     float* sP = sm;                       // [TI][512]
     float* sRB = sm + kSmTI * 512;        // [TI][16]  rowblk + bias
     const int tid = threadIdx.x;

@@ -15,19 +15,7 @@
 using namespace sgpr;
 using namespace sgpr::train;
 
-#ifdef SGPR_EMU
-namespace { thread_local char g_emu_err[512] = ""; }
-extern "C" const char* sgpr_last_error(void) { return g_emu_err; }
-int sgpr_fail(int code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_emu_err, sizeof(g_emu_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-#else
 int sgpr_fail(int code, const char* fmt, ...);      // api.cu: sets the text sgpr_last_error() returns
-#endif
 
 namespace {
 

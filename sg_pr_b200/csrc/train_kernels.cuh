@@ -29,14 +29,6 @@
 #include "common.cuh"
 #include "embed_kernel.cuh"
 
-#ifdef SGPR_EMU
-#define SGPR_LAUNCH(kern, grid, block, smem, st, ...) emu::launch((grid), (block), (smem), [=] { kern(__VA_ARGS__); })
-#define SGPR_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
-#else
-#define SGPR_LAUNCH(kern, grid, block, smem, st, ...) kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__)
-#define SGPR_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
-#endif
-
 namespace sgpr {
 namespace train {
 

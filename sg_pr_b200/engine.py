@@ -103,16 +103,23 @@ def _check_graphs(t: torch.Tensor, what: str) -> Tuple[int, int]:
 class Engine:
     """Owns one sgpr_ctx (device-bound packed weights + scratch)."""
 
-    def __init__(self, device: int | torch.device | str = 0):
-        if not torch.cuda.is_available():
-            raise RuntimeError("sg_pr_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
-        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
-        if dev.type != "cuda":
-            raise RuntimeError(f"sg_pr_b200 engine cannot run on {dev}")
-        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
-        self._lib = _lib.load()
+    def __init__(self, device: int | torch.device | str = 0, lib=None):
+        """`lib`: tests/emu only — the emulator build of the same sources, with host memory standing in for the device.
+        The product never passes it: without a CUDA device the constructor raises."""
+        self._emulated = lib is not None
+        if self._emulated:
+            self.device = torch.device("cpu")
+            self._lib = lib
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError("sg_pr_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+            dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+            if dev.type != "cuda":
+                raise RuntimeError(f"sg_pr_b200 engine cannot run on {dev}")
+            self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+            self._lib = _lib.load()
         handle = C.c_void_p()
-        check(self._lib.sgpr_create(C.byref(handle), self.device.index), "sgpr_create")
+        check(self._lib.sgpr_create(C.byref(handle), 0 if self._emulated else self.device.index), "sgpr_create", self._lib)
         self._ctx = handle
         self.has_weights = False
 
@@ -130,7 +137,7 @@ class Engine:
     # ---- weights ------------------------------------------------------------------------------------------
     def set_weights(self, state: Dict[str, torch.Tensor], bn_eps: float = 1e-5):
         w, keep = weights_struct(state, bn_eps)
-        check(self._lib.sgpr_set_weights(self._ctx, C.byref(w)), "sgpr_set_weights")
+        check(self._lib.sgpr_set_weights(self._ctx, C.byref(w)), "sgpr_set_weights", self._lib)
         del keep
         self.has_weights = True
 
@@ -138,6 +145,8 @@ class Engine:
         return int(self._lib.sgpr_launch_count(self._ctx))
 
     def _stream(self) -> C.c_void_p:
+        if self._emulated:
+            return None
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _dev(self, t: torch.Tensor, what: str, allow_pinned: bool = False) -> torch.Tensor:
@@ -165,7 +174,7 @@ class Engine:
         check(self._lib.sgpr_forward_pairs(self._ctx, f1.data_ptr(), f2.data_ptr(), b, n, int(k), score.data_ptr(),
                                            att1.data_ptr() if want_att else None,
                                            att2.data_ptr() if want_att else None, self._stream()),
-              "sgpr_forward_pairs")
+              "sgpr_forward_pairs", self._lib)
         return score, att1, att2
 
     def forward_pairs_host(self, f1: torch.Tensor, f2: torch.Tensor, k: int, want_att: bool = True,
@@ -184,7 +193,7 @@ class Engine:
         check(self._lib.sgpr_forward_pairs_host(self._ctx, f1.data_ptr(), f2.data_ptr(), b, n, int(k), score.data_ptr(),
                                                 att1.data_ptr() if att1 is not None else None,
                                                 att2.data_ptr() if att2 is not None else None),
-              "sgpr_forward_pairs_host")
+              "sgpr_forward_pairs_host", self._lib)
         return score, att1, att2
 
     # ---- embed-once / score-many ------------------------------------------------------------------------------
@@ -202,7 +211,7 @@ class Engine:
             out["layers"] = torch.zeros(m, 6, n, 64, dtype=torch.float32, device=self.device)
         p = lambda key: out[key].data_ptr() if key in out else None
         check(self._lib.sgpr_embed_trace(self._ctx, graphs.data_ptr(), m, n, int(k), p("pooled"), p("att"), p("emb"),
-                                         p("knn"), p("layers"), self._stream()), "sgpr_embed")
+                                         p("knn"), p("layers"), self._stream()), "sgpr_embed", self._lib)
         return out
 
     def score_pairs(self, pooled: torch.Tensor, pair_idx: torch.Tensor) -> torch.Tensor:
@@ -211,7 +220,7 @@ class Engine:
         p = int(idx.shape[0])
         score = torch.empty(p, dtype=torch.float32, device=self.device)
         check(self._lib.sgpr_score_pairs(self._ctx, pooled.data_ptr(), idx.data_ptr(), p, score.data_ptr(), self._stream()),
-              "sgpr_score_pairs")
+              "sgpr_score_pairs", self._lib)
         return score
 
     def score_matrix(self, pooled_rows: torch.Tensor, pooled_cols: torch.Tensor, out: Optional[torch.Tensor] = None):
@@ -222,5 +231,5 @@ class Engine:
         if out.shape != (r, m) or out.stride(1) != 1 or out.device != self.device or out.dtype != torch.float32:
             raise ValueError("score_matrix: `out` must be a float32 [R, M] device tensor with unit column stride")
         check(self._lib.sgpr_score_matrix(self._ctx, rows.data_ptr(), r, cols.data_ptr(), m, out.data_ptr(),
-                                          int(out.stride(0)) if r > 0 else m, self._stream()), "sgpr_score_matrix")
+                                          int(out.stride(0)) if r > 0 else m, self._stream()), "sgpr_score_matrix", self._lib)
         return out

@@ -1,14 +1,16 @@
 // TEST INFRASTRUCTURE ONLY — a minimal CUDA execution-model emulator for the host compiler.
 //
 // Purpose: this repo is developed in a container without a GPU and with a small budget of B200 minutes.  To debug the
-// training kernels (sg_pr_b200/csrc/train_kernels.cuh) before spending GPU time, tests/emu/build_emu.py compiles the
-// SAME kernel and host source with g++ -DSGPR_EMU against this header into tests/emu/libsgpr_train_emu.so; every CUDA
-// thread of a block becomes a std::thread, __syncthreads / __syncwarp / warp shuffles become barriers.  Blocks run one
-// after the other.  Nothing in sg_pr_b200/ ever loads that library (sg_pr_b200/_lib.py binds libsgpr_b200.so only and
-// fails without it): it exists so that tests/test_train_emu.py can check the kernels' logic against the oracle on CPU.
+// kernels (sg_pr_b200/csrc/*.cuh) before spending GPU time, tests/emu/build_emu.py compiles the SAME kernel and host
+// source with g++ -DSGPR_EMU against this header into tests/emu/libsgpr_emu.so; every CUDA thread of a block becomes a
+// std::thread, __syncthreads / __syncwarp / warp shuffles become barriers.  Blocks run one after the other.  Nothing in
+// sg_pr_b200/ ever loads that library by itself (sg_pr_b200/_lib.py binds libsgpr_b200.so only and fails without it): it
+// exists so that tests/test_train_emu.py and tests/test_eval_emu.py can check the kernels' logic against the reference's
+// golden vectors on the CPU.
 //
-// Supported subset: 1-D grids and blocks, full-mask warp primitives, static and dynamic shared memory, atomicAdd on
-// int / float / double, the cudaMalloc / cudaMemcpy / cudaMemset family on host memory, streams as no-ops.
+// Supported subset: 1-D blocks, 1-D / 2-D grids, full-mask warp primitives, static and dynamic shared memory, atomicAdd on
+// int / float / double, the cudaMalloc / cudaMemcpy / cudaMemset family on host memory, streams as no-ops.  mbarriers
+// and bulk (TMA) copies are emulated in csrc/common.cuh under SGPR_EMU.
 #pragma once
 #include <atomic>
 #include <barrier>
@@ -32,7 +34,7 @@
 #define __align__(x) alignas(x)
 #define __shared__ static          // blocks run sequentially, so one static instance per kernel IS the block's copy
 
-struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() = default; dim3(unsigned a) : x(a) {} };
+struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() = default; dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct uint2 { unsigned x, y; };
@@ -143,12 +145,23 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+struct cudaFuncAttributes { size_t sharedSizeBytes = 0; };
+template <typename F> inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, F) { *a = cudaFuncAttributes(); return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type = cudaMemoryTypeDevice; void* devicePointer = nullptr; };
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {      // every buffer is "device" memory here
+    a->type = cudaMemoryTypeDevice; a->devicePointer = const_cast<void*>(p); return cudaSuccess;
+}
+enum { cudaStreamNonBlocking = 1 };
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
 namespace emu {
 // Run `body` once per CUDA thread, block after block.  One pool of `block` host threads serves every block of the
 // launch; each block gets fresh barrier objects (a CUDA thread that returns early drops out of them).
-inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()>& body) {
+inline void launch(dim3 grid3, unsigned block, size_t smem_bytes, const std::function<void()>& body) {
+    const unsigned grid = grid3.x * grid3.y;
     std::vector<unsigned char> dyn(smem_bytes + 256);
     unsigned char* dyn_aligned = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 127) & ~uintptr_t(127));
     std::barrier<> outer(block);
@@ -161,7 +174,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
                 if (t == 0) { current = new Block(block); current->dyn = dyn_aligned; }
                 outer.arrive_and_wait();
                 blk = current;
-                threadIdx = dim3(t); blockIdx = dim3(b); blockDim = dim3(block); gridDim = dim3(grid);
+                threadIdx = dim3(t); blockIdx = dim3(b % grid3.x, b / grid3.x); blockDim = dim3(block); gridDim = grid3;
                 body();
                 // a thread that returns early must not block its peers' later barriers
                 current->warp[t >> 5]->arrive_and_drop();

@@ -1,0 +1,88 @@
+"""The EVAL hot path's source (csrc/embed_kernel.cuh, head_kernels.cuh, api.cu) executed on the CPU by the
+thread-per-CUDA-thread emulator of tests/emu (mbarriers and bulk copies included), against the golden vectors the
+reference itself produced.  Kernel-logic coverage without a GPU; the `-m gpu` suite runs the same checks on the B200.
+The emulator build is test infrastructure: sg_pr_b200 never loads it."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sgpr_oracle as orc
+from sg_pr_b200 import _lib, synth
+from sg_pr_b200.engine import Engine
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def emu_engine(kitti_state):
+    from tests.emu import build_emu
+    lib = _lib.bind(C.CDLL(build_emu.build()), _lib.SYMBOLS)
+    eng = Engine(lib=lib)
+    eng.set_weights(kitti_state)
+    yield eng
+    eng.close()
+
+
+def test_emulated_fused_kernel_matches_reference_scores(emu_engine):
+    """Golden synthetic batch (N = 32, k = 10) produced by the unmodified reference: scores and attention within 1e-5."""
+    g = np.load(os.path.join(GOLDEN, "ref_synth_n32_k10.npz"))
+    f1, f2 = torch.from_numpy(g["features_1"])[:4], torch.from_numpy(g["features_2"])[:4]
+    score, a1, a2 = emu_engine.forward_pairs(f1, f2, 10)
+    assert float(np.abs(score.numpy() - g["score"][:4]).max()) <= 1e-5
+    assert float(np.abs(a1.numpy().reshape(4, -1) - g["att_1"][:4].reshape(4, -1)).max()) <= 1e-5
+    assert emu_engine.launch_count() >= 1
+
+
+def test_emulated_knn_sets_and_stage_outputs_match_oracle(emu_engine, kitti_state):
+    """Per-stage parity of the embed kernel (k-NN sets of all six layers, layer outputs, pooled vectors) at N = 64, k = 20,
+    then the pair head through score_pairs and the score matrix."""
+    graphs = synth.make_graphs(3, 64, 20, seed=17)
+    got = emu_engine.embed(graphs, 20, want_att=True, want_emb=True, trace=True)
+    want = orc.embed_graphs(graphs, 20, kitti_state, want_trace=True)
+    for layer in range(6):
+        code = orc.classify_knn_rows(want["knn_pd"][layer], want["knn_idx"][layer], got["knn"][:, layer].long(),
+                                     want["layer_in"][layer])
+        assert int((code > 0).sum()) == 0, f"layer {layer}: k-NN rows differ"
+    want_pooled = want["pooled"].reshape(3, 32)
+    assert float((got["pooled"] - want_pooled).abs().max()) <= 1e-5
+    assert float((got["emb"] - want["emb"]).abs().max()) <= 1e-5
+    idx = torch.tensor([[0, 1], [2, 0]], dtype=torch.int32)
+    pairs = emu_engine.score_pairs(got["pooled"], idx)
+    mat = emu_engine.score_matrix(got["pooled"], got["pooled"])
+    assert float((mat[0, 1] - pairs[0]).abs()) <= 2e-6 and float((mat[2, 0] - pairs[1]).abs()) <= 2e-6
+    ref = orc.score_matrix(want_pooled, want_pooled, kitti_state)
+    assert float((mat - ref).abs().max()) <= 1e-5
+
+
+def test_emulated_reference_fixture_pair(emu_engine):
+    """data/0.json vs data/250.json at the shipped config (K = 10, node_num = 100: the NPL = 4 kernel) — BASELINE config 1,
+    the pair eval_pair.py prints "Score: 1.3489922e-06" for — and one positive pair."""
+    with np.load(os.path.join(GOLDEN, "ref_fixture_pairs.npz")) as z:
+        for a, b in (("0", "250"), ("0", "3")):
+            p = f"K10_N100_{a}_{b}_"
+            f1, f2 = torch.from_numpy(z[p + "features_1"]), torch.from_numpy(z[p + "features_2"])
+            score, a1, a2 = emu_engine.forward_pairs(f1, f2, 10)
+            assert abs(float(score[0]) - float(z[p + "score"][0])) <= 1e-5, (a, b)
+            assert float(np.abs(a2.numpy() - z[p + "att_2"]).max()) <= 1e-5
+
+
+def test_emulated_persistent_launch_and_edge_cases(emu_engine, kitti_state):
+    """More graphs than resident CTAs (the emulated device has 4 SMs): heaviest-first work queue (sgpr_order_kernel);
+    k = N, k = 1 and an all-pad graph; batch independence."""
+    f1, f2 = synth.make_pair_batch(9, 16, 10, seed=4)                 # 18 graphs > 8 resident CTAs
+    score, _, _ = emu_engine.forward_pairs(f1, f2, 10)
+    want = orc.forward_pairs(f1, f2, 10, kitti_state)["score"]
+    assert float((score - want).abs().max()) <= 1e-5
+    one, _, _ = emu_engine.forward_pairs(f1[3:4], f2[3:4], 10)
+    assert torch.equal(one[0], score[3])                                # a pair's score does not depend on its batch
+    g = synth.make_graphs(2, 16, 4, seed=2)
+    g[1] = 0.0                                                          # a graph of zero pads only
+    for k in (16, 1):
+        got = emu_engine.embed(g, k)["pooled"]
+        ref = orc.embed_graphs(g, k, kitti_state)["pooled"].reshape(2, 32)
+        assert float((got - ref).abs().max()) <= 1e-5, k
+    with pytest.raises(_lib.SgprError, match="topk"):
+        emu_engine.embed(g, 17)
