@@ -90,7 +90,7 @@ def check_split_forward_backward(eng, g, sd, device, pred_tol, mirrored=False):
     loss = torch.mean(torch.nn.functional.binary_cross_entropy(leaf, target))
     loss.backward()
     flat = eng.backward(leaf.grad)
-    assert abs(float(loss) - float(g["loss1"])) < pred_tol
+    assert abs(loss.item() - float(g["loss1"])) < pred_tol
     grads = eng.grads()
     off = 0
     for name, got in grads.items():
