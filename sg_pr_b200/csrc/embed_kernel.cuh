@@ -520,81 +520,56 @@ __device__ __forceinline__ void norms_rows(const float* __restrict__ sT, float* 
 // (j*YS) of the neighbour rows; 4*GW of them are fetched per step (GW 8-byte list words, then 4*GW independent row
 // loads) to keep the shared-memory pipe busy.
 // ------------------------------------------------------------------------------------------------------------
-#ifndef SGPR_GATHER_ROWS
-#define SGPR_GATHER_ROWS 1     // own rows gathered together per step (2: two independent rows interleaved for latency hiding)
-#endif
 template <int COUT>
 __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const uint16_t* __restrict__ sIdx,
                                             const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ ab,
                                             float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane) {
     constexpr int CPL = COUT / 32;
     constexpr int GW = SGPR_GATHER_W;
-    constexpr int RW = SGPR_GATHER_ROWS;
     float al[CPL], be[CPL];
 #pragma unroll
     for (int p = 0; p < CPL; ++p) { al[p] = __ldg(ab + lane * CPL + p); be[p] = __ldg(ab + COUT + lane * CPL + p); }
     const float* base = sY + lane * CPL;
 #pragma unroll 1
-    for (int i0 = r0; i0 < r1; i0 += RW) {
-        // RW independent rows per step (the last group repeats its final row; repeats are harmless under max and are
-        // not stored twice)
-        int ri[RW], nw[RW];
-        const uint2* row[RW];
-        float m[RW][CPL];
-        int nwmax = 0;
+    for (int i = r0; i < r1; ++i) {
+        float m[CPL];
 #pragma unroll
-        for (int r = 0; r < RW; ++r) {
-            ri[r] = min(i0 + r, r1 - 1);
-            row[r] = reinterpret_cast<const uint2*>(sIdx + ri[r] * KS);
-            nw[r] = sCnt[ri[r]] >> 2;                    // list words (4 neighbours each), >= 1
-            nwmax = max(nwmax, nw[r]);
+        for (int p = 0; p < CPL; ++p) m[p] = -INFINITY;
+        const uint2* row = reinterpret_cast<const uint2*>(sIdx + i * KS);
+        const int nw = sCnt[i] >> 2;                    // list words (4 neighbours each), >= 1
+        float ai[CPL], bi[CPL];
 #pragma unroll
-            for (int p = 0; p < CPL; ++p) m[r][p] = -INFINITY;
-        }
+        for (int p = 0; p < CPL; ++p) { ai[p] = base[i * YS + p]; bi[p] = base[i * YS + COUT + p]; }
 #pragma unroll 1
-        for (int t = 0; t < nwmax; t += GW) {
-            uint2 wd[RW][GW];
+        for (int t = 0; t < nw; t += GW) {
+            uint2 wd[GW];
 #pragma unroll
-            for (int r = 0; r < RW; ++r)
+            for (int q = 0; q < GW; ++q) wd[q] = row[min(t + q, nw - 1)];      // tail words repeat (harmless under max)
+            float v[4 * GW][CPL];
 #pragma unroll
-                for (int q = 0; q < GW; ++q) wd[r][q] = row[r][min(t + q, nw[r] - 1)];   // tail words repeat (harmless under max)
-            float v[RW][4 * GW][CPL];
-#pragma unroll
-            for (int r = 0; r < RW; ++r) {
-#pragma unroll
-                for (int e = 0; e < 4 * GW; ++e) {
-                    const uint32_t w = (e & 2) ? wd[r][e >> 2].y : wd[r][e >> 2].x;
-                    const uint32_t off = (e & 1) ? (w >> 16) : (w & 0xffffu);
-                    if constexpr (CPL == 2) {
-                        const float2 a = *reinterpret_cast<const float2*>(base + off);
-                        v[r][e][0] = a.x; v[r][e][1] = a.y;
-                    } else {
-                        v[r][e][0] = base[off];
-                    }
+            for (int e = 0; e < 4 * GW; ++e) {
+                const uint32_t w = (e & 2) ? wd[e >> 2].y : wd[e >> 2].x;
+                const uint32_t off = (e & 1) ? (w >> 16) : (w & 0xffffu);
+                if constexpr (CPL == 2) {
+                    const float2 a = *reinterpret_cast<const float2*>(base + off);
+                    v[e][0] = a.x; v[e][1] = a.y;
+                } else {
+                    v[e][0] = base[off];
                 }
             }
 #pragma unroll
-            for (int r = 0; r < RW; ++r)
+            for (int p = 0; p < CPL; ++p) {
 #pragma unroll
-                for (int p = 0; p < CPL; ++p) {
-#pragma unroll
-                    for (int q = 0; q < GW; ++q)
-                        m[r][p] = fmaxf(m[r][p], fmaxf(fmaxf(v[r][4 * q][p], v[r][4 * q + 1][p]), fmaxf(v[r][4 * q + 2][p], v[r][4 * q + 3][p])));
-                }
+                for (int q = 0; q < GW; ++q)
+                    m[p] = fmaxf(m[p], fmaxf(fmaxf(v[4 * q][p], v[4 * q + 1][p]), fmaxf(v[4 * q + 2][p], v[4 * q + 3][p])));
+            }
         }
 #pragma unroll
-        for (int r = 0; r < RW; ++r) {
-            if (r == 0 || i0 + r < r1) {
-                const int i = ri[r];
-#pragma unroll
-                for (int p = 0; p < CPL; ++p) {
-                    const float ai = base[i * YS + p], bi = base[i * YS + COUT + p];
-                    const float y = __fadd_rn(__fsub_rn(m[r][p], ai), bi);
-                    const float z = lrelu(fmaf(y, al[p], be[p]));
-                    sDst[i * XS + lane * CPL + p] = z;
-                    if (trace) trace[i * 64 + lane * CPL + p] = z;
-                }
-            }
+        for (int p = 0; p < CPL; ++p) {
+            const float y = __fadd_rn(__fsub_rn(m[p], ai[p]), bi[p]);
+            const float z = lrelu(fmaf(y, al[p], be[p]));
+            sDst[i * XS + lane * CPL + p] = z;
+            if (trace) trace[i * 64 + lane * CPL + p] = z;
         }
     }
 }
