@@ -86,3 +86,14 @@ def test_emulated_persistent_launch_and_edge_cases(emu_engine, kitti_state):
         assert float((got - ref).abs().max()) <= 1e-5, k
     with pytest.raises(_lib.SgprError, match="topk"):
         emu_engine.embed(g, 17)
+
+
+@pytest.mark.parametrize("tag,tol", [("n64_k20", 1e-5), ("n16_k10", 1e-5)])
+def test_emulated_synthetic_goldens(emu_engine, tag, tol):
+    """Reference-produced synthetic batches at the headline shape (N = 64, k = 20) and the smallest one."""
+    g = np.load(os.path.join(GOLDEN, f"ref_synth_{tag}.npz"))
+    f1, f2 = torch.from_numpy(g["features_1"]), torch.from_numpy(g["features_2"])
+    score, a1, a2 = emu_engine.forward_pairs(f1, f2, int(g["K"]))
+    assert float(np.abs(score.numpy() - g["score"]).max()) <= tol
+    assert float(np.abs(a1.numpy().reshape(len(f1), -1) - g["att_1"].reshape(len(f1), -1)).max()) <= tol
+    assert float(np.abs(a2.numpy().reshape(len(f1), -1) - g["att_2"].reshape(len(f1), -1)).max()) <= tol
