@@ -287,6 +287,65 @@ class SGTrainer(object):
             batch_xyz_1 = fn(batch_xyz_1)
         return batch_xyz_1
 
+    @staticmethod
+    def _augment_cloud(xyz):
+        """augment_data for ONE cloud [1, N, 3] in a single function: the same five numpy draws in the same order and the
+        same arithmetic (dtype of every intermediate included) as utils.rotate_point_cloud -> jitter_point_cloud ->
+        random_scale_point_cloud -> rotate_perturbation_point_cloud -> shift_point_cloud, hence bit-identical output for a
+        given numpy RNG state (tests/test_host_logic.py) — minus five calls' worth of Python overhead."""
+        pts = xyz[0].reshape((-1, 3))
+        angle = np.random.uniform() * 2 * np.pi
+        c, s = np.cos(angle), np.sin(angle)
+        rotated = np.dot(pts, np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])).astype(np.float32)
+        cloud = np.clip(0.01 * np.random.randn(1, pts.shape[0], 3), -0.05, 0.05)
+        cloud += rotated[None]
+        cloud[0] *= np.random.uniform(0.8, 1.25, 1)[0]
+        ax, ay, az = np.clip(0.015 * np.random.randn(3), -0.045, 0.045)
+        rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+        ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+        rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+        out = np.dot(cloud[0].reshape((-1, 3)), np.dot(rz, np.dot(ry, rx))).astype(np.float32)[None]
+        out[0] += np.random.uniform(-0.3, 0.3, (1, 3))[0]
+        return out
+
+    def _training_features(self, graph_pair):
+        """(features_1, features_2 [15, node_num] float64, target) of one listed pair for a TRAINING batch — what
+        transfer_to_torch(process_pair(pair), training=True) returns (sg_net.py:241-310), bit for bit and with the same
+        consumption of numpy's / random's global streams, built from the parsed-once arrays of the GraphStore."""
+        store = self._store()
+        want = int(self.args.node_num)
+        sides = []
+        for path in graph_pair:                                   # _fit_node_count, graph 1 then graph 2
+            nodes, centers, _ = store._load(path)
+            have = len(nodes)
+            if have > want:
+                keep = np.random.choice(have, want, replace=False)
+                keep.sort()
+                nodes, centers = nodes[keep], centers[keep]
+            sides.append((nodes, centers))
+        flip = random.random() > 0.5                              # sg_net.py:288
+        feats = []
+        for nodes, centers in sides:
+            n = len(nodes)
+            xyz = np.zeros((1, want, 3))
+            xyz[0, :n] = centers
+            if flip:
+                xyz[:, :, 0] = -xyz[:, :, 0]
+            xyz = self._augment_cloud(xyz)
+            block = np.zeros((3 + self.number_of_labels, want))
+            block[:3] = xyz[0].T
+            block[3 + nodes, np.arange(n)] = 1.0
+            feats.append(block)
+        d = store.distance(graph_pair[0], graph_pair[1])
+        if d <= self.args.p_thresh:
+            target = 1.0
+        elif d >= 20:
+            target = 0.0
+        else:
+            print("distance error: ", d)
+            exit(-1)
+        return feats[0], feats[1], target
+
     def pc_normalize(self, pc):
         pc = pc - np.mean(pc, axis=0)
         return pc / np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
@@ -437,6 +496,11 @@ class SGTrainer(object):
         if getattr(self, "_json_cache", None) is None:
             self._json_cache = {}
         for graph_pair in batch:
+            if training:
+                a, b, t = self._training_features(graph_pair)
+                f1 += [a, b]
+                targets += [t, t]
+                continue
             data = self.transfer_to_torch(process_pair(graph_pair, self._json_cache), training)
             f1 += [data["features_1"], data["features_2"]]
             targets += [data["target"], data["target"]]

@@ -184,3 +184,30 @@ def test_load_paires_and_listdir(tmp_path):
     found = []
     listDir(str(tmp_path), found)
     assert sorted(os.path.basename(p) for p in found) == ["00.txt", "a.json"]
+
+
+def test_fast_training_features_are_bit_identical_to_the_reference_shaped_path(tree):
+    """process_batch's training host path (_training_features: parsed-once arrays + one fused augmentation function) builds
+    the same float64 blocks, with the same consumption of numpy's and random's global streams, as
+    transfer_to_torch(process_pair(pair), training=True) — padding, subsampling (node_num below the graph size) and flip."""
+    import random
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SGTrainer
+    from sg_pr_b200.utils import process_pair
+    root, cfg = tree
+    pairs = [[f"{root}/data/{a}.json", f"{root}/data/{b}.json"] for a, b in (("0", "3"), ("0", "250"), ("3", "250"), ("0", "0"))]
+    for node_num in (64, 100, 16):
+        args = sgpr_args().load(cfg)
+        args.node_num = node_num
+        trainer = SGTrainer(args, False)
+        for seed in range(6):
+            np.random.seed(seed); random.seed(seed)
+            want = [trainer.transfer_to_torch(process_pair(p), True) for p in pairs]
+            tail_w = (np.random.rand(), random.random())
+            np.random.seed(seed); random.seed(seed)
+            got = [trainer._training_features(p) for p in pairs]
+            tail_g = (np.random.rand(), random.random())
+            assert tail_w == tail_g                                  # both RNG streams advanced identically
+            for w, (a, b, t) in zip(want, got):
+                assert a.dtype == w["features_1"].dtype == np.float64 and a.shape == (15, node_num)
+                assert np.array_equal(a, w["features_1"]) and np.array_equal(b, w["features_2"]) and t == w["target"]
