@@ -97,3 +97,13 @@ def test_emulated_synthetic_goldens(emu_engine, tag, tol):
     assert float(np.abs(score.numpy() - g["score"]).max()) <= tol
     assert float(np.abs(a1.numpy().reshape(len(f1), -1) - g["att_1"].reshape(len(f1), -1)).max()) <= tol
     assert float(np.abs(a2.numpy().reshape(len(f1), -1) - g["att_2"].reshape(len(f1), -1)).max()) <= tol
+
+
+def test_emulated_host_entry_point_matches_device_entry(emu_engine):
+    """sgpr_forward_pairs_host (staged copies + kernel + copies back) == sgpr_forward_pairs, bit for bit."""
+    f1, f2 = synth.make_pair_batch(3, 32, 10, seed=12)
+    d_score, d_a1, d_a2 = emu_engine.forward_pairs(f1, f2, 10)
+    h_score, h_a1, h_a2 = emu_engine.forward_pairs_host(f1, f2, 10)
+    assert torch.equal(h_score, d_score) and torch.equal(h_a1, d_a1) and torch.equal(h_a2, d_a2)
+    empty, _, _ = emu_engine.forward_pairs(f1[:0], f2[:0], 10)
+    assert empty.shape == (0,)
