@@ -5,6 +5,7 @@ This checks kernel LOGIC (indexing, barriers, the backward algebra, the optimise
 (tests/test_gpu_train.py) runs the identical checks through the real library.  The emulator build is test
 infrastructure: sg_pr_b200 never loads it."""
 import ctypes as C
+import os
 
 import pytest
 
@@ -96,4 +97,55 @@ def test_emulated_gradients_match_reference_at_64_nodes(emu_lib):
 def test_emulated_general_two_sided_batch(emu_lib, kitti_state):
     eng = TrainEngine(lib=emu_lib)
     tc.check_general_two_sided_batch(eng, kitti_state, "cpu", B=3, N=32, k=10)
+    eng.close()
+
+
+def test_emulated_process_batch_glue(emu_lib, golden_dir, tmp_path):
+    """SGTrainer.process_batch(batch, training=True) — host path, mirrored step, state sync — with the emulated library
+    standing in for the device: the step equals the oracle's on the batch the reference-shaped host code builds from the
+    same seeds, and sync_model_from_device() brings parameters, running statistics and counters back into the module."""
+    import random
+    import numpy as np
+    import torch
+    from oracle import sgpr_oracle_train as ort
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SGTrainer, _DeviceAdam
+    from sg_pr_b200.utils import process_pair
+    from tests.helpers import write_fixture_tree
+    root = str(tmp_path)
+    cfg = write_fixture_tree(golden_dir, root)
+    os.makedirs(f"{root}/lists", exist_ok=True)
+    for seq in ("00", "08"):
+        with open(f"{root}/lists/{seq}.txt", "w") as f:
+            f.write("0.json 3.json\n0.json 250.json\n")
+    args = sgpr_args().load(cfg)
+    args.K, args.node_num, args.batch_size = 10, 64, 2
+    trainer = SGTrainer(args, True)
+    trainer.optimizer = _DeviceAdam(trainer)
+    state0 = {k: v.detach().clone() for k, v in trainer.model.module.state_dict().items()}
+    eng = TrainEngine(lib=emu_lib)                       # what _device_trainer() would create on a GPU box
+    eng.set_state(state0, reset_optimizer=True)
+    eng.set_optimizer(float(args.learning_rate), float(args.weight_decay))
+    trainer._train_engine, trainer._unsynced_steps = eng, 0
+    random.seed(5); np.random.seed(5)
+    loss, pred, gt = trainer.process_batch(trainer.training_graphs, True)
+    random.seed(5); np.random.seed(5)
+    f1, tg = [], []
+    for pair in trainer.training_graphs:                 # the reference-shaped host path on the same seeds
+        d = trainer.transfer_to_torch(process_pair(pair), True)
+        f1 += [d["features_1"], d["features_2"]]
+        tg += [d["target"]] * 2
+    f2 = [f1[i ^ 1] for i in range(len(f1))]
+    work = {k: v.clone() for k, v in state0.items()}
+    want = ort.train_step(work, torch.FloatTensor(np.array(f1)), torch.FloatTensor(np.array(f2)), torch.FloatTensor(tg), 10,
+                          ort.new_adam_state(work), float(args.learning_rate), float(args.weight_decay))
+    assert gt.tolist() == tg and np.abs(pred - want["pred"].numpy()).max() < 5e-4
+    assert abs(loss - want["loss"]) < 1e-3 * max(1.0, want["loss"])
+    trainer.sync_model_from_device()
+    synced = trainer.model.module.state_dict()
+    assert int(synced["dgcnn_conv_end.1.num_batches_tracked"]) == int(state0["dgcnn_conv_end.1.num_batches_tracked"]) + 2
+    for name in ("dgcnn_s_conv1.1.running_mean", "dgcnn_conv_end.1.running_var"):
+        ref = work[name]
+        assert float((synced[name] - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), name
+    assert not torch.equal(synced["attention.weight_matrix"], state0["attention.weight_matrix"])
     eng.close()
