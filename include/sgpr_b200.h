@@ -159,6 +159,31 @@ int sgpr_embed_trace(sgpr_ctx* ctx, const float* graphs_dev, int M, int N, int k
 size_t sgpr_packed_size(void);
 int sgpr_pack_weights_host(const sgpr_weights* host_weights, float* blob, float* head289, size_t* offsets17);
 
+/*
+ * k-NN tie rule of `dgcnn.knn`'s topk (dgcnn.py:19).  Distances on the one-hot semantic branch (sg_net.py:94) tie at the
+ * k-th position in most rows; when a graph has at least k zero pads every rule picks equivalent nodes, otherwise the
+ * rule decides the score (by up to ~0.2).  ATen breaks such ties differently on its two devices, so "the reference"
+ * means one of:
+ *   SGPR_TIES_CUDA (default)  ties at the k-th value go to the lowest column index — ATen's CUDA radix-select topk,
+ *                             i.e. the reference on its native device (`.cuda(gpu)`, sg_net.py:119-120, 176);
+ *   SGPR_TIES_CPU             the order std::nth_element leaves behind in ATen's CPU topk (TopKImpl.h), restated step
+ *                             for step in csrc/topk_nth.cuh — bit-for-bit the index sets of the reference run on a CPU
+ *                             (the build container's oracle and golden vectors).  One lane per row, serial: a parity
+ *                             mode, several times slower in the selection stage.
+ * Applies to every later launch of the context.  SGPR_KNN_TIES=cpu in the environment sets the initial mode.
+ */
+#define SGPR_TIES_CUDA 0
+#define SGPR_TIES_CPU  1
+int sgpr_set_knn_ties(sgpr_ctx* ctx, int mode);
+int sgpr_get_knn_ties(const sgpr_ctx* ctx);
+
+/*
+ * Host-only view of the SGPR_TIES_CPU selection (no device needed; used by the CPU tests that pin it against libstdc++
+ * and torch's CPU topk): rows [num_rows][n] -> idx_out [num_rows][k] in nth_element's order.  depth_limit < 0 runs
+ * std::nth_element's own budget 2*floor(log2 n); >= 0 forces it (exercises the heap-select fallback).
+ */
+int sgpr_topk_cpu_rule_host(const float* rows, int num_rows, int n, int k, int depth_limit, int32_t* idx_out);
+
 /* Number of kernel launches this context has enqueued so far (bench.py's `gpu_launches`). */
 int64_t sgpr_launch_count(const sgpr_ctx* ctx);
 

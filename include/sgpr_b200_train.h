@@ -111,6 +111,17 @@ int sgpr_train_get_state_dev(sgpr_train* t, float* state_dev, void* stream);
 int sgpr_train_assemble(sgpr_train* t, const float* graphs_dev, int M, int N, const int32_t* pair_idx_dev, int P,
                         uint64_t seed, uint64_t step, float* out_f1_dev, float* draws_dev, float* jitter_dev, void* stream);
 
+/*
+ * Every sgpr_train_forward overwrites the context's single activation workspace and advances this counter; a caller that
+ * keeps several forwards alive (autograd graphs) records the value after its forward and must find it unchanged when it
+ * calls sgpr_train_backward — otherwise the backward would differentiate a LATER forward's activations.
+ */
+int64_t sgpr_train_forward_generation(const sgpr_train* t);
+
+/* k-NN tie rule of the train-mode forward: SGPR_TIES_CUDA (default) / SGPR_TIES_CPU, see sgpr_set_knn_ties (sgpr_b200.h). */
+int sgpr_train_set_knn_ties(sgpr_train* t, int mode);
+int sgpr_train_get_knn_ties(const sgpr_train* t);
+
 /* Gradients of the last step w.r.t. the trainable parameters (before weight decay), flat layout, host pointer. */
 int sgpr_train_get_grads(sgpr_train* t, float* grads_host);
 

@@ -47,6 +47,9 @@ SYMBOLS = {
     "sgpr_packed_size": (C.c_size_t, []),
     "sgpr_pack_weights_host": (C.c_int, [C.POINTER(SgprWeights), c_float_p, c_float_p, C.POINTER(C.c_size_t)]),
     "sgpr_launch_count": (C.c_int64, [C.c_void_p]),
+    "sgpr_set_knn_ties": (C.c_int, [C.c_void_p, C.c_int]),
+    "sgpr_get_knn_ties": (C.c_int, [C.c_void_p]),
+    "sgpr_topk_cpu_rule_host": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
 }
 
 # every symbol include/sgpr_b200_train.h declares
@@ -71,6 +74,9 @@ TRAIN_SYMBOLS = {
     "sgpr_train_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgpr_train_get_grads": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgpr_train_forward_generation": (C.c_int64, [C.c_void_p]),
+    "sgpr_train_set_knn_ties": (C.c_int, [C.c_void_p, C.c_int]),
+    "sgpr_train_get_knn_ties": (C.c_int, [C.c_void_p]),
     "sgpr_train_step_count": (C.c_int64, [C.c_void_p]),
     "sgpr_train_launch_count": (C.c_int64, [C.c_void_p]),
     "sgpr_train_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]),

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "embed_kernel.cuh"
 #include "head_kernels.cuh"
+#include "launchers.hpp"
 #include "pack.hpp"
 
 using namespace sgpr;
@@ -94,6 +95,7 @@ struct sgpr_ctx {
     int zerocopy = 1;            // host entry point: read pinned buffers in place; SGPR_NO_ZEROCOPY=1 forces staged copies
     int balance = 1;             // order graphs by active rows before the fused kernel; SGPR_NO_BALANCE=1 disables it
     int dedup = 1;               // collapse trailing all-zero nodes (exact); SGPR_NO_DEDUP=1 disables it for experiments
+    int knn_ties = SGPR_TIES_CUDA;   // k-NN tie rule (sgpr_set_knn_ties); SGPR_KNN_TIES=cpu|cuda sets the initial value
 };
 
 extern "C" {
@@ -126,18 +128,13 @@ int sgpr_create(sgpr_ctx** out, int device) {
     if (const char* nd = getenv("SGPR_NO_DEDUP")) ctx->dedup = (nd[0] == '1') ? 0 : 1;
     if (const char* nz = getenv("SGPR_NO_ZEROCOPY")) ctx->zerocopy = (nz[0] == '1') ? 0 : 1;
     if (const char* nb = getenv("SGPR_NO_BALANCE")) ctx->balance = (nb[0] == '1') ? 0 : 1;
-    // opt in to the full shared-memory carve-out; the dynamic limit excludes each kernel's static __shared__ bytes
-    auto opt_in = [&](const void* fn) -> cudaError_t {
-        cudaFuncAttributes fa;
-        cudaError_t er = cudaFuncGetAttributes(&fa, fn);
-        if (er != cudaSuccess) return er;
-        const int dyn = static_cast<int>(prop.sharedMemPerBlockOptin) - static_cast<int>(fa.sharedSizeBytes);
-        return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    };
-    e = opt_in(reinterpret_cast<const void*>(&sgpr_embed_kernel<1>));
-    if (e == cudaSuccess) e = opt_in(reinterpret_cast<const void*>(&sgpr_embed_kernel<2>));
-    if (e == cudaSuccess) e = opt_in(reinterpret_cast<const void*>(&sgpr_embed_kernel<4>));
-    if (e == cudaSuccess) e = opt_in(reinterpret_cast<const void*>(&sgpr_score_matrix_kernel));
+    if (const char* kt = getenv("SGPR_KNN_TIES")) ctx->knn_ties = (strcmp(kt, "cpu") == 0) ? SGPR_TIES_CPU : SGPR_TIES_CUDA;
+    // opt in to the full shared-memory carve-out (the per-NPL objects subtract each kernel's static __shared__ bytes)
+    const int optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    e = embed_optin<1>(optin);
+    if (e == cudaSuccess) e = embed_optin<2>(optin);
+    if (e == cudaSuccess) e = embed_optin<4>(optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_score_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_blob), ctx->off.total * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_ctrs), 2 * sizeof(int));
@@ -259,9 +256,9 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
         if (!resident) a.work_ctr = ctx->d_ctrs + 1;
     }
     switch (npl) {
-        case 1: SGPR_LAUNCH(sgpr_embed_kernel<1>, grid, kThreads, L.total, st, a, ctx->pw, ctx->hp); break;
-        case 2: SGPR_LAUNCH(sgpr_embed_kernel<2>, grid, kThreads, L.total, st, a, ctx->pw, ctx->hp); break;
-        default: SGPR_LAUNCH(sgpr_embed_kernel<4>, grid, kThreads, L.total, st, a, ctx->pw, ctx->hp); break;
+        case 1: embed_launch<1>(ctx->knn_ties, grid, L.total, st, a, ctx->pw, ctx->hp); break;
+        case 2: embed_launch<2>(ctx->knn_ties, grid, L.total, st, a, ctx->pw, ctx->hp); break;
+        default: embed_launch<4>(ctx->knn_ties, grid, L.total, st, a, ctx->pw, ctx->hp); break;
     }
     ctx->launches += 1;
     cudaError_t e = cudaGetLastError();
@@ -414,6 +411,31 @@ int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const 
 }
 
 int64_t sgpr_launch_count(const sgpr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sgpr_set_knn_ties(sgpr_ctx* ctx, int mode) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_set_knn_ties: ctx is NULL");
+    if (mode != SGPR_TIES_CUDA && mode != SGPR_TIES_CPU)
+        return fail(SGPR_E_INVALID, "sgpr_set_knn_ties: mode %d is neither SGPR_TIES_CUDA (0) nor SGPR_TIES_CPU (1)", mode);
+    ctx->knn_ties = mode;
+    return SGPR_OK;
+}
+
+int sgpr_get_knn_ties(const sgpr_ctx* ctx) { return ctx ? ctx->knn_ties : SGPR_E_INVALID; }
+
+int sgpr_topk_cpu_rule_host(const float* rows, int num_rows, int n, int k, int depth_limit, int32_t* idx_out) {
+    if (!rows || !idx_out) return fail(SGPR_E_INVALID, "sgpr_topk_cpu_rule_host: NULL argument");
+    if (num_rows < 0 || n < 1 || n > SGPR_MAX_NODES || k < 1 || k > n)
+        return fail(SGPR_E_INVALID, "sgpr_topk_cpu_rule_host: need 1 <= k <= n <= %d", SGPR_MAX_NODES);
+    float v[SGPR_MAX_NODES];
+    uint8_t ix[SGPR_MAX_NODES];
+    for (int r = 0; r < num_rows; ++r) {
+        for (int j = 0; j < n; ++j) { v[j] = rows[static_cast<size_t>(r) * n + j]; ix[j] = static_cast<uint8_t>(j); }
+        if (depth_limit < 0) nth::topk_cpu_rule<uint8_t>(v, ix, n, k);
+        else nth::introselect(nth::Seq<uint8_t>{v, ix}, 0, k - 1, n, depth_limit);
+        for (int j = 0; j < k; ++j) idx_out[static_cast<size_t>(r) * k + j] = ix[j];
+    }
+    return SGPR_OK;
+}
 
 #ifdef SGPR_TIMELINE
 // debug builds only (not declared in the public header): copy CTA 0's clock stamps, [8 warps][128 slots]

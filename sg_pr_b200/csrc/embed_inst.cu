@@ -1,0 +1,44 @@
+// One object per NPL (-DSGPR_INST_NPL=1|2|4): the instantiations of the fused eval kernel and their launch wrappers.
+#include "../../include/sgpr_b200.h"
+#include "embed_kernel.cuh"
+#include "launchers.hpp"
+
+#ifndef SGPR_INST_NPL
+#error "compile with -DSGPR_INST_NPL=1, 2 or 4"
+#endif
+
+namespace sgpr {
+
+template <>
+cudaError_t embed_optin<SGPR_INST_NPL>(int optin_bytes) {
+#ifdef SGPR_EMU
+    (void)optin_bytes;
+    return cudaSuccess;
+#else
+    // the dynamic limit excludes each kernel's static __shared__ bytes
+    const void* fns[2] = {reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 0>),
+                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 1>)};
+    for (const void* fn : fns) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_bytes - static_cast<int>(fa.sharedSizeBytes));
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+#endif
+}
+
+template <>
+void embed_launch<SGPR_INST_NPL>(int ties, int grid, int smem, cudaStream_t st, const EmbedArgs& a, const PackedWeights& pw,
+                                 const HeadParams& hp) {
+    if (ties == SGPR_TIES_CPU) {
+        const auto kern = &sgpr_embed_kernel<SGPR_INST_NPL, 1>;
+        SGPR_LAUNCH(kern, grid, kThreads, smem, st, a, pw, hp);
+    } else {
+        const auto kern = &sgpr_embed_kernel<SGPR_INST_NPL, 0>;
+        SGPR_LAUNCH(kern, grid, kThreads, smem, st, a, pw, hp);
+    }
+}
+
+}  // namespace sgpr

@@ -35,6 +35,7 @@
 //   * layer matrices are prefetched into shared memory with 1-D bulk TMA (cp.async.bulk + mbarrier) one layer ahead.
 #pragma once
 #include "common.cuh"
+#include "topk_nth.cuh"
 
 // tuning switches (defaults are the measured-best variants; see profiles/r01_variants.txt)
 #ifndef SGPR_GRAM_V
@@ -262,10 +263,49 @@ __device__ __forceinline__ uint32_t feq_mask(float a, float b) {
 }
 #endif
 
+// Selection with the reference's CPU tie behaviour (`knn_ties = cpu`, topk_nth.cuh): one lane runs ATen's
+// nth_element over the row's N (value, column) pairs in place — the collapsed pad columns R..N-1 are present in the row
+// with the pad class's value, exactly as an uncollapsed run would see them — and lists the first k columns, the pad
+// class (columns >= R-1 when row R-1 is a pad) once.  A parity mode: ~8 lanes of a warp work, serially.
 template <int NPL>
-__device__ __forceinline__ void select_rows(const float* __restrict__ sY, uint16_t* __restrict__ sIdx,
+__device__ __forceinline__ void select_rows_cpu_rule(float* __restrict__ sY, uint16_t* __restrict__ sIdx,
+                                                     uint8_t* __restrict__ sCnt, uint8_t* __restrict__ trace, int R, int N,
+                                                     int k, int KS, int scale, int r0, int nr, int lane) {
+    constexpr int NMAX = 32 * NPL;
+    if (lane < nr) {
+        const int row = r0 + lane;
+        float* prow = sY + row * YS;
+        uint8_t ix[NMAX];
+        for (int c = 0; c < N; ++c) ix[c] = static_cast<uint8_t>(c);
+        nth::topk_cpu_rule<uint8_t>(prow, ix, N, k);
+        uint16_t* list = sIdx + row * KS;
+        int pos = 0;
+        bool pad_listed = false;
+        uint16_t last = 0;
+        for (int e = 0; e < k; ++e) {
+            int c = ix[e];
+            if (trace) trace[row * k + e] = static_cast<uint8_t>(c);
+            if (c >= R - 1) {
+                if (pad_listed) continue;
+                pad_listed = true;
+                c = R - 1;
+            }
+            last = static_cast<uint16_t>(c * scale);
+            list[pos++] = last;
+        }
+        for (int e = pos; e < ((pos + 3) & ~3); ++e) list[e] = last;
+        sCnt[row] = static_cast<uint8_t>((pos + 3) & ~3);
+    }
+}
+
+template <int NPL, int TIES = 0>
+__device__ __forceinline__ void select_rows(float* __restrict__ sY, uint16_t* __restrict__ sIdx,
                                             uint8_t* __restrict__ sCnt, uint8_t* __restrict__ trace, int R, int N, int k,
                                             int KS, int scale, int r0, int nr, int lane) {
+    if constexpr (TIES == 1) {
+        select_rows_cpu_rule<NPL>(sY, sIdx, sCnt, trace, R, N, k, KS, scale, r0, nr, lane);
+        return;
+    }
     constexpr int NMAX = 32 * NPL;
     constexpr int EPL = 8 * NPL;
     const int sub = lane >> 3, rl = lane & 7;
@@ -718,7 +758,7 @@ struct FrontCtx {
 
 // front of one pass (up to 8 own rows): distance rows -> selection -> GEMM rows.  Only the row-tiled pieces are
 // specialised on the row count; the selection network exists once.
-template <int NPL>
+template <int NPL, int TIES>
 __device__ __forceinline__ void front_pass(const FrontCtx& F, int r0, int nr, int lane, uint64_t* barW, uint32_t& phW,
                                            bool& waited) {
     // column blocks holding active nodes: all of them, or (small graphs) the lower half
@@ -727,7 +767,7 @@ __device__ __forceinline__ void front_pass(const FrontCtx& F, int r0, int nr, in
     else                 { SGPR_NR_SWITCH(nr, (gram_rows<NPL, NPL, NR>(F.sXt, F.sXX, F.sY, F.c4n, F.R, F.N, r0, lane))) }
     __syncwarp();
     SGPR_TL(8 + F.layer * 8 + 1);
-    select_rows<NPL>(F.sY, F.sIdx, F.sCnt, F.trace_knn, F.R, F.N, F.k, F.KS, (F.layer == 0) ? XS : YS, r0, nr, lane);
+    select_rows<NPL, TIES>(F.sY, F.sIdx, F.sCnt, F.trace_knn, F.R, F.N, F.k, F.KS, (F.layer == 0) ? XS : YS, r0, nr, lane);
     __syncwarp();                                      // the distance rows are dead; A|B may overwrite them
     SGPR_TL(8 + F.layer * 8 + 2);
     if (F.layer != 0) {
@@ -748,7 +788,7 @@ __device__ __forceinline__ void conv_end_dispatch(const float* sCat, const float
 #ifndef SGPR_MINBLOCKS_SMALL
 #define SGPR_MINBLOCKS_SMALL 2
 #endif
-template <int NPL>
+template <int NPL, int TIES = 0>       // TIES: 0 = lowest index first (ATen CUDA topk), 1 = ATen CPU nth_element order
 __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? SGPR_MINBLOCKS_SMALL : 1)
 sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) {
     constexpr int NMAX = 32 * NPL;
@@ -866,7 +906,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             FrontCtx F{(l == 0) ? sCat : sX, (l == 0) ? sXX0 : sXX, sY, sW, sIdx, sCnt, tkl, D.cin4, D.cout, R, N, k, KS, l};
             bool waited = false;
             SGPR_TL(8 + l * 8 + 0);
-            for (int r0 = w0; r0 < w1; r0 += 8) front_pass<NPL>(F, r0, min(8, w1 - r0), lane, barW, phW, waited);
+            for (int r0 = w0; r0 < w1; r0 += 8) front_pass<NPL, TIES>(F, r0, min(8, w1 - r0), lane, barW, phW, waited);
             SGPR_TL(8 + l * 8 + 3);
             if (l != 0 && !waited) { mbar_wait(barW, phW); phW ^= 1; }       // warps without rows still track the phase
 

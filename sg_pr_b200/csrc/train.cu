@@ -11,6 +11,7 @@
 
 #include "../../include/sgpr_b200_train.h"
 #include "train_kernels.cuh"
+#include "launchers.hpp"
 
 using namespace sgpr;
 using namespace sgpr::train;
@@ -106,6 +107,8 @@ struct sgpr_train {
     float lr = 1e-3f, wd = 0.0f, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     long long steps = 0;
     long long launches = 0;
+    long long forward_gen = 0;     // counts train-mode forwards; sgpr_train_backward names the one it differentiates
+    int knn_ties = SGPR_TIES_CUDA; // k-NN tie rule (sgpr_train_set_knn_ties)
     TrainWs last{};                // pointers of the last step (debug taps)
     bool has_last = false;
     Plan plan;
@@ -158,18 +161,10 @@ int sgpr_train_create(sgpr_train** out, int device) {
     t->device = device;
     t->sm_count = prop.multiProcessorCount;
     const int optin = static_cast<int>(prop.sharedMemPerBlockOptin) - 1024;
-    e = cudaFuncSetAttribute(sgpr_train_edge_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_edge_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_edge_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_edge_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_edge_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_edge_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_end_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (const char* kt = getenv("SGPR_KNN_TIES")) t->knn_ties = (strcmp(kt, "cpu") == 0) ? SGPR_TIES_CPU : SGPR_TIES_CUDA;
+    e = train_optin<1>(optin);
+    if (e == cudaSuccess) e = train_optin<2>(optin);
+    if (e == cudaSuccess) e = train_optin<4>(optin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_train_pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_state), STATE_TOTAL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->d_adam), 2 * P_TOTAL * sizeof(float));
@@ -343,12 +338,12 @@ int make_plan(sgpr_train* t, const float* f1_dev, const float* f2_dev, const flo
     return SGPR_OK;
 }
 
-#define BY_NPL(KERN, GRID, SMEM, ...)                                                                    \
-    do {                                                                                                 \
-        if (P.npl == 1) { SGPR_LAUNCH(KERN<1>, GRID, kThreads, SMEM, st, __VA_ARGS__); }                 \
-        else if (P.npl == 2) { SGPR_LAUNCH(KERN<2>, GRID, kThreads, SMEM, st, __VA_ARGS__); }            \
-        else { SGPR_LAUNCH(KERN<4>, GRID, kThreads, SMEM, st, __VA_ARGS__); }                            \
-        t->launches += 1;                                                                                \
+#define BY_NPL(FN, ...)                                                   \
+    do {                                                                  \
+        if (P.npl == 1) FN<1>(__VA_ARGS__);                               \
+        else if (P.npl == 2) FN<2>(__VA_ARGS__);                          \
+        else FN<4>(__VA_ARGS__);                                          \
+        t->launches += 1;                                                 \
     } while (0)
 
 // pack | EdgeConv fwd x3 | conv_end fwd  (statistics zeroed first)
@@ -361,8 +356,8 @@ int launch_forward(sgpr_train* t, cudaStream_t st) {
         t->launches += 1;
         t->wpk_valid = true;
     }
-    for (int l = 0; l < 3; ++l) BY_NPL(sgpr_train_edge_fwd, P.grid4, P.fwd_smem, W, l);
-    BY_NPL(sgpr_train_end_fwd, P.grid2, P.end_fwd_smem, W);
+    for (int l = 0; l < 3; ++l) BY_NPL(launch_edge_fwd, t->knn_ties, P.grid4, P.fwd_smem, st, W, l);
+    BY_NPL(launch_end_fwd, P.grid2, P.end_fwd_smem, st, W);
     return SGPR_OK;
 }
 
@@ -377,8 +372,8 @@ void launch_head(sgpr_train* t, cudaStream_t st, int mode) {
 int launch_backward(sgpr_train* t, cudaStream_t st) {
     Plan& P = t->plan;
     const TrainWs& W = P.W;
-    BY_NPL(sgpr_train_end_bwd, P.grid2, P.end_bwd_smem, W, P.part_end);
-    for (int l = 2; l >= 0; --l) BY_NPL(sgpr_train_edge_bwd, P.grid4, P.bwd_smem, W, l, P.part_conv[l], P.part_conv[3 + l]);
+    BY_NPL(launch_end_bwd, P.grid2, P.end_bwd_smem, st, W, P.part_end);
+    for (int l = 2; l >= 0; --l) BY_NPL(launch_edge_bwd, P.grid4, P.bwd_smem, st, W, l, P.part_conv[l], P.part_conv[3 + l]);
     return SGPR_OK;
 }
 #undef BY_NPL
@@ -446,6 +441,7 @@ int sgpr_train_forward(sgpr_train* t, const float* f1_dev, const float* f2_dev, 
     t->last = W;
     t->has_last = true;
     t->plan.backward_ready = true;
+    t->forward_gen += 1;
     return SGPR_OK;
 }
 
@@ -511,6 +507,17 @@ int sgpr_train_get_grads(sgpr_train* t, float* grads_host) {
     TRY_CUDA(cudaMemcpy(grads_host, t->d_grads, P_TOTAL * sizeof(float), cudaMemcpyDeviceToHost));
     return SGPR_OK;
 }
+
+int64_t sgpr_train_forward_generation(const sgpr_train* t) { return t ? t->forward_gen : 0; }
+
+int sgpr_train_set_knn_ties(sgpr_train* t, int mode) {
+    if (!t) return sgpr_fail(SGPR_E_INVALID, "sgpr_train_set_knn_ties: NULL context");
+    if (mode != SGPR_TIES_CUDA && mode != SGPR_TIES_CPU)
+        return sgpr_fail(SGPR_E_INVALID, "sgpr_train_set_knn_ties: mode %d is neither SGPR_TIES_CUDA (0) nor SGPR_TIES_CPU (1)", mode);
+    t->knn_ties = mode;
+    return SGPR_OK;
+}
+int sgpr_train_get_knn_ties(const sgpr_train* t) { return t ? t->knn_ties : SGPR_E_INVALID; }
 
 int64_t sgpr_train_step_count(const sgpr_train* t) { return t ? t->steps : 0; }
 int64_t sgpr_train_launch_count(const sgpr_train* t) { return t ? t->launches : 0; }

@@ -182,6 +182,7 @@ __device__ __forceinline__ void pack_element(float* __restrict__ wpk, int L, int
 }
 
 // whole-state pack (after sgpr_train_set_state*); during training the optimiser kernel keeps the copies current
+#ifndef SGPR_TRAIN_INST_ONLY   // non-template kernels live in train.cu only (train_inst.cu holds the per-NPL templates)
 __global__ void __launch_bounds__(kThreads) sgpr_train_pack_kernel(const TrainWs T) {
     const int stride = gridDim.x * blockDim.x;
     for (int L = 1; L <= 6; ++L) {
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_pack_kernel(const TrainWs
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) pack_element(T.wpk, L, e, w[e]);
     }
 }
+#endif  // !SGPR_TRAIN_INST_ONLY
 
 // ---- shared-memory carve-outs ----------------------------------------------------------------------------------------
 struct FwdSmem { int w, x, y, xx, idx, cnt, prm, stat, total; };
@@ -394,7 +396,7 @@ __device__ __forceinline__ void flush_channel_sums(double* sStat, double* dst, c
 // =====================================================================================================================
 // EdgeConv layer l (0..2) forward for both branches and both sides: grid = multiple of 4, CTA -> (branch, side), loops g
 // =====================================================================================================================
-template <int NPL>
+template <int NPL, int TIES = 0>      // TIES: k-NN tie rule, as in sgpr_embed_kernel (0 = ATen CUDA topk, 1 = ATen CPU topk)
 __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_fwd(const TrainWs T, int l) {
     constexpr int NMAX = 32 * NPL;
     SGPR_DYN_SMEM(smem);
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_edge_
             const int nr = min(8, w1 - r0);
             SGPR_NR_SWITCH(nr, (gram_rows<NPL, NPL, NR>(sX, sXX, sY, cin4, N, N, r0, lane)))
             __syncwarp();
-            select_rows<NPL>(sY, sIdx, sCnt, nullptr, N, N, k, KS, 1, r0, nr, lane);
+            select_rows<NPL, TIES>(sY, sIdx, sCnt, nullptr, N, N, k, KS, 1, r0, nr, lane);
             __syncwarp();
             if (!direct) {
                 if (cout == 64) { SGPR_NR_SWITCH(nr, (gemm_rows<NR, 4, 0>(sX, sW, sY, YS, nullptr, cin4, r0, lane))) }
@@ -540,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? 2 : 1) sgpr_train_end_f
 // Outputs: pred, att, pooled, dpooled (taps), gz_end = d loss / d (conv_end BN output) with its dbeta / dgamma sums;
 // partial rows: part_head [grid][kHeadFloats], part_att [grid][1024].
 // =====================================================================================================================
+#ifndef SGPR_TRAIN_INST_ONLY   // non-template kernels live in train.cu only (train_inst.cu holds the per-NPL templates)
 __global__ void __launch_bounds__(kThreads, 2) sgpr_train_pool_head_kernel(const TrainWs T, float* __restrict__ part_head,
                                                                          float* __restrict__ part_att, int mode) {
     SGPR_DYN_SMEM(smem);
@@ -815,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, 2) sgpr_train_pool_head_kernel(const
         }
     }
 }
+#endif  // !SGPR_TRAIN_INST_ONLY
 
 // =====================================================================================================================
 // conv_end backward: BatchNorm backward with the complete dbeta/dgamma, d cat(xyz3, sem3), dW_end, and the gz of the
@@ -1287,6 +1291,7 @@ struct AdamArgs {
 
 // One block per 32 consecutive state elements: lane = element, the 8 warps split the partial rows (j = warp, warp + 8,
 // ...) and their sums are added in warp order — a fixed summation order whatever the grid did.
+#ifndef SGPR_TRAIN_INST_ONLY   // non-template kernels live in train.cu only (train_inst.cu holds the per-NPL templates)
 __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs T, const AdamArgs A) {
     __shared__ float sPart[kWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1364,6 +1369,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_adam_kernel(const TrainWs
         T.state[e] = run;
     }
 }
+#endif  // !SGPR_TRAIN_INST_ONLY
 
 // =====================================================================================================================
 // Training-batch assembly + augmentation on the device.  Replaces, for graphs already resident in HBM, the host loop of
@@ -1409,6 +1415,7 @@ struct AssembleArgs {
     uint32_t seed_lo, seed_hi, step_lo, step_hi;
 };
 
+#ifndef SGPR_TRAIN_INST_ONLY   // non-template kernels live in train.cu only (train_inst.cu holds the per-NPL templates)
 __global__ void __launch_bounds__(kThreads) sgpr_train_assemble_kernel(const AssembleArgs A) {
     __shared__ float sPar[16];
     const int tid = threadIdx.x, N = A.N;
@@ -1464,6 +1471,7 @@ __global__ void __launch_bounds__(kThreads) sgpr_train_assemble_kernel(const Ass
         __syncthreads();
     }
 }
+#endif  // !SGPR_TRAIN_INST_ONLY
 
 }  // namespace train
 }  // namespace sgpr

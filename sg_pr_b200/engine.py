@@ -144,6 +144,20 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.sgpr_launch_count(self._ctx))
 
+    # ---- k-NN tie rule (dgcnn.py:19) ------------------------------------------------------------------------
+    KNN_TIES = {"cuda": 0, "cpu": 1}
+
+    def set_knn_ties(self, mode: str):
+        """"cuda" (default): ties at the k-th distance go to the lowest node index — ATen's CUDA topk, the reference on
+        its native device.  "cpu": the order ATen's CPU topk (std::nth_element) leaves — the reference run on a CPU.
+        The two differ only for graphs with fewer than k zero pads (include/sgpr_b200.h, sgpr_set_knn_ties)."""
+        if mode not in self.KNN_TIES:
+            raise ValueError(f"knn_ties must be one of {sorted(self.KNN_TIES)}, got {mode!r}")
+        check(self._lib.sgpr_set_knn_ties(self._ctx, self.KNN_TIES[mode]), "sgpr_set_knn_ties", self._lib)
+
+    def knn_ties(self) -> str:
+        return {v: k for k, v in self.KNN_TIES.items()}[int(self._lib.sgpr_get_knn_ties(self._ctx))]
+
     def _stream(self) -> C.c_void_p:
         if self._emulated:
             return None
@@ -166,15 +180,17 @@ class Engine:
                 raise ValueError(f"features_2 {tuple(f2.shape)} != features_1 {tuple(f1.shape)}")
             f1, f2 = self._dev(f1, "features_1", True), self._dev(f2, "features_2", True)
         b, n = int(f1.shape[0]), int(f1.shape[2])
-        # one allocation for the three results (views are returned)
-        buf = torch.empty(b + (2 * b * n if want_att else 0), dtype=torch.float32, device=self.device)
-        score = buf[:b]
-        att1 = buf[b:b + b * n].view(b, n, 1) if want_att else None
-        att2 = buf[b + b * n:].view(b, n, 1) if want_att else None
-        check(self._lib.sgpr_forward_pairs(self._ctx, f1.data_ptr(), f2.data_ptr(), b, n, int(k), score.data_ptr(),
-                                           att1.data_ptr() if want_att else None,
-                                           att2.data_ptr() if want_att else None, self._stream()),
-              "sgpr_forward_pairs", self._lib)
+        score = torch.empty(b, dtype=torch.float32, device=self.device)
+        if want_att:
+            att1 = torch.empty((b, n, 1), dtype=torch.float32, device=self.device)
+            att2 = torch.empty((b, n, 1), dtype=torch.float32, device=self.device)
+            p1, p2 = att1.data_ptr(), att2.data_ptr()
+        else:
+            att1 = att2 = p1 = p2 = None
+        rc = self._lib.sgpr_forward_pairs(self._ctx, f1.data_ptr(), f2.data_ptr(), b, n, int(k), score.data_ptr(), p1, p2,
+                                          self._stream())
+        if rc:
+            check(rc, "sgpr_forward_pairs", self._lib)
         return score, att1, att2
 
     def forward_pairs_host(self, f1: torch.Tensor, f2: torch.Tensor, k: int, want_att: bool = True,

@@ -82,6 +82,7 @@ class _TrainForward(torch.autograd.Function):
                 if name.endswith("num_batches_tracked"):
                     buf.add_(2)                       # one BatchNorm call per side (sg_net.py:123-124)
         ctx.eng = eng
+        ctx.generation = eng.forward_generation()     # the engine keeps ONE forward's activations
         ctx.save_for_backward(f1, f2)                 # the layer-1 backward re-reads the input blocks: keep them alive
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.mark_non_differentiable(att1, att2)
@@ -89,6 +90,11 @@ class _TrainForward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dpred, _datt1, _datt2):
+        if ctx.eng.forward_generation() != ctx.generation:
+            raise RuntimeError(
+                "sg_pr_b200: backward() of a train-mode SG.forward whose activations are gone — another train-mode "
+                "forward ran on this module since (the device workspace holds one forward at a time). Call backward() "
+                "before the next forward; for gradient accumulation, backward each micro-batch before forwarding the next.")
         flat = ctx.eng.backward(dpred.contiguous().to(torch.float32))
         grads, off = [], 0
         for shape in ctx.shapes:
@@ -111,6 +117,7 @@ class SG(torch.nn.Module):
         self.setup_layers()
         self._engine = None
         self._packed_version = None
+        self._pinned_in_flight = []
 
     def calculate_bottleneck_features(self):
         self.feature_count = self.args.tensor_neurons
@@ -142,19 +149,31 @@ class SG(torch.nn.Module):
         return out
 
     def _weights_version(self):
+        """Changes whenever a parameter / buffer is modified in place (`_version`) or re-pointed (`p.data = t`,
+        `data_ptr`).  In-place writes THROUGH `.data` (`p.data.mul_()`, `m.weight.data.fill_()`) bump neither: call
+        `invalidate_packed_weights()` after those."""
         if getattr(self, "_tensors", None) is None:
             self._tensors = list(self.parameters()) + list(self.buffers())
-        return tuple(t._version for t in self._tensors)
+        return [t._version for t in self._tensors] + [t.data_ptr() for t in self._tensors]
+
+    def invalidate_packed_weights(self):
+        """Force the next eval-mode forward to re-pack the weights (and SGTrainer to drop cached embeddings)."""
+        self._packed_version = None
+        self._tensors = None
 
     def engine(self):
         """The device context with this module's CURRENT eval-mode weights packed (re-packed when they change)."""
         from .engine import Engine
         if self._engine is None:
             self._engine = Engine(self._device())
+        ties = str(getattr(self.args, "knn_ties", "cuda"))
+        if self._engine.knn_ties() != ties:
+            self._engine.set_knn_ties(ties)
         version = self._weights_version()
         if version != self._packed_version:
             self._engine.set_weights({k: v for k, v in self.state_dict().items()})
             self._packed_version = version
+            self._pack_serial = getattr(self, "_pack_serial", 0) + 1
         return self._engine
 
     # ---- train mode: the same C-ABI kernels as SGTrainer.process_batch, split at the loss ----------------------------
@@ -162,6 +181,7 @@ class SG(torch.nn.Module):
         from .train_engine import TrainEngine
         if getattr(self, "_autograd_engine", None) is None:
             self._autograd_engine = TrainEngine(self._device())
+        self._autograd_engine.set_knn_ties(str(getattr(self.args, "knn_ties", "cuda")))
         return self._autograd_engine
 
     def _train_params_in_layout_order(self):
@@ -179,13 +199,23 @@ class SG(torch.nn.Module):
             return _TrainForward.apply(self, f1.to(dev, dtype=torch.float32).contiguous(),
                                        f2.to(dev, dtype=torch.float32).contiguous(), *self._train_params_in_layout_order())
         # pinned fp32 host tensors are read in place by the kernel (zero-copy over PCIe); anything else is moved first
-        ok = (f1.dim() == 3 and f1.shape[1] == 15 and f2.shape == f1.shape and f1.dtype == torch.float32
-              and f2.dtype == torch.float32 and f1.is_contiguous() and f2.is_contiguous())
-        if not (ok and f1.device.type == "cpu" and f2.device.type == "cpu" and f1.is_pinned() and f2.is_pinned()):
-            ok = False
-            f1 = f1.to(dev, dtype=torch.float32, non_blocking=True)
-            f2 = f2.to(dev, dtype=torch.float32, non_blocking=True)
-        return self.engine().forward_pairs(f1, f2, int(self.args.K), want_att=True, _checked=ok)
+        eng = self.engine()
+        if (f1.device.type == "cpu" and f2.device.type == "cpu" and f1.dtype == torch.float32 and f2.dtype == torch.float32
+                and f1.dim() == 3 and f1.shape[1] == 15 and f2.shape == f1.shape and f1.is_contiguous()
+                and f2.is_contiguous() and f1.is_pinned() and f2.is_pinned()):
+            out = eng.forward_pairs(f1, f2, int(self.args.K), True, True)
+            # the launch is asynchronous and torch's pinned-memory cache knows nothing about it: keep the two host tensors
+            # referenced until an event recorded behind the launch has completed
+            done = torch.cuda.Event()
+            done.record()
+            hold = self._pinned_in_flight
+            if len(hold) >= 8:
+                hold[:] = [h for h in hold if not h[2].query()]
+            hold.append((f1, f2, done))
+            return out
+        f1 = f1.to(dev, dtype=torch.float32, non_blocking=True)
+        f2 = f2.to(dev, dtype=torch.float32, non_blocking=True)
+        return eng.forward_pairs(f1, f2, int(self.args.K), True, False)
 
 
 class _DeviceReplica(torch.nn.Module):
@@ -415,6 +445,7 @@ class SGTrainer(object):
             self._train_engine = TrainEngine(torch.device("cuda", int(self.args.gpu)))
             self._train_engine.set_state(self.model.module.state_dict(), reset_optimizer=True)
             self._train_engine.set_optimizer(float(self.args.learning_rate), float(self.args.weight_decay))
+            self._train_engine.set_knn_ties(str(getattr(self.args, "knn_ties", "cuda")))
             self._unsynced_steps = 0
         return self._train_engine
 
@@ -479,7 +510,8 @@ class SGTrainer(object):
         targets = np.repeat(np.array([t for _, _, t in known], dtype=np.float32), 2)
         idx = torch.tensor(rows, dtype=torch.int32).view(-1, 2).to(eng.device, non_blocking=True)
         tgt = torch.from_numpy(targets).to(eng.device, non_blocking=True)
-        f1 = eng.assemble(self._dev_graphs["blocks"], idx, self.augment_seed, eng.step_count())
+        f1 = eng.assemble(self._dev_graphs["blocks"], idx, self.augment_seed, eng.step_count(),
+                          rows_filled=self._dev_graphs["count"])
         loss, prediction = eng.step(f1, None, tgt, int(self.args.K), apply=True, mirrored=True)
         self._unsynced_steps += 1
         return loss.item(), prediction.cpu().numpy().reshape(-1), targets.astype(np.float32)
@@ -528,6 +560,12 @@ class SGTrainer(object):
         """sg_net.py:347-384."""
         print("\nModel training.\n")
         self.optimizer = _DeviceAdam(self)
+        if getattr(self, "_train_engine", None) is not None:
+            # the reference builds a NEW torch.optim.Adam in every fit() (sg_net.py:351-352): fresh moments and step count,
+            # parameters as they stand
+            self.sync_model_from_device()
+            self._train_engine.set_state(self.model.module.state_dict(), reset_optimizer=True)
+            self._train_engine.set_optimizer(float(self.args.learning_rate), float(self.args.weight_decay))
         f1_max_his = 0
         self.model.train()
         epochs = trange(self.args.epochs, leave=True, desc="Epoch")
@@ -632,7 +670,7 @@ class SGTrainer(object):
         not seen yet under the current weights / K / node_num."""
         module = self.model.module
         eng = module.engine()
-        key = (module._packed_version, int(self.args.K), int(self.args.node_num))
+        key = (module._pack_serial, int(self.args.K), int(self.args.node_num), eng.knn_ties())
         if self._emb is None or self._emb["key"] != key:
             self._emb = {"key": key, "index": {}, "pool": torch.empty(1024, 32, device=eng.device), "count": 0}
         emb, store = self._emb, self._store()
@@ -640,6 +678,11 @@ class SGTrainer(object):
         if fresh:
             blocks = torch.stack([store.block(p) for p in fresh]).pin_memory()
             pooled = eng.embed(blocks, int(self.args.K))["pooled"]
+            # the kernel reads `blocks` in place over PCIe, asynchronously: keep the pinned tensor alive until an event
+            # recorded after the launch has completed (torch's pinned-memory cache would otherwise recycle it)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(eng.device))
+            emb["staging"] = [(b, e) for b, e in emb.get("staging", []) if not e.query()] + [(blocks, done)]
             need = emb["count"] + len(fresh)
             if need > emb["pool"].shape[0]:
                 grown = torch.empty(max(need, 2 * emb["pool"].shape[0]), 32, device=eng.device)

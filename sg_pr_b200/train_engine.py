@@ -181,17 +181,22 @@ class TrainEngine:
                    "sgpr_train_backward", self._lib)
         return grads
 
-    def assemble(self, graphs: torch.Tensor, pair_idx: torch.Tensor, seed: int, step: int, want_draws: bool = False):
+    def assemble(self, graphs: torch.Tensor, pair_idx: torch.Tensor, seed: int, step: int, want_draws: bool = False,
+                 rows_filled: Optional[int] = None):
         """Device batch assembly + augmentation: graphs [M,15,N] and pair_idx [P,2] int32 on the device -> features_1
         [2P,15,N] of the mirrored batch (row 2p / 2p+1 = augmented graph a / b of listed pair p).  want_draws also
-        returns the random draws (draws [2P,12], raw jitter normals [2P,N,3]) for the parity tests."""
+        returns the random draws (draws [2P,12], raw jitter normals [2P,N,3]) for the parity tests.  Indices are the
+        caller's responsibility (SGTrainer validates them on the host from its row table); the library rejects
+        indices >= M, with M = rows_filled when the table has spare capacity."""
         graphs = self._buf(graphs, "graphs")
         if pair_idx.dtype != torch.int32 or pair_idx.device != self.device or pair_idx.dim() != 2 or pair_idx.shape[1] != 2:
             raise ValueError("pair_idx must be an int32 [P, 2] tensor on the engine's device")
         pair_idx = pair_idx.contiguous()
         M, _, N = graphs.shape
+        if rows_filled is not None:                     # a table with spare capacity: only the first rows hold graphs
+            M = min(M, int(rows_filled))
         P = int(pair_idx.shape[0])
-        if P and (int(pair_idx.min()) < 0 or int(pair_idx.max()) >= M) and want_draws:
+        if want_draws and P and (int(pair_idx.min()) < 0 or int(pair_idx.max()) >= M):   # debug/parity mode only: two syncs
             raise IndexError("pair_idx out of range")
         out = torch.empty(2 * P, 15, N, dtype=torch.float32, device=self.device)
         draws = torch.zeros(2 * P, 12, dtype=torch.float32, device=self.device) if want_draws else None
@@ -205,6 +210,18 @@ class TrainEngine:
 
     def step_count(self) -> int:
         return int(self._lib.sgpr_train_step_count(self._h))
+
+    def forward_generation(self) -> int:
+        """How many train-mode forwards this context has run.  The context keeps the activations of the LAST one only;
+        an autograd node records the value after its forward and refuses to run backward if it has moved on."""
+        return int(self._lib.sgpr_train_forward_generation(self._h))
+
+    def set_knn_ties(self, mode: str):
+        """k-NN tie rule of the train-mode forward: "cuda" (default) or "cpu" — see Engine.set_knn_ties."""
+        codes = {"cuda": 0, "cpu": 1}
+        if mode not in codes:
+            raise ValueError(f"knn_ties must be one of {sorted(codes)}, got {mode!r}")
+        _lib.check(self._lib.sgpr_train_set_knn_ties(self._h, codes[mode]), "sgpr_train_set_knn_ties", self._lib)
 
     def launch_count(self) -> int:
         return int(self._lib.sgpr_train_launch_count(self._h))

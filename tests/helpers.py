@@ -57,11 +57,50 @@ eva_pair:
     return cfg
 
 
-def tie_divergences(eng, state, graphs, k):
-    """First k-NN divergence of every (graph, branch) between the kernel and the oracle, classified by
-    oracle.classify_knn_rows: {(graph, branch): (layer, [codes of the diverging rows])}."""
+def reference_on_cuda(state, graphs, k):
+    """The reference's module code (sg_net.py:79-138 as stock PyTorch ops, sg_pr_b200/torch_baseline.py) run on cuda:0 with
+    TF32 off — the reference on its native device, ATen CUDA topk included.  Returns the oracle-shaped trace dict
+    (knn_pd / knn_idx / layer_in per layer, pooled, att) on the CPU."""
+    import torch
+    from sg_pr_b200 import dgcnn as our_dgcnn
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SG
+    from sg_pr_b200.torch_baseline import dgcnn_conv_pass
+    rec = {"knn_pd": [], "knn_idx": [], "layer_in": []}
+
+    def recording_knn(x, kk):
+        inner = -2 * torch.matmul(x.transpose(2, 1), x)
+        xx = torch.sum(x ** 2, dim=1, keepdim=True)
+        pd = -xx - inner - xx.transpose(2, 1)
+        idx = pd.topk(k=kk, dim=-1)[1]
+        rec["knn_pd"].append(pd.cpu()); rec["knn_idx"].append(idx.cpu()); rec["layer_in"].append(x.cpu())
+        return idx
+
+    margs = sgpr_args()
+    margs.K, margs.node_num, margs.gpu, margs.cuda = k, int(graphs.shape[2]), 0, "0"
+    model = SG(margs, 12)
+    model.load_state_dict(state)
+    model.cuda(0).eval()
+    old = (our_dgcnn.knn, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    our_dgcnn.knn = recording_knn
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            emb = dgcnn_conv_pass(model, graphs.cuda())
+            pooled, att = model.attention(emb)
+    finally:
+        our_dgcnn.knn, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    rec.update(emb=emb.cpu(), pooled=pooled.cpu(), att=att.cpu())
+    return rec
+
+
+def tie_divergences(eng, state, graphs, k, want=None):
+    """First k-NN divergence of every (graph, branch) between the kernel and the reference trace `want` (default: the
+    CPU oracle), classified by oracle.classify_knn_rows: {(graph, branch): (layer, [codes of the diverging rows])}."""
     from oracle import sgpr_oracle as orc
-    want = orc.embed_graphs(graphs, k, state, want_trace=True)
+    if want is None:
+        want = orc.embed_graphs(graphs, k, state, want_trace=True)
     got = eng.embed(graphs.cuda(), k, trace=True)
     knn = got["knn"].cpu().long()
     first = {}
