@@ -33,6 +33,13 @@ for _npl in (1, 2, 4):
     UNITS[f"train_npl{_npl}.o"] = ("train_inst.cu", [f"-DSGPR_INST_NPL={_npl}"], TRAIN_DEPS)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+# experiments: SGPR_EXTRA_NVCC_FLAGS="-DSGPR_UMMA_EPI_WARPS=16" SGPR_BUILD_TAG=epi16 builds libsgpr_b200_epi16.so beside
+# the product library (select it at run time with SGPR_B200_LIB=...); the product build sets neither
+EXTRA = os.environ.get("SGPR_EXTRA_NVCC_FLAGS", "").split()
+TAG = os.environ.get("SGPR_BUILD_TAG", "")
+if TAG:
+    OBJ_DIR = os.path.join(PKG, "build", "variant_" + TAG)
+    LIB = os.path.join(ROOT, "tools", "variants", f"libsgpr_b200_{TAG}.so")
 
 
 def _nvcc() -> str:
@@ -63,7 +70,7 @@ def stale() -> bool:
 
 
 def _compile(obj: str, unit, verbose: bool):
-    cmd = [_nvcc(), *NVCC_FLAGS, *unit[1], "-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, unit[0]),
+    cmd = [_nvcc(), *NVCC_FLAGS, *EXTRA, *unit[1], "-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, unit[0]),
            "-o", os.path.join(OBJ_DIR, obj)]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
@@ -77,6 +84,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not todo and os.path.exists(LIB) and not stale():
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
     with cf.ThreadPoolExecutor(max_workers=min(len(todo) or 1, os.cpu_count() or 4)) as pool:
         for obj, cmd, res in pool.map(lambda it: _compile(it[0], it[1], verbose), todo.items()):
             if res.returncode != 0:

@@ -95,6 +95,7 @@ struct sgpr_ctx {
     int zerocopy = 1;            // host entry point: read pinned buffers in place; SGPR_NO_ZEROCOPY=1 forces staged copies
     int balance = 1;             // order graphs by active rows before the fused kernel; SGPR_NO_BALANCE=1 disables it
     int dedup = 1;               // collapse trailing all-zero nodes (exact); SGPR_NO_DEDUP=1 disables it for experiments
+    int scoremat_ffma = 0;       // score matrix on fp32 FMA instead of tcgen05 (SGPR_SCOREMAT_FFMA=1; always in tests/emu)
     int knn_ties = SGPR_TIES_CUDA;   // k-NN tie rule (sgpr_set_knn_ties); SGPR_KNN_TIES=cpu|cuda sets the initial value
 };
 
@@ -128,6 +129,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
     if (const char* nd = getenv("SGPR_NO_DEDUP")) ctx->dedup = (nd[0] == '1') ? 0 : 1;
     if (const char* nz = getenv("SGPR_NO_ZEROCOPY")) ctx->zerocopy = (nz[0] == '1') ? 0 : 1;
     if (const char* nb = getenv("SGPR_NO_BALANCE")) ctx->balance = (nb[0] == '1') ? 0 : 1;
+    if (const char* sf = getenv("SGPR_SCOREMAT_FFMA")) ctx->scoremat_ffma = (sf[0] == '1') ? 1 : 0;
     if (const char* kt = getenv("SGPR_KNN_TIES")) ctx->knn_ties = (strcmp(kt, "cpu") == 0) ? SGPR_TIES_CPU : SGPR_TIES_CUDA;
     // opt in to the full shared-memory carve-out (the per-NPL objects subtract each kernel's static __shared__ bytes)
     const int optin = static_cast<int>(prop.sharedMemPerBlockOptin);
@@ -135,6 +137,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
     if (e == cudaSuccess) e = embed_optin<2>(optin);
     if (e == cudaSuccess) e = embed_optin<4>(optin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_score_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = score_matrix_umma_optin();
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_blob), ctx->off.total * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_ctrs), 2 * sizeof(int));
@@ -391,20 +394,36 @@ int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const 
     if (!pooled_rows_dev || !pooled_cols_dev || !scores_dev) return fail(SGPR_E_INVALID, "sgpr_score_matrix: NULL pointer");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = ensure(ctx->d_proj, ctx->proj_cap, static_cast<size_t>(R) * 512);
-    if (rc) return rc;
-    rc = ensure(ctx->d_blk, ctx->blk_cap, (static_cast<size_t>(R) + M) * kT);
-    if (rc) return rc;
-    float* rowblk = ctx->d_blk;
-    float* colblk = ctx->d_blk + static_cast<size_t>(R) * kT;
-    const int cap = ctx->sm_count * 8;
-    float* const no_out = nullptr;
-    SGPR_LAUNCH(sgpr_ntn_prep_kernel, R < cap ? R : cap, kThreads, 0, st, pooled_rows_dev, R, ctx->d_proj, rowblk, no_out, ctx->pw);
-    SGPR_LAUNCH(sgpr_ntn_prep_kernel, M < cap ? M : cap, kThreads, 0, st, pooled_cols_dev, M, no_out, no_out, colblk, ctx->pw);
-    const dim3 grid((M + kSmTJ - 1) / kSmTJ, (R + kSmTI - 1) / kSmTI);
-    const size_t smem = (kSmTI * 512 + kSmTI * kT) * sizeof(float);
-    SGPR_LAUNCH(sgpr_score_matrix_kernel, grid, kThreads, smem, st, ctx->d_proj, rowblk, pooled_cols_dev, colblk, R, M, scores_dev,
-                static_cast<long long>(ld_scores), ctx->pw.ntn_b, ctx->hp);
+#ifdef SGPR_EMU
+    const bool ffma = true;
+#else
+    const bool ffma = ctx->scoremat_ffma != 0;
+#endif
+    if (ffma) {
+        int rc = ensure(ctx->d_proj, ctx->proj_cap, static_cast<size_t>(R) * 512);
+        if (rc) return rc;
+        rc = ensure(ctx->d_blk, ctx->blk_cap, (static_cast<size_t>(R) + M) * kT);
+        if (rc) return rc;
+        float* rowblk = ctx->d_blk;
+        float* colblk = ctx->d_blk + static_cast<size_t>(R) * kT;
+        const int cap = ctx->sm_count * 8;
+        float* const no_out = nullptr;
+        SGPR_LAUNCH(sgpr_ntn_prep_kernel, R < cap ? R : cap, kThreads, 0, st, pooled_rows_dev, R, ctx->d_proj, rowblk, no_out, ctx->pw);
+        SGPR_LAUNCH(sgpr_ntn_prep_kernel, M < cap ? M : cap, kThreads, 0, st, pooled_cols_dev, M, no_out, no_out, colblk, ctx->pw);
+        const dim3 grid((M + kSmTJ - 1) / kSmTJ, (R + kSmTI - 1) / kSmTI);
+        const size_t smem = (kSmTI * 512 + kSmTI * kT) * sizeof(float);
+        SGPR_LAUNCH(sgpr_score_matrix_kernel, grid, kThreads, smem, st, ctx->d_proj, rowblk, pooled_cols_dev, colblk, R, M, scores_dev,
+                    static_cast<long long>(ld_scores), ctx->pw.ntn_b, ctx->hp);
+    }
+#ifndef SGPR_EMU
+    else {
+        // tcgen05 path: split/swizzled operand planes (2 launches), then the persistent UMMA kernel
+        int rc = ensure(ctx->d_proj, ctx->proj_cap, score_matrix_umma_scratch_floats(R, M));
+        if (rc) return rc;
+        score_matrix_umma_launch(ctx->sm_count, st, pooled_rows_dev, pooled_cols_dev, ctx->d_proj, scores_dev,
+                                 static_cast<long long>(ld_scores), R, M, ctx->pw, ctx->hp);
+    }
+#endif
     ctx->launches += 3;
     CUDA_TRY(cudaGetLastError());
     return SGPR_OK;

@@ -23,6 +23,12 @@ SGPR_DECL_EMBED(2)
 SGPR_DECL_EMBED(4)
 #undef SGPR_DECL_EMBED
 
+// scoremat_umma.cu: the tcgen05 score-matrix kernel (not part of the tests/emu build: inline tcgen05 PTX)
+cudaError_t score_matrix_umma_optin();
+size_t score_matrix_umma_scratch_floats(int R, int M);     // operand planes + V-block terms
+void score_matrix_umma_launch(int sm_count, cudaStream_t st, const float* pooled_rows, const float* pooled_cols, float* scratch,
+                              float* scores, long long ld, int R, int M, const PackedWeights& pw, const HeadParams& hp);
+
 namespace train {
 
 struct TrainWs;

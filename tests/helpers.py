@@ -68,11 +68,11 @@ def reference_on_cuda(state, graphs, k):
     from sg_pr_b200.torch_baseline import dgcnn_conv_pass
     rec = {"knn_pd": [], "knn_idx": [], "layer_in": []}
 
-    def recording_knn(x, kk):
+    def recording_knn(x, k):
         inner = -2 * torch.matmul(x.transpose(2, 1), x)
         xx = torch.sum(x ** 2, dim=1, keepdim=True)
         pd = -xx - inner - xx.transpose(2, 1)
-        idx = pd.topk(k=kk, dim=-1)[1]
+        idx = pd.topk(k=k, dim=-1)[1]
         rec["knn_pd"].append(pd.cpu()); rec["knn_idx"].append(idx.cpu()); rec["layer_in"].append(x.cpu())
         return idx
 
