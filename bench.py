@@ -30,6 +30,7 @@ from sg_pr_b200 import synth  # noqa: E402
 BATCH, NODES, K_NN, SEQ_GRAPHS = 128, 64, 20, 1000
 ALG_BYTES_PER_PAIR = 128 * NODES + 4          # 2x15xNx4 read + (2N+1)x4 written = 8,196 B at N=64
 ALG_FLOP_PER_PAIR = 12.9e6                    # SURVEY §8(d), exact refactored form
+FFMA_PEAK_TFLOPS = 71.65                      # measured on this pool: profiles/r01_microbench_pipes.json (tools/microbench_ffma.cu)
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "graph-pairs/sec @ batch 128, 64-node graphs, k=20"
 WORKLOAD = "eval_batch synthetic sequence of 1000 graphs, 64 nodes x 12 feat, k=20, batch 128 (BASELINE configs[1])"
@@ -94,6 +95,7 @@ class ClockSampler:
 def time_cpu_oracle(state, f1, f2, budget_s: float, max_batches: int):
     """Oracle port of the reference's CPU SG.forward on all host threads: returns (pairs/s, pairs timed, seconds)."""
     from oracle import sgpr_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
     orc.forward_pairs(f1[0][:16], f2[0][:16], K_NN, state)            # warm-up (thread pool, oneDNN primitives)
     done, t0 = 0, time.perf_counter()
     for i in range(max_batches):
@@ -112,6 +114,8 @@ def run_reference_arm(args, rank: int):
     if rank != 0:
         return
     from oracle import sgpr_oracle as orc
+    # every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which is not "the reference on the box's cores"
+    torch.set_num_threads(os.cpu_count() or 1)
     state = load_state()
     f1, f2 = build_batches(4, seed=0)
     threads = torch.get_num_threads()
@@ -143,6 +147,112 @@ def run_reference_arm(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------------
+# extra keys of the JSON line (VERDICT r01 task 2): the other BASELINE configs on the driver's clock
+# ------------------------------------------------------------------------------------------------------------------------
+def measure_scan(eng, dev, rank, world, dist, graphs_m=4000, steps=5, warmup=2):
+    """BASELINE configs[3]: all ordered pairs of a 4000-graph sequence, row blocks sharded over the ranks (sg_pr_b200/scan.py),
+    phases timed with CUDA events on every rank, max over ranks."""
+    from sg_pr_b200 import scan
+    graphs = synth.make_graphs(graphs_m, NODES, K_NN, seed=42).to(dev)
+    sc = scan.SequenceScanner(eng, rank, world)
+    names = ("embed", "gather_pooled", "score", "gather_scores")
+
+    def one():
+        ev = {"start": torch.cuda.Event(enable_timing=True)}
+        ev["start"].record()
+
+        def mark(name):
+            ev[name] = torch.cuda.Event(enable_timing=True)
+            ev[name].record()
+        mat, _ = sc.scan(graphs, K_NN, marks=mark)
+        return mat, ev
+    for _ in range(warmup):
+        one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    acc = torch.zeros(5, dtype=torch.float64)
+    for _ in range(steps):
+        if world > 1:
+            dist.barrier()
+        mat, ev = one()
+        torch.cuda.synchronize()
+        prev = "start"
+        for i, name in enumerate(names):
+            acc[i] += ev[prev].elapsed_time(ev[name])
+            prev = name
+        acc[4] += ev["start"].elapsed_time(ev[names[-1]])
+    t = (acc / steps).to(dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    embed_ms, gp_ms, score_ms, gs_ms, total_ms = (float(x) for x in t.tolist())
+    idx = synth.make_sequence_pairs(graphs_m, 512, seed=9).to(dev)
+    fused, _, _ = eng.forward_pairs(graphs[idx[:, 0]], graphs[idx[:, 1]], K_NN)
+    err = float((mat[idx[:, 0], idx[:, 1]] - fused).abs().max())
+    return {"workload": f"all ordered pairs of a {graphs_m}-graph synthetic sequence (BASELINE configs[3]), row blocks over "
+                        f"{world} GPU(s), one in-place NCCL all-gather of the score rows",
+            "value": graphs_m * graphs_m / (total_ms * 1e-3), "unit": "ordered graph-pairs/s", "graphs": graphs_m,
+            "ms_per_scan": total_ms,
+            "phases_ms": {"embed_row_block": embed_ms, "allgather_pooled": gp_ms, "score_row_block_tcgen05": score_ms,
+                          "allgather_scores": gs_ms},
+            "allgather_share": (gp_ms + gs_ms) / total_ms if total_ms > 0 else None,
+            "score_matrix_bytes": graphs_m * graphs_m * 4, "max_abs_diff_vs_fused_pair_kernel": err,
+            "timing": "CUDA events per phase, mean of %d scans after %d warm-ups, max over ranks" % (steps, warmup)}
+
+
+def measure_train(state, dev, steps=30, warmup=5):
+    """BASELINE configs[2]: one optimiser step (train-mode forward, BCE, backward, Adam) on 128 listed pairs -> 256 forward
+    pairs, N = 64, k = 20, inputs in HBM — the device half of SGTrainer.process_batch (sgpr_train_step, mirrored)."""
+    from sg_pr_b200.train_engine import TrainEngine
+    f1, target = synth.make_train_batch(BATCH, NODES, K_NN, seed=1)
+    f1, target = f1.to(dev), target.to(dev)
+    eng = TrainEngine(dev)
+    eng.set_state(state)
+    eng.set_optimizer(1e-3, 5e-4)
+    for _ in range(warmup):
+        eng.step(f1, None, target, K_NN, mirrored=True)
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _ = eng.step(f1, None, target, K_NN, mirrored=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"workload": "main_sg.py training step, 128 listed synthetic pairs -> 256 forward pairs (BASELINE configs[2])",
+           "ms_per_step": ms, "listed_pairs_per_s": BATCH / (ms * 1e-3), "launches_per_step": (eng.launch_count() - l0) // steps,
+           "loss_after": float(loss), "what": "sgpr_train_step (mirrored), inputs in HBM, CUDA events"}
+    eng.close()
+    return out
+
+
+def measure_sweep(eng, dev, batch=512, iters=30, warmup=5):
+    """BASELINE configs[4]: node-count sweep 16/32/64/128 x k in {10, 20} at batch 512 (k = 20 > N = 16 is invalid: topk
+    raises in the reference)."""
+    rows = []
+    for n in (16, 32, 64, 128):
+        for k in (10, 20):
+            if k > n - 1:
+                continue
+            f1, f2 = synth.make_pair_batch(batch, n, k, seed=2)
+            f1, f2 = f1.to(dev), f2.to(dev)
+            for _ in range(warmup):
+                eng.forward_pairs(f1, f2, k)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                eng.forward_pairs(f1, f2, k)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / iters * 1e3
+            rows.append({"node_num": n, "k": k, "batch": batch, "us_per_batch": us, "pairs_per_s": batch / us * 1e6,
+                         "hbm_GBps_algorithmic": batch * (128 * n + 4) / us * 1e-3})
+    return {"workload": "node-count sweep, batch 512 (BASELINE configs[4]); inputs in HBM (L2-resident across iterations)", "rows": rows}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,6 +260,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the scan / train / sweep keys (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "ours" else 1)
 
@@ -186,6 +297,9 @@ def main():
     f1_cpu, f2_cpu = build_batches(num_batches, seed=100 + rank)
     f1_dev, f2_dev = f1_cpu.to(dev), f2_cpu.to(dev)
     f1_pin, f2_pin = f1_cpu.pin_memory(), f2_cpu.pin_memory()
+    from sg_pr_b200.engine import compact_graphs
+    c1_pin = compact_graphs(f1_cpu.view(-1, synth.NUM_CHANNELS, NODES)).view(num_batches, BATCH, -1).pin_memory()
+    c2_pin = compact_graphs(f2_cpu.view(-1, synth.NUM_CHANNELS, NODES)).view(num_batches, BATCH, -1).pin_memory()
 
     def barrier():
         if world > 1:
@@ -201,6 +315,27 @@ def main():
         with torch.no_grad():
             prediction, _, _ = model({"features_1": f1_pin[j], "features_2": f2_pin[j]})
         return prediction.cpu()
+
+    def step_e2e_pageable(i):          # what the reference's own callers hand over: plain torch.FloatTensor (sg_net.py:517-519)
+        j = i % num_batches
+        with torch.no_grad():
+            prediction, _, _ = model({"features_1": f1_cpu[j], "features_2": f2_cpu[j]})
+        return prediction.cpu()
+
+    def step_e2e_compact(i):           # 13-byte nodes, pinned, read in place
+        j = i % num_batches
+        score, _, _ = eng.forward_pairs_compact(c1_pin[j], c2_pin[j], NODES, K_NN, want_att=False)
+        return score.cpu()
+
+    def time_host_loop(fn):
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            fn(args.warmup + i)
+        barrier()
+        return (time.perf_counter() - t0) * 1e3
 
     # ---------------- value: device-resident inputs ----------------
     for i in range(args.warmup):
@@ -249,11 +384,21 @@ def main():
         eng.forward_pairs_host(f1_pin[j], f2_pin[j], K_NN, want_att=False, out=out)
     barrier()
     cabi_ms = (time.perf_counter() - t0) * 1e3
+    page_ms = time_host_loop(step_e2e_pageable)
+    compact_ms = time_host_loop(step_e2e_compact)
 
-    times = torch.tensor([dev_ms, e2e_ms, cabi_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_ms, cabi_ms, page_ms, compact_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, cabi_ms = (float(x) for x in times.tolist())
+    dev_ms, e2e_ms, cabi_ms, page_ms, compact_ms = (float(x) for x in times.tolist())
+
+    extras = {}
+    if not args.no_extras:
+        extras["scan"] = measure_scan(eng, dev, rank, world, dist)
+        if rank == 0:
+            extras["train"] = measure_train(state, dev)
+            extras["sweep"] = measure_sweep(eng, dev)
+        barrier()
 
     if rank == 0:
         total_pairs = world * BATCH * args.steps
@@ -289,7 +434,13 @@ def main():
                     "h2d_bytes_per_step": per_batch, "d2h_bytes_per_step": BATCH * 4,
                     "api": "sg_pr_b200.sg_net.SG.forward(data) with pinned CPU tensors + prediction.cpu()",
                     "ms_per_step": e2e_ms / args.steps,
-                    "c_abi_host_call": {"value": total_pairs / (cabi_ms * 1e-3), "ms_per_step": cabi_ms / args.steps}},
+                    "c_abi_host_call": {"value": total_pairs / (cabi_ms * 1e-3), "ms_per_step": cabi_ms / args.steps},
+                    "pageable_inputs": {"value": total_pairs / (page_ms * 1e-3), "ms_per_step": page_ms / args.steps,
+                                        "api": "the same call with plain (pageable) torch.FloatTensor inputs, as the reference's "
+                                               "callers build them (sg_net.py:517-519): two staged H2D copies, then the kernel"},
+                    "compact_inputs": {"value": total_pairs / (compact_ms * 1e-3), "ms_per_step": compact_ms / args.steps,
+                                       "h2d_bytes_per_step": int(2 * BATCH * c1_pin.shape[-1]),
+                                       "api": "Engine.forward_pairs_compact on pinned 13-byte-per-node records + score.cpu()"}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -300,9 +451,12 @@ def main():
                          "avg_kernel_us": kernel_s * 1e6,
                          "note": "path is issue/latency-bound (~1570 flop/B, SURVEY §8d); see compute_roofline"},
             "compute_roofline": {"bound": "fp32-fma", "achieved_tflops": BATCH * ALG_FLOP_PER_PAIR / kernel_s / 1e12,
-                                 "peak_tflops_nominal": 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12,
+                                 "peak_tflops": FFMA_PEAK_TFLOPS, "frac": BATCH * ALG_FLOP_PER_PAIR / kernel_s / 1e12 / FFMA_PEAK_TFLOPS,
+                                 "peak_source": "measured FFMA throughput of this pool's B200 (tools/microbench_ffma.cu, "
+                                                "profiles/r01_microbench_pipes.json), not a nominal figure",
                                  "flop_per_pair": ALG_FLOP_PER_PAIR},
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             v, n, dt = time_cpu_oracle(state, f1_cpu, f2_cpu, budget_s=15.0, max_batches=16)
             line["cpu_baseline"] = {"value": v, "unit": "graph-pairs/s", "cores": torch.get_num_threads(), "kind": "port",

@@ -117,6 +117,22 @@ int sgpr_forward_pairs_host(sgpr_ctx* ctx, const float* f1_host, const float* f2
                             float* score_host, float* att1_host, float* att2_host);
 
 /*
+ * Compact input: the [15][N] block the reference builds per graph (sg_net.py:270-299) is 3 coordinates
+ * plus a ONE-HOT label per node — 60 bytes a node for 13 bytes of information.  A compact graph record is
+ *     float   xyz[3][N];     rows 0-2 of the block, unchanged
+ *     uint8_t label[N];      0..11 = the one-hot row that holds the 1; any other value = no label (zero pad)
+ * padded to sgpr_compact_stride(N) = ceil16(13 N) bytes; records are contiguous and 16-byte aligned.  The kernel pulls
+ * one record per graph (device memory, or pinned host memory read in place over PCIe) and expands it in shared memory
+ * into the block the one-hot entry points read — results are bit-identical to sgpr_forward_pairs / sgpr_embed on the
+ * expanded input.  4.6x fewer input bytes per pair (1,664 instead of 7,680 at N = 64).
+ */
+size_t sgpr_compact_stride(int N);
+int sgpr_forward_pairs_compact(sgpr_ctx* ctx, const void* graphs1, const void* graphs2, int B, int N, int k,
+                               float* score_dev, float* att1_dev, float* att2_dev, void* stream);
+int sgpr_embed_compact(sgpr_ctx* ctx, const void* graphs, int M, int N, int k, float* pooled_dev, float* att_dev,
+                       float* emb_dev, void* stream);
+
+/*
  * Per-graph half of the path (sg_net.py:123,126 for one side): node embeddings + attention pooling.
  *   graphs_dev : [M][15][N]
  *   pooled_dev : [M][32]        AttentionModule `representation`            layers_batch.py:38

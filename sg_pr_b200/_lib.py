@@ -47,6 +47,11 @@ SYMBOLS = {
     "sgpr_packed_size": (C.c_size_t, []),
     "sgpr_pack_weights_host": (C.c_int, [C.POINTER(SgprWeights), c_float_p, c_float_p, C.POINTER(C.c_size_t)]),
     "sgpr_launch_count": (C.c_int64, [C.c_void_p]),
+    "sgpr_compact_stride": (C.c_size_t, [C.c_int]),
+    "sgpr_forward_pairs_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sgpr_embed_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
     "sgpr_set_knn_ties": (C.c_int, [C.c_void_p, C.c_int]),
     "sgpr_get_knn_ties": (C.c_int, [C.c_void_p]),
     "sgpr_topk_cpu_rule_host": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),

@@ -137,7 +137,9 @@ int sgpr_create(sgpr_ctx** out, int device) {
     if (e == cudaSuccess) e = embed_optin<2>(optin);
     if (e == cudaSuccess) e = embed_optin<4>(optin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_score_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+#ifndef SGPR_EMU
     if (e == cudaSuccess) e = score_matrix_umma_optin();
+#endif
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_blob), ctx->off.total * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_ctrs), 2 * sizeof(int));
@@ -246,7 +248,7 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     // launch is short; results are unchanged.  Not worth its ~3 us pre-pass while every graph has its own resident CTA
     // (the hardware's CTA->SM placement cannot be steered, profiles/r01_variants_timeline.txt), and skipped when the
     // graphs sit in pinned host memory (the pre-pass would pull them over PCIe a second time).
-    if (ctx->balance && a.G > capacity && is_device_memory(a.g0)) {
+    if (ctx->balance && !a.compact && a.G > capacity && is_device_memory(a.g0)) {
         int rc = ensure(ctx->d_order, ctx->order_cap, static_cast<size_t>(2) * a.G);
         if (rc) return rc;
         const int resident = (a.G <= capacity) ? 1 : 0;
@@ -270,7 +272,7 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
 }
 
 int forward_pairs_impl(sgpr_ctx* ctx, const float* f1, const float* f2, int B, int N, int k, float* score, float* att1,
-                       float* att2, cudaStream_t st) {
+                       float* att2, cudaStream_t st, int compact = 0) {
     int rc = ensure(ctx->d_pooled, ctx->pooled_cap, static_cast<size_t>(2) * B * kF3);
     if (rc) return rc;
     if (static_cast<size_t>(B) > ctx->counters_cap) {
@@ -279,7 +281,7 @@ int forward_pairs_impl(sgpr_ctx* ctx, const float* f1, const float* f2, int B, i
         CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_cap * sizeof(int), st));
     }
     EmbedArgs a{};
-    a.g0 = f1; a.g1 = f2; a.G = 2 * B; a.N = N; a.k = k; a.pairs = 1;
+    a.g0 = f1; a.g1 = f2; a.G = 2 * B; a.N = N; a.k = k; a.pairs = 1; a.compact = compact;
     a.pooled = ctx->d_pooled; a.att0 = att1; a.att1 = att2; a.emb = nullptr;
     a.score = score; a.counters = ctx->d_counters; a.trace_knn = nullptr; a.trace_layers = nullptr;
     return launch_embed(ctx, a, st);
@@ -299,6 +301,41 @@ int sgpr_forward_pairs(sgpr_ctx* ctx, const float* f1_dev, const float* f2_dev, 
     if (!f1_dev || !f2_dev || !score_dev) return fail(SGPR_E_INVALID, "sgpr_forward_pairs: NULL feature/score pointer");
     DeviceGuard guard(ctx->device);
     return forward_pairs_impl(ctx, f1_dev, f2_dev, B, N, k, score_dev, att1_dev, att2_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t sgpr_compact_stride(int N) { return (static_cast<size_t>(N) * 13 + 15) & ~static_cast<size_t>(15); }
+
+int sgpr_forward_pairs_compact(sgpr_ctx* ctx, const void* g1, const void* g2, int B, int N, int k, float* score_dev,
+                               float* att1_dev, float* att2_dev, void* stream) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_forward_pairs_compact: ctx is NULL");
+    if (!ctx->has_weights) return fail(SGPR_E_NOWEIGHTS, "sgpr_forward_pairs_compact: call sgpr_set_weights first");
+    int rc = check_shape("sgpr_forward_pairs_compact", B, N, k);
+    if (rc) return rc;
+    if (B == 0) return SGPR_OK;
+    if (!g1 || !g2 || !score_dev) return fail(SGPR_E_INVALID, "sgpr_forward_pairs_compact: NULL graph/score pointer");
+    if ((reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(g2)) & 15u)
+        return fail(SGPR_E_INVALID, "sgpr_forward_pairs_compact: graph records must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    return forward_pairs_impl(ctx, static_cast<const float*>(g1), static_cast<const float*>(g2), B, N, k, score_dev, att1_dev,
+                              att2_dev, static_cast<cudaStream_t>(stream), static_cast<int>(sgpr_compact_stride(N)));
+}
+
+int sgpr_embed_compact(sgpr_ctx* ctx, const void* graphs, int M, int N, int k, float* pooled_dev, float* att_dev,
+                       float* emb_dev, void* stream) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_embed_compact: ctx is NULL");
+    if (!ctx->has_weights) return fail(SGPR_E_NOWEIGHTS, "sgpr_embed_compact: call sgpr_set_weights first");
+    int rc = check_shape("sgpr_embed_compact", M, N, k);
+    if (rc) return rc;
+    if (M == 0) return SGPR_OK;
+    if (!graphs || !pooled_dev) return fail(SGPR_E_INVALID, "sgpr_embed_compact: NULL graphs/pooled pointer");
+    if (reinterpret_cast<uintptr_t>(graphs) & 15u)
+        return fail(SGPR_E_INVALID, "sgpr_embed_compact: graph records must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    EmbedArgs a{};
+    a.g0 = static_cast<const float*>(graphs); a.g1 = nullptr; a.G = M; a.N = N; a.k = k; a.pairs = 0;
+    a.compact = static_cast<int>(sgpr_compact_stride(N));
+    a.pooled = pooled_dev; a.att0 = att_dev; a.att1 = nullptr; a.emb = emb_dev;
+    return launch_embed(ctx, a, static_cast<cudaStream_t>(stream));
 }
 
 int sgpr_forward_pairs_host(sgpr_ctx* ctx, const float* f1_host, const float* f2_host, int B, int N, int k,

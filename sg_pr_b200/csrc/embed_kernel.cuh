@@ -68,6 +68,8 @@ struct EmbedArgs {
     int N, k, KS;           // KS = k rounded up to 4 (neighbour-list row stride in 16-bit entries)
     int pairs;
     int dedup;              // 1: collapse trailing all-zero nodes into one row (exact); 0: process every node
+    int compact;            // 0: graphs are [15][N] fp32 blocks; else: compact records of `compact` bytes each —
+                            //    xyz [3][N] fp32 followed by N uint8 labels (0..11, anything else = no label), see sgpr_b200.h
     float* pooled;          // [G][32]
     float* att0;            // pairs: [B][N] side 0 ; else [G][N]   (may be null)
     float* att1;            // pairs: [B][N] side 1                 (may be null)
@@ -828,7 +830,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
     for (int e = tid; e < 2 * NMAX; e += kThreads) sXX[e] = 0.0f;
     __syncthreads();
 
-    const uint32_t inBytes = static_cast<uint32_t>(kInCh * N * 4);
+    const uint32_t inBytes = A.compact ? static_cast<uint32_t>(A.compact) : static_cast<uint32_t>(kInCh * N * 4);
 
     __shared__ int sSlot;
 #pragma unroll 1
@@ -842,8 +844,8 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         }
         if (slot >= A.G) break;
         const int g = A.order ? __ldg(A.order + slot) : slot;
-        const float* gin = A.pairs ? (((g & 1) ? A.g1 : A.g0) + static_cast<size_t>(g >> 1) * kInCh * N)
-                                   : (A.g0 + static_cast<size_t>(g) * kInCh * N);
+        const float* gin = reinterpret_cast<const float*>(
+            reinterpret_cast<const unsigned char*>((A.pairs && (g & 1)) ? A.g1 : A.g0) + static_cast<size_t>(A.pairs ? (g >> 1) : g) * inBytes);
         const bool bulk_ok = ((inBytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0);
         uint8_t* tk = A.trace_knn ? A.trace_knn + static_cast<size_t>(g) * 6 * N * k : nullptr;
         float* tl = A.trace_layers ? A.trace_layers + static_cast<size_t>(g) * 6 * N * 64 : nullptr;
@@ -856,7 +858,18 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             bulk_g2s(sW, W.w_s2, 64 * 128 * 4, barW);
         }
         if (bulk_ok) { mbar_wait(barIn, phIn); phIn ^= 1; }
-        else { for (int e = tid; e < kInCh * N; e += kThreads) sIn[e] = __ldg(gin + e); __syncthreads(); }
+        else { for (int e = tid; e < static_cast<int>(inBytes / 4); e += kThreads) sIn[e] = __ldg(gin + e); __syncthreads(); }
+        if (A.compact) {
+            // expand the record in place into the [15][N] block the rest of the kernel reads: rows 0-2 (xyz) already sit
+            // where they belong, the N label bytes behind them become the twelve one-hot rows (sg_net.py:270-286)
+            const int lab = (tid < N) ? reinterpret_cast<const uint8_t*>(sIn)[12 * N + tid] : 255;
+            __syncthreads();
+            if (tid < N) {
+#pragma unroll
+                for (int c = 0; c < kLabels; ++c) sIn[(3 + c) * N + tid] = (lab == c) ? 1.0f : 0.0f;
+            }
+            __syncthreads();
+        }
 
         SGPR_TL(1);
         // ---- layer-0 tile (x, y, z, 0) + squared norms for every node, and the last non-zero node ----

@@ -92,6 +92,25 @@ def pack_weights_host(state: Dict[str, "torch.Tensor"]):
     return blob, head, dict(zip(names, [int(x) for x in offs]))
 
 
+def compact_graphs(blocks: torch.Tensor, stride: Optional[int] = None) -> torch.Tensor:
+    """[B, 15, N] one-hot blocks (CPU) -> uint8 [B, ceil16(13 N)] compact records: xyz rows as they are, then one label
+    byte per node (index of the one-hot 1; 255 where the node has none, e.g. zero pads).  Raises if a node's label rows
+    are not one-hot / all-zero — such a block has no compact form."""
+    b, c, n = blocks.shape
+    if c != IN_CHANNELS or blocks.dtype != torch.float32:
+        raise ValueError(f"expected float32 [B, {IN_CHANNELS}, N], got {blocks.dtype} {tuple(blocks.shape)}")
+    sem = blocks[:, 3:, :]
+    ones = (sem == 1.0).sum(dim=1)
+    if not bool((((ones == 1) & ((sem != 0).sum(dim=1) == 1)) | ((sem != 0).sum(dim=1) == 0)).all()):
+        raise ValueError("label rows are not one-hot: this batch has no compact form")
+    label = torch.where(ones == 1, sem.argmax(dim=1), torch.full_like(ones, 255)).to(torch.uint8)
+    stride = stride or ((13 * n + 15) // 16) * 16
+    out = torch.zeros(b, stride, dtype=torch.uint8)
+    out[:, :12 * n] = blocks[:, :3, :].contiguous().view(b, 3 * n).view(torch.uint8).view(b, 12 * n)
+    out[:, 12 * n:13 * n] = label
+    return out
+
+
 def _check_graphs(t: torch.Tensor, what: str) -> Tuple[int, int]:
     if t.dim() != 3 or t.shape[1] != IN_CHANNELS:
         raise ValueError(f"{what}: expected [B, {IN_CHANNELS}, N], got {tuple(t.shape)}")
@@ -211,6 +230,43 @@ class Engine:
                                                 att2.data_ptr() if att2 is not None else None),
               "sgpr_forward_pairs_host", self._lib)
         return score, att1, att2
+
+    # ---- compact input (13 bytes per node instead of 60) -------------------------------------------------------------
+    def compact_stride(self, n: int) -> int:
+        return int(self._lib.sgpr_compact_stride(int(n)))
+
+    def _check_compact(self, g: torch.Tensor, n: int, what: str) -> torch.Tensor:
+        if g.dtype != torch.uint8 or g.dim() != 2 or g.shape[1] != self.compact_stride(n):
+            raise ValueError(f"{what}: expected uint8 [B, {self.compact_stride(n)}] compact records (see compact_graphs), "
+                             f"got {g.dtype} {tuple(g.shape)}")
+        return self._dev(g, what, True)
+
+    def forward_pairs_compact(self, g1: torch.Tensor, g2: torch.Tensor, n: int, k: int, want_att: bool = True):
+        """Compact records in (device or pinned host), device tensors out — bit-identical to forward_pairs on the expanded
+        [B,15,N] blocks."""
+        g1, g2 = self._check_compact(g1, n, "graphs_1"), self._check_compact(g2, n, "graphs_2")
+        if g1.shape != g2.shape:
+            raise ValueError("graphs_1 / graphs_2 differ in shape")
+        b = int(g1.shape[0])
+        score = torch.empty(b, dtype=torch.float32, device=self.device)
+        att1 = torch.empty((b, n, 1), dtype=torch.float32, device=self.device) if want_att else None
+        att2 = torch.empty((b, n, 1), dtype=torch.float32, device=self.device) if want_att else None
+        check(self._lib.sgpr_forward_pairs_compact(self._ctx, g1.data_ptr(), g2.data_ptr(), b, int(n), int(k), score.data_ptr(),
+                                                   att1.data_ptr() if want_att else None,
+                                                   att2.data_ptr() if want_att else None, self._stream()),
+              "sgpr_forward_pairs_compact", self._lib)
+        return score, att1, att2
+
+    def embed_compact(self, graphs: torch.Tensor, n: int, k: int, want_att: bool = False) -> dict:
+        graphs = self._check_compact(graphs, n, "graphs")
+        m = int(graphs.shape[0])
+        out = {"pooled": torch.empty(m, F3, dtype=torch.float32, device=self.device)}
+        if want_att:
+            out["att"] = torch.empty(m, n, 1, dtype=torch.float32, device=self.device)
+        check(self._lib.sgpr_embed_compact(self._ctx, graphs.data_ptr(), m, int(n), int(k), out["pooled"].data_ptr(),
+                                           out["att"].data_ptr() if want_att else None, None, self._stream()),
+              "sgpr_embed_compact", self._lib)
+        return out
 
     # ---- embed-once / score-many ------------------------------------------------------------------------------
     def embed(self, graphs: torch.Tensor, k: int, want_att: bool = False, want_emb: bool = False, trace: bool = False):

@@ -9,8 +9,11 @@ so the scan is: embed each graph ONCE (fused kernel, csrc/embed_kernel.cuh), the
 
 Sharding over R ranks (one process per GPU, `torch.distributed`):
     rank r embeds graphs [lo_r, hi_r)  ->  all-gather of the pooled vectors (M x 32 fp32, 512 KB at M = 4000)
-    rank r scores rows  [lo_r, hi_r) against all M columns  ->  ONE all-gather of the [rows, M] score blocks
+    rank r scores rows  [lo_r, hi_r) against all M columns, writing its block INTO the final [M, M] buffer
+                                     ->  ONE in-place all-gather of the score rows (64 MB at M = 4000)
 Both collectives are NCCL all-gathers over NVLink (gloo in the CPU tests); there is no reduction and no all-to-all.
+(The pooled all-gather could be traded for every rank embedding all M graphs; sharding the embed is the faster choice
+from 2 GPUs up — bench.py's `scan` key reports each phase.)
 The compute callables are injected so that the row-block / gather logic is testable on CPU with world_size 2.
 """
 from __future__ import annotations
@@ -28,33 +31,61 @@ def row_block(m: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def _all_gather_rows(local: torch.Tensor, m: int, world: int, group=None) -> torch.Tensor:
-    """All-gather row blocks of unequal height (at most one row apart) into [m, ...]: pad to the tallest block."""
+def _backend(group=None) -> str:
+    return str(dist.get_backend(group)) if dist.is_initialized() else "none"
+
+
+def _all_gather_rows(local: torch.Tensor, m: int, world: int, group=None, out: Optional[torch.Tensor] = None,
+                     rank: Optional[int] = None) -> torch.Tensor:
+    """All-gather row blocks into [m, ...].
+
+    m % world == 0 (equal blocks): ONE collective straight into the final buffer, no staging copy.  When `local` already
+    IS this rank's slice of `out` (the score block is computed in place there) the NCCL all-gather runs in place.
+    Otherwise (blocks one row apart): blocks are padded to the tallest, gathered, and the padding rows dropped."""
     if world == 1:
-        return local
+        if out is not None and out.data_ptr() != local.data_ptr():
+            out.copy_(local)
+        return local if out is None else out
+    tail = tuple(local.shape[1:])
+    if m % world == 0:
+        if out is None:
+            out = torch.empty((m,) + tail, dtype=local.dtype, device=local.device)
+        src = local
+        if _backend(group) != "nccl" and rank is not None and src.data_ptr() == out[rank * (m // world):].data_ptr():
+            src = local.clone()                     # gloo (CPU tests): no aliasing of input and output
+        dist.all_gather_into_tensor(out, src.contiguous(), group=group)
+        return out
     tallest = -(-m // world)
-    pad = torch.zeros((tallest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad = torch.zeros((tallest,) + tail, dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    out = torch.empty((world * tallest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad, group=group)
-    pieces = []
+    buf = torch.empty((world * tallest,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    if out is None:
+        out = torch.empty((m,) + tail, dtype=local.dtype, device=local.device)
     for r in range(world):
         lo, hi = row_block(m, r, world)
-        pieces.append(out[r * tallest: r * tallest + (hi - lo)])
-    return torch.cat(pieces, dim=0)
+        out[lo:hi] = buf[r * tallest: r * tallest + (hi - lo)]
+    return out
 
 
 def scan_all_pairs(graphs: torch.Tensor, k: int,
                    embed_fn: Callable[[torch.Tensor, int], torch.Tensor],
-                   score_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+                   score_fn: Callable[..., torch.Tensor],
                    rank: int = 0, world: int = 1, group=None, gather_scores: bool = True,
-                   graphs_are_local: bool = False):
+                   graphs_are_local: bool = False, marks: Optional[Callable[[str], None]] = None):
     """Score matrix S[i, j] = score(graph i as side 1, graph j as side 2) for a sequence of M graphs.
 
     graphs : [M, 15, N] (every rank holds the sequence) or, with graphs_are_local, this rank's row block only.
-    embed_fn(graph_block, k) -> pooled [rows, 32];  score_fn(pooled_rows, pooled_all) -> [rows, M].
+    embed_fn(graph_block, k) -> pooled [rows, 32];  score_fn(pooled_rows, pooled_all, out) -> [rows, M] written into the
+    view `out` of the final matrix (out may be None: allocate).
+    `marks(name)`: optional callback at the phase boundaries ("embed", "gather_pooled", "score", "gather_scores") —
+    bench.py records CUDA events there.
     Returns (scores, (lo, hi)): the full [M, M] matrix on every rank when gather_scores, else this rank's rows.
+
+    Collectives: the pooled vectors (M x 32 fp32, 512 KB at M = 4000) and — the one exchange of real size — the score
+    rows, gathered by ONE all-gather directly into the [M, M] result (in place: every rank computes its block inside it).
     """
+    mark = marks or (lambda name: None)
     if graphs_are_local:
         counts = torch.tensor([graphs.shape[0]], dtype=torch.int64, device=graphs.device)
         if world > 1:
@@ -69,11 +100,21 @@ def scan_all_pairs(graphs: torch.Tensor, k: int,
         lo, hi = row_block(m, rank, world)
         mine = graphs[lo:hi]
     pooled_rows = embed_fn(mine.contiguous(), k)
+    mark("embed")
     pooled_all = _all_gather_rows(pooled_rows, m, world, group)
-    block = score_fn(pooled_rows, pooled_all)
+    mark("gather_pooled")
     if not gather_scores:
+        block = score_fn(pooled_rows, pooled_all, None)
+        mark("score")
         return block, (lo, hi)
-    return _all_gather_rows(block, m, world, group), (lo, hi)
+    full = torch.empty((m, m), dtype=pooled_all.dtype, device=pooled_all.device)
+    block = score_fn(pooled_rows, pooled_all, full[lo:hi])
+    if block.data_ptr() != full[lo:hi].data_ptr():      # a score_fn that ignores `out`
+        full[lo:hi] = block
+    mark("score")
+    _all_gather_rows(full[lo:hi], m, world, group, out=full, rank=rank)
+    mark("gather_scores")
+    return full, (lo, hi)
 
 
 class SequenceScanner:
@@ -87,12 +128,14 @@ class SequenceScanner:
             return torch.empty(0, 32, dtype=torch.float32, device=self.engine.device)
         return self.engine.embed(block.to(self.engine.device, non_blocking=True), k)["pooled"]
 
-    def _score(self, rows: torch.Tensor, cols: torch.Tensor) -> torch.Tensor:
-        return self.engine.score_matrix(rows, cols)
+    def _score(self, rows: torch.Tensor, cols: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if rows.shape[0] == 0:
+            return out if out is not None else torch.empty(0, cols.shape[0], dtype=torch.float32, device=self.engine.device)
+        return self.engine.score_matrix(rows, cols, out=out)
 
-    def scan(self, graphs: torch.Tensor, k: int, gather_scores: bool = True, graphs_are_local: bool = False):
+    def scan(self, graphs: torch.Tensor, k: int, gather_scores: bool = True, graphs_are_local: bool = False, marks=None):
         return scan_all_pairs(graphs, k, self._embed, self._score, self.rank, self.world, self.group,
-                              gather_scores, graphs_are_local)
+                              gather_scores, graphs_are_local, marks)
 
     def top_matches(self, graphs: torch.Tensor, k: int, per_row: int = 5, exclude_window: int = 50):
         """Loop-closure style query: for each row graph of this rank, the best-scoring earlier frames outside a

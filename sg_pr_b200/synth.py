@@ -61,3 +61,13 @@ def make_sequence_pairs(num_graphs: int, num_pairs: int, seed: int = 0) -> torch
     """`[num_pairs, 2]` int64 ordered index pairs drawn from a sequence of `num_graphs` graphs."""
     g = torch.Generator().manual_seed(seed + 7919)
     return torch.randint(0, num_graphs, (num_pairs, 2), generator=g)
+
+
+def make_train_batch(listed: int, node_num: int = 64, k: int = 20, seed: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
+    """What `SGTrainer.process_batch` feeds the model for `listed` pairs (sg_net.py:324-331): every pair in both orders,
+    so features_1 is `[2*listed, 15, N]` with rows (a0, b0, a1, b1, ...) and features_2[p] == features_1[p ^ 1].
+    Returns (features_1, target [2*listed]) — half the listed pairs positive (BASELINE config 3: p_thresh 3 m)."""
+    a, b = make_pair_batch(listed, node_num, k, seed=seed)
+    f1 = torch.stack([a, b], dim=1).reshape(2 * listed, NUM_CHANNELS, node_num).contiguous()
+    target = torch.tensor([float(i % 2 == 0) for i in range(listed)]).repeat_interleave(2)
+    return f1, target

@@ -31,3 +31,47 @@ def test_scan_matches_pairwise_forward(kitti_state):
     vals, nbr, _ = sc.top_matches(graphs, 20, per_row=3, exclude_window=10)
     assert vals.shape == (m, 3) and int(nbr[-1].max()) <= m - 1 - 10
     eng.close()
+
+
+def _nccl_worker(rank, world, port, m, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from sg_pr_b200.engine import Engine
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        eng = Engine(rank)
+        eng.set_weights(orc.load_state_npz(os.path.join(root, "tests", "golden", "model_kitti.npz")))
+        graphs = synth.make_graphs(m, 64, 20, seed=13).cuda()
+        full, (lo, hi) = scan.SequenceScanner(eng, rank, world).scan(graphs, 20)
+        torch.cuda.synchronize()
+        torch.save({"full": full.cpu(), "lo": lo, "hi": hi}, os.path.join(out_dir, f"r{rank}.pt"))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m", [256, 301])      # equal row blocks (one in-place all-gather) and unequal ones (pad path)
+def test_two_rank_nccl_scan_is_bit_equal_to_single_gpu(kitti_state, tmp_path, m):
+    """Config 4 on real ranks: two processes, one GPU each, NCCL — the sharded [M, M] matrix every rank ends up with is
+    bit-equal to the single-GPU scan (the row block a rank computes does not depend on how many ranks there are)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    from sg_pr_b200.engine import Engine
+    eng = Engine(0)
+    eng.set_weights(kitti_state)
+    single, _ = scan.SequenceScanner(eng).scan(synth.make_graphs(m, 64, 20, seed=13).cuda(), 20)
+    single = single.cpu()
+    eng.close()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(2, port, m, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        o = torch.load(tmp_path / f"r{r}.pt")
+        assert o["full"].shape == (m, m)
+        assert torch.equal(o["full"], single), f"rank {r}: sharded scan differs from the single-GPU scan"

@@ -37,7 +37,7 @@ def _worker(rank, world, port, m, out_dir):
         sd = orc.load_state_npz(os.path.join(root, "tests", "golden", "model_kitti.npz"))
         graphs = synth.make_graphs(m, 32, 10, seed=3)
         embed = lambda g, k: orc.embed_graphs(g, k, sd)["pooled"].squeeze(-1) if g.shape[0] else torch.empty(0, 32)
-        score = lambda rows, cols: orc.score_matrix(rows, cols, sd) if rows.shape[0] else torch.empty(0, cols.shape[0])
+        score = lambda rows, cols, out=None: orc.score_matrix(rows, cols, sd) if rows.shape[0] else torch.empty(0, cols.shape[0])
         full, (lo, hi) = scan.scan_all_pairs(graphs, 10, embed, score, rank, world)
         lo2, hi2 = scan.row_block(m, rank, world)
         local, _ = scan.scan_all_pairs(graphs[lo2:hi2], 10, embed, score, rank, world, gather_scores=False,
@@ -47,7 +47,7 @@ def _worker(rank, world, port, m, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("m", [9, 12])
+@pytest.mark.parametrize("m", [9, 12])      # unequal blocks (pad path) and equal blocks (direct, one collective)
 def test_two_rank_scan_matches_single_rank(tmp_path, m):
     from oracle import sgpr_oracle as orc
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,7 +56,7 @@ def test_two_rank_scan_matches_single_rank(tmp_path, m):
     pooled = orc.embed_graphs(graphs, 10, sd)["pooled"].squeeze(-1)
     want = orc.score_matrix(pooled, pooled, sd)
     single, _ = scan.scan_all_pairs(graphs, 10, lambda g, k: orc.embed_graphs(g, k, sd)["pooled"].squeeze(-1),
-                                    lambda r, c: orc.score_matrix(r, c, sd))
+                                    lambda r, c, out=None: orc.score_matrix(r, c, sd))
     assert torch.equal(single, want)
     mp.spawn(_worker, args=(2, _free_port(), m, str(tmp_path)), nprocs=2, join=True)
     outs = [torch.load(tmp_path / f"r{r}.pt") for r in range(2)]
