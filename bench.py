@@ -157,6 +157,7 @@ def measure_scan(eng, dev, rank, world, dist, graphs_m=4000, steps=5, warmup=2):
     graphs = synth.make_graphs(graphs_m, NODES, K_NN, seed=42).to(dev)
     sc = scan.SequenceScanner(eng, rank, world)
     names = ("embed", "gather_pooled", "score", "gather_scores")
+    result = torch.empty(graphs_m, graphs_m, dtype=torch.float32, device=dev)     # reused by every scan
 
     def one():
         ev = {"start": torch.cuda.Event(enable_timing=True)}
@@ -165,7 +166,7 @@ def measure_scan(eng, dev, rank, world, dist, graphs_m=4000, steps=5, warmup=2):
         def mark(name):
             ev[name] = torch.cuda.Event(enable_timing=True)
             ev[name].record()
-        mat, _ = sc.scan(graphs, K_NN, marks=mark)
+        mat, _ = sc.scan(graphs, K_NN, marks=mark, out=result)
         return mat, ev
     for _ in range(warmup):
         one()
@@ -183,6 +184,8 @@ def measure_scan(eng, dev, rank, world, dist, graphs_m=4000, steps=5, warmup=2):
             acc[i] += ev[prev].elapsed_time(ev[name])
             prev = name
         acc[4] += ev["start"].elapsed_time(ev[names[-1]])
+    if os.environ.get("SGPR_BENCH_DEBUG"):
+        print(f"[scan rank {rank}] per-phase ms {(acc / steps).tolist()}", file=sys.stderr, flush=True)
     t = (acc / steps).to(dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -24,6 +24,7 @@ class GraphStore:
         self.labels = int(number_of_labels)
         self._raw: Dict[str, tuple] = {}            # path -> (nodes int64[n], centers float64[n,3], (x, z))
         self._blocks: Dict[str, torch.Tensor] = {}  # path -> [15, node_num] float32 (only graphs with n <= node_num)
+        self._compact: Dict[str, torch.Tensor] = {}  # path -> uint8 [ceil16(13 node_num)] compact record (same graphs)
 
     def __len__(self):
         return len(self._raw)
@@ -60,6 +61,22 @@ class GraphStore:
         if len(nodes) <= self.node_num:
             self._blocks[path] = blk
         return blk
+
+    def compact_record(self, path: str) -> torch.Tensor:
+        """The graph as a compact record (include/sgpr_b200.h: xyz [3][node_num] fp32, then one label byte per node, 255 for
+        pads, padded to 16 bytes) — the 13-byte-per-node form of `block(path)`; the kernels expand it to the same bits."""
+        hit = self._compact.get(path)
+        if hit is not None:
+            return hit
+        blk = self.block(path)
+        n = self.node_num
+        rec = torch.zeros(((13 * n + 15) // 16) * 16, dtype=torch.uint8)
+        rec[:12 * n] = blk[:3].contiguous().view(-1).view(torch.uint8)
+        sem = blk[3:]
+        rec[12 * n:13 * n] = torch.where(sem.sum(dim=0) > 0, sem.argmax(dim=0), torch.full((n,), 255)).to(torch.uint8)
+        if len(self._load(path)[0]) <= self.node_num:
+            self._compact[path] = rec
+        return rec
 
     def is_static(self, path: str) -> bool:
         """True when the graph's block never changes between calls (no random subsampling)."""

@@ -33,6 +33,30 @@ def pr_curve(labels: torch.Tensor, scores: torch.Tensor) -> Tuple[torch.Tensor, 
     return torch.cat([precision[rev], one]), torch.cat([recall[rev], 0 * one]), thr[rev]
 
 
+def roc_curve(labels: torch.Tensor, scores: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(fpr, tpr, thresholds) as sklearn.metrics.roc_curve(labels, scores, drop_intermediate=False) returns them: one point
+    per distinct score in decreasing order, preceded by the (0, 0) point with threshold +inf."""
+    scores = scores.reshape(-1).to(torch.float64)
+    labels = labels.reshape(-1).to(torch.float64)
+    order = torch.argsort(scores, descending=True, stable=True)
+    s, y = scores[order], labels[order]
+    distinct = torch.nonzero(s[1:] != s[:-1]).reshape(-1)
+    idx = torch.cat([distinct, torch.tensor([s.numel() - 1], device=s.device)])
+    tps = torch.cumsum(y, 0)[idx]
+    fps = 1 + idx.to(torch.float64) - tps
+    zero = torch.zeros(1, dtype=torch.float64, device=s.device)
+    tps, fps = torch.cat([zero, tps]), torch.cat([zero, fps])
+    thr = torch.cat([torch.full((1,), float("inf"), dtype=torch.float64, device=s.device), s[idx]])
+    fpr = fps / fps[-1] if fps[-1] > 0 else torch.full_like(fps, float("nan"))
+    tpr = tps / tps[-1] if tps[-1] > 0 else torch.full_like(tps, float("nan"))
+    return fpr, tpr, thr
+
+
+def auc(x: torch.Tensor, y: torch.Tensor) -> float:
+    """Trapezoidal area under a curve given by increasing x (sklearn.metrics.auc)."""
+    return float(torch.trapezoid(y.to(torch.float64), x.to(torch.float64)))
+
+
 def f1_max(labels: torch.Tensor, scores: torch.Tensor) -> float:
     """max over the PR curve of 2PR/(P+R), NaN -> 0 — the number eval_batch.py writes to <seq>_DL_F1_max.txt."""
     p, r, _ = pr_curve(labels, scores)

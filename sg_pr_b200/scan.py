@@ -72,7 +72,8 @@ def scan_all_pairs(graphs: torch.Tensor, k: int,
                    embed_fn: Callable[[torch.Tensor, int], torch.Tensor],
                    score_fn: Callable[..., torch.Tensor],
                    rank: int = 0, world: int = 1, group=None, gather_scores: bool = True,
-                   graphs_are_local: bool = False, marks: Optional[Callable[[str], None]] = None):
+                   graphs_are_local: bool = False, marks: Optional[Callable[[str], None]] = None,
+                   out: Optional[torch.Tensor] = None):
     """Score matrix S[i, j] = score(graph i as side 1, graph j as side 2) for a sequence of M graphs.
 
     graphs : [M, 15, N] (every rank holds the sequence) or, with graphs_are_local, this rank's row block only.
@@ -80,6 +81,8 @@ def scan_all_pairs(graphs: torch.Tensor, k: int,
     view `out` of the final matrix (out may be None: allocate).
     `marks(name)`: optional callback at the phase boundaries ("embed", "gather_pooled", "score", "gather_scores") —
     bench.py records CUDA events there.
+    `out`: optional [M, M] result buffer to reuse across scans (a fresh 64 MB allocation per scan makes the caching
+    allocator wait on the NCCL stream's use of the previous one).
     Returns (scores, (lo, hi)): the full [M, M] matrix on every rank when gather_scores, else this rank's rows.
 
     Collectives: the pooled vectors (M x 32 fp32, 512 KB at M = 4000) and — the one exchange of real size — the score
@@ -107,7 +110,10 @@ def scan_all_pairs(graphs: torch.Tensor, k: int,
         block = score_fn(pooled_rows, pooled_all, None)
         mark("score")
         return block, (lo, hi)
-    full = torch.empty((m, m), dtype=pooled_all.dtype, device=pooled_all.device)
+    if out is not None and (tuple(out.shape) != (m, m) or out.dtype != pooled_all.dtype or out.device != pooled_all.device
+                            or not out.is_contiguous()):
+        raise ValueError(f"`out` must be a contiguous [{m}, {m}] {pooled_all.dtype} tensor on {pooled_all.device}")
+    full = out if out is not None else torch.empty((m, m), dtype=pooled_all.dtype, device=pooled_all.device)
     block = score_fn(pooled_rows, pooled_all, full[lo:hi])
     if block.data_ptr() != full[lo:hi].data_ptr():      # a score_fn that ignores `out`
         full[lo:hi] = block
@@ -133,9 +139,10 @@ class SequenceScanner:
             return out if out is not None else torch.empty(0, cols.shape[0], dtype=torch.float32, device=self.engine.device)
         return self.engine.score_matrix(rows, cols, out=out)
 
-    def scan(self, graphs: torch.Tensor, k: int, gather_scores: bool = True, graphs_are_local: bool = False, marks=None):
+    def scan(self, graphs: torch.Tensor, k: int, gather_scores: bool = True, graphs_are_local: bool = False, marks=None,
+             out: Optional[torch.Tensor] = None):
         return scan_all_pairs(graphs, k, self._embed, self._score, self.rank, self.world, self.group,
-                              gather_scores, graphs_are_local, marks)
+                              gather_scores, graphs_are_local, marks, out)
 
     def top_matches(self, graphs: torch.Tensor, k: int, per_row: int = 5, exclude_window: int = 50):
         """Loop-closure style query: for each row graph of this rank, the best-scoring earlier frames outside a

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import metrics as _metrics
 from . import utils as _utils
 from .graph_store import GraphStore
 from .layers_batch import AttentionModule, TenorNetworkModule
@@ -601,7 +602,6 @@ class SGTrainer(object):
 
     def score(self, split="test"):
         """sg_net.py:386-422: eval-mode pass over the split, F1max from the precision-recall curve."""
-        from sklearn import metrics
         print("\n\nModel evaluation.\n")
         self.model.eval()
         self.scores, self.ground_truth = [], []
@@ -618,10 +618,11 @@ class SGTrainer(object):
             losses += loss_score
             pred_db.extend(pred_b)
             gt_db.extend(gt_b)
-        precision, recall, _ = metrics.precision_recall_curve(gt_db, pred_db)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            f1 = np.nan_to_num(2 * precision * recall / (precision + recall))
-        f1_max = np.max(f1)
+        # precision-recall curve -> F1max (sg_net.py:414-418), as one sort + cumsum on the device (sg_pr_b200/metrics.py;
+        # same definition and float64 arithmetic as sklearn.metrics.precision_recall_curve, tests/test_metrics.py)
+        dev = torch.device("cuda", int(self.args.gpu)) if torch.cuda.is_available() else torch.device("cpu")
+        f1_max = _metrics.f1_max(torch.as_tensor(np.asarray(gt_db, dtype=np.float64), device=dev),
+                                 torch.as_tensor(np.asarray(pred_db, dtype=np.float64), device=dev))
         print("\nModel " + split + " F1_max_score: " + str(f1_max) + ".")
         model_loss = losses / len(batches)
         print("\nModel " + split + " loss: " + str(model_loss) + ".")
@@ -676,8 +677,9 @@ class SGTrainer(object):
         emb, store = self._emb, self._store()
         fresh = [p for p in dict.fromkeys(paths) if p not in emb["index"]]
         if fresh:
-            blocks = torch.stack([store.block(p) for p in fresh]).pin_memory()
-            pooled = eng.embed(blocks, int(self.args.K))["pooled"]
+            # compact records (13 bytes per node instead of 60) cross PCIe; the kernel expands them in shared memory
+            blocks = torch.stack([store.compact_record(p) for p in fresh]).pin_memory()
+            pooled = eng.embed_compact(blocks, int(self.args.node_num), int(self.args.K))["pooled"]
             # the kernel reads `blocks` in place over PCIe, asynchronously: keep the pinned tensor alive until an event
             # recorded after the launch has completed (torch's pinned-memory cache would otherwise recycle it)
             done = torch.cuda.Event()

@@ -231,6 +231,30 @@ def test_score_matrix_vs_oracle(eng, kitti_state):
     assert torch.equal(big[:, 10:80].cpu(), mat) and float(big[:, :10].abs().max()) == 0.0
 
 
+def test_compact_input_is_bit_identical(eng):
+    """13-byte-per-node records (xyz + uint8 label) expanded in shared memory give the SAME bits as the
+    one-hot [15, N] blocks — device-resident, and pinned host records read in place over PCIe."""
+    from sg_pr_b200.engine import compact_graphs
+    for n, k, b in ((64, 20, 300), (100, 10, 40), (16, 10, 33), (128, 20, 20), (30, 7, 9)):
+        f1, f2 = synth.make_pair_batch(b, n, k, seed=40 + n)
+        f2[0].zero_()                                   # an all-pad graph
+        c1, c2 = compact_graphs(f1), compact_graphs(f2)
+        assert c1.shape == (b, eng.compact_stride(n)) and c1.shape[1] * 4 < 15 * n * 4
+        want = eng.forward_pairs(_cuda(f1), _cuda(f2), k)
+        got = eng.forward_pairs_compact(_cuda(c1), _cuda(c2), n, k)
+        pinned = eng.forward_pairs_compact(c1.pin_memory(), c2.pin_memory(), n, k)
+        for w, g, p in zip(want, got, pinned):
+            assert torch.equal(w, g) and torch.equal(w, p), (n, k)
+        e0 = eng.embed(_cuda(f1), k, want_att=True)
+        e1 = eng.embed_compact(_cuda(c1), n, k, want_att=True)
+        assert torch.equal(e0["pooled"], e1["pooled"]) and torch.equal(e0["att"], e1["att"])
+    with pytest.raises(ValueError):
+        compact_graphs(torch.rand(2, 15, 64))           # label rows that are not one-hot have no compact form
+    with pytest.raises(ValueError):
+        eng.forward_pairs_compact(torch.zeros(2, 100, dtype=torch.uint8, device="cuda"),
+                                  torch.zeros(2, 100, dtype=torch.uint8, device="cuda"), 64, 20)
+
+
 def test_host_entry_point_matches_device(eng):
     f1, f2 = synth.make_pair_batch(64, 64, 20, seed=21)
     d_score, d_a1, d_a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)

@@ -99,6 +99,9 @@ def test_graph_store_matches_reference_host_prep(tree, golden_dir):
             np.testing.assert_array_equal(f1.numpy(), z[p + "features_1"])
             np.testing.assert_array_equal(f2.numpy(), z[p + "features_2"])
             assert gt[0] == float(z[p + "target"]) and store.is_static(pa)
+            from sg_pr_b200.engine import compact_graphs
+            rec = store.compact_record(pa)              # the 13-byte-per-node record == compact form of the reference's block
+            assert torch.equal(rec, compact_graphs(f1)[0]) and rec.numel() == ((13 * N + 15) // 16) * 16
         assert len(store) == 3                          # three files parsed once each, however many pairs
     small = GraphStore(16, 12)
     np.random.seed(0)
