@@ -95,6 +95,9 @@ struct sgpr_ctx {
     int zerocopy = 1;            // host entry point: read pinned buffers in place; SGPR_NO_ZEROCOPY=1 forces staged copies
     int balance = 1;             // order graphs by active rows before the fused kernel; SGPR_NO_BALANCE=1 disables it
     int dedup = 1;               // collapse trailing all-zero nodes (exact); SGPR_NO_DEDUP=1 disables it for experiments
+    float* d_fc1_planes = nullptr;   // [2][16][32] FC1 weights as UMMA B operand (tcgen05 score matrix, version 2)
+    int scoremat_version = 1;    // tcgen05 score-matrix kernel: 1 = FFMA2 epilogue (default, faster), 2 = FC1 on the tensor cores
+                                 // too, A operand in TMEM (SGPR_SCOREMAT_V2=1; see scoremat_umma.cuh for the measurements)
     int scoremat_ffma = 0;       // score matrix on fp32 FMA instead of tcgen05 (SGPR_SCOREMAT_FFMA=1; always in tests/emu)
     int knn_ties = SGPR_TIES_CUDA;   // k-NN tie rule (sgpr_set_knn_ties); SGPR_KNN_TIES=cpu|cuda sets the initial value
 };
@@ -129,6 +132,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
     if (const char* nd = getenv("SGPR_NO_DEDUP")) ctx->dedup = (nd[0] == '1') ? 0 : 1;
     if (const char* nz = getenv("SGPR_NO_ZEROCOPY")) ctx->zerocopy = (nz[0] == '1') ? 0 : 1;
     if (const char* nb = getenv("SGPR_NO_BALANCE")) ctx->balance = (nb[0] == '1') ? 0 : 1;
+    if (const char* v2 = getenv("SGPR_SCOREMAT_V2")) ctx->scoremat_version = (v2[0] == '1') ? 2 : 1;
     if (const char* sf = getenv("SGPR_SCOREMAT_FFMA")) ctx->scoremat_ffma = (sf[0] == '1') ? 1 : 0;
     if (const char* kt = getenv("SGPR_KNN_TIES")) ctx->knn_ties = (strcmp(kt, "cpu") == 0) ? SGPR_TIES_CPU : SGPR_TIES_CUDA;
     // opt in to the full shared-memory carve-out (the per-NPL objects subtract each kernel's static __shared__ bytes)
@@ -142,6 +146,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
 #endif
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_blob), ctx->off.total * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_fc1_planes), 1024 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_ctrs), 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_ctrs, 0, 2 * sizeof(int));
     if (e != cudaSuccess) {
@@ -165,6 +170,7 @@ int sgpr_destroy(sgpr_ctx* ctx) {
     cudaFree(ctx->d_blk);
     cudaFree(ctx->d_order);
     cudaFree(ctx->d_ctrs);
+    cudaFree(ctx->d_fc1_planes);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SGPR_OK;
@@ -200,6 +206,13 @@ int sgpr_set_weights(sgpr_ctx* ctx, const sgpr_weights* w) {
     ctx->pw = PackedWeights{b + o.s1,    b + o.w_s2,  b + o.w_s3,  b + o.w_f1,  b + o.w_f2,  b + o.w_f3,
                             b + o.w_end, b + o.ab_s2, b + o.ab_s3, b + o.ab_f1, b + o.ab_f2, b + o.ab_f3,
                             b + o.ab_end, b + o.att_w, b + o.ntn_w, b + o.ntn_v, b + o.ntn_b};
+#ifndef SGPR_EMU
+    {
+        float planes[1024];
+        score_matrix_fc1_planes(w->fc1_w, planes);
+        CUDA_TRY(cudaMemcpy(ctx->d_fc1_planes, planes, sizeof(planes), cudaMemcpyHostToDevice));
+    }
+#endif
     ctx->has_weights = true;
     return SGPR_OK;
 }
@@ -458,10 +471,10 @@ int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const 
         int rc = ensure(ctx->d_proj, ctx->proj_cap, score_matrix_umma_scratch_floats(R, M));
         if (rc) return rc;
         score_matrix_umma_launch(ctx->sm_count, st, pooled_rows_dev, pooled_cols_dev, ctx->d_proj, scores_dev,
-                                 static_cast<long long>(ld_scores), R, M, ctx->pw, ctx->hp);
+                                 static_cast<long long>(ld_scores), R, M, ctx->pw, ctx->hp, ctx->d_fc1_planes, ctx->scoremat_version);
     }
 #endif
-    ctx->launches += 3;
+    ctx->launches += ffma ? 3 : 2;
     CUDA_TRY(cudaGetLastError());
     return SGPR_OK;
 }

@@ -255,6 +255,31 @@ def test_compact_input_is_bit_identical(eng):
                                   torch.zeros(2, 100, dtype=torch.uint8, device="cuda"), 64, 20)
 
 
+@pytest.mark.parametrize("env", [{}, {"SGPR_SCOREMAT_V2": "1"}, {"SGPR_SCOREMAT_FFMA": "1"}])
+def test_score_matrix_kernel_variants_agree(kitti_state, monkeypatch, env):
+    """The three score-matrix kernels — tcgen05 3xTF32 bilinear + FFMA2 epilogue (default), the same with FC1 on the tensor
+    cores from a TMEM-resident A operand (SGPR_SCOREMAT_V2), and the fp32-FMA kernel (SGPR_SCOREMAT_FFMA) — against the
+    oracle at ragged shapes, and a 1000 x 1000 block against the fused pair kernel's own head."""
+    from sg_pr_b200.engine import Engine
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    e = Engine(0)
+    for key in env:
+        monkeypatch.delenv(key)
+    e.set_weights(kitti_state)
+    g = synth.make_graphs(1000, 64, 20, seed=19)
+    pooled = e.embed(_cuda(g), 20)["pooled"]
+    for r, m in ((1, 1), (7, 129), (17, 300), (130, 257)):
+        mat = e.score_matrix(pooled[:r].contiguous(), pooled[5:5 + m].contiguous()).cpu()
+        want = orc.score_matrix(pooled[:r].cpu(), pooled[5:5 + m].cpu(), kitti_state)
+        assert float((mat - want).abs().max()) <= SCORE_TOL, (env, r, m)
+    big = e.score_matrix(pooled, pooled)
+    idx = synth.make_sequence_pairs(1000, 4096, seed=2).cuda()
+    pairs = e.score_pairs(pooled, idx)
+    assert float((big[idx[:, 0], idx[:, 1]] - pairs).abs().max()) <= 4e-6, env
+    e.close()
+
+
 def test_host_entry_point_matches_device(eng):
     f1, f2 = synth.make_pair_batch(64, 64, 20, seed=21)
     d_score, d_a1, d_a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)
