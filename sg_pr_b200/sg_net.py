@@ -119,6 +119,7 @@ class SG(torch.nn.Module):
         self._engine = None
         self._packed_version = None
         self._pinned_in_flight = []
+        self._ring_pos = 0
 
     def calculate_bottleneck_features(self):
         self.feature_count = self.args.tensor_neurons
@@ -150,12 +151,19 @@ class SG(torch.nn.Module):
         return out
 
     def _weights_version(self):
-        """Changes whenever a parameter / buffer is modified in place (`_version`) or re-pointed (`p.data = t`,
-        `data_ptr`).  In-place writes THROUGH `.data` (`p.data.mul_()`, `m.weight.data.fill_()`) bump neither: call
-        `invalidate_packed_weights()` after those."""
+        """Changes whenever a parameter / buffer is modified in place (`_version`, checked on EVERY forward) or re-pointed
+        (`p.data = t` changes `data_ptr`; checked on every 32nd forward and whenever the cheap check fires — it costs as much
+        as the version walk).  In-place writes THROUGH `.data` (`p.data.mul_()`, `m.weight.data.fill_()`) bump neither:
+        call `invalidate_packed_weights()` after those."""
         if getattr(self, "_tensors", None) is None:
             self._tensors = list(self.parameters()) + list(self.buffers())
-        return [t._version for t in self._tensors] + [t.data_ptr() for t in self._tensors]
+            self._ptr_key, self._ptr_age = None, 0
+        versions = [t._version for t in self._tensors]
+        self._ptr_age -= 1
+        if self._ptr_age < 0 or self._packed_version is None or versions != self._packed_version[0]:
+            self._ptr_key = [t.data_ptr() for t in self._tensors]
+            self._ptr_age = 32
+        return (versions, self._ptr_key)
 
     def invalidate_packed_weights(self):
         """Force the next eval-mode forward to re-pack the weights (and SGTrainer to drop cached embeddings)."""
@@ -206,13 +214,16 @@ class SG(torch.nn.Module):
                 and f2.is_contiguous() and f1.is_pinned() and f2.is_pinned()):
             out = eng.forward_pairs(f1, f2, int(self.args.K), True, True)
             # the launch is asynchronous and torch's pinned-memory cache knows nothing about it: keep the two host tensors
-            # referenced until an event recorded behind the launch has completed
-            done = torch.cuda.Event()
-            done.record()
-            hold = self._pinned_in_flight
-            if len(hold) >= 8:
-                hold[:] = [h for h in hold if not h[2].query()]
-            hold.append((f1, f2, done))
+            # referenced until an event recorded behind the launch has completed (a ring of 8 reusable events)
+            ring = self._pinned_in_flight
+            if len(ring) < 8:
+                ring.append([None, None, torch.cuda.Event()])
+            slot = ring[self._ring_pos % len(ring)] if len(ring) == 8 else ring[-1]
+            if slot[0] is not None and not slot[2].query():
+                slot[2].synchronize()                 # 8 forwards in flight with live host inputs: wait for the oldest
+            slot[0], slot[1] = f1, f2
+            slot[2].record()
+            self._ring_pos += 1
             return out
         f1 = f1.to(dev, dtype=torch.float32, non_blocking=True)
         f2 = f2.to(dev, dtype=torch.float32, non_blocking=True)

@@ -149,3 +149,52 @@ def test_emulated_process_batch_glue(emu_lib, golden_dir, tmp_path):
         assert float((synced[name] - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), name
     assert not torch.equal(synced["attention.weight_matrix"], state0["attention.weight_matrix"])
     eng.close()
+
+
+def test_emulated_train_forward_in_cpu_tie_mode_matches_oracle_on_dense_graphs(emu_lib, kitti_state):
+    """Graphs without zero pads (the k-NN tie-rule regime, see tests/test_tie_rule.py): the train-mode forward with
+    knn_ties="cpu" reproduces the reference's CPU predictions; the default rule does not (it is the CUDA reference)."""
+    import torch
+    from oracle import sgpr_oracle_train as ort
+    from sg_pr_b200 import synth
+    a, b = synth.make_pair_batch(3, 32, 10, seed=8, dense=True)
+    f1 = torch.stack([a, b], dim=1).reshape(6, 15, 32).contiguous()
+    f2 = torch.stack([b, a], dim=1).reshape(6, 15, 32).contiguous()
+    want = ort.forward_train(kitti_state, f1, f2, 10)[0].detach()
+    eng = TrainEngine(lib=emu_lib)
+    eng.set_state(kitti_state)
+    eng.set_knn_ties("cpu")
+    pred, _, _ = eng.forward(f1, f2, 10, update_running=False)
+    assert float((pred - want).abs().max()) <= 2e-5
+    eng.set_knn_ties("cuda")
+    plain, _, _ = eng.forward(f1, f2, 10, update_running=False)
+    assert float((plain - want).abs().max()) > 1e-4
+    with pytest.raises(ValueError):
+        eng.set_knn_ties("numpy")
+    eng.close()
+
+
+def test_backward_of_a_stale_forward_is_refused(emu_lib, kitti_state):
+    """the engine keeps ONE forward's activations.  A second train-mode forward before backward() must make
+    the first node's backward raise instead of silently differentiating the second forward."""
+    import torch
+    from sg_pr_b200 import synth
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SG
+    args = sgpr_args()
+    args.K, args.node_num = 10, 32
+    model = SG(args, 12)
+    model.load_state_dict(kitti_state)
+    model._device = lambda: torch.device("cpu")
+    model._autograd_engine = TrainEngine(lib=emu_lib)
+    model.train()
+    fa = synth.make_pair_batch(2, 32, 10, seed=1)
+    fb = synth.make_pair_batch(2, 32, 10, seed=2)
+    pa, _, _ = model({"features_1": fa[0], "features_2": fa[1]})
+    pb, _, _ = model({"features_1": fb[0], "features_2": fb[1]})
+    gen = model._autograd_engine.forward_generation()
+    assert gen == 2
+    with pytest.raises(RuntimeError, match="another train-mode forward"):
+        pa.sum().backward()
+    pb.sum().backward()                                  # the latest forward is still differentiable
+    assert model.scoring_layer.weight.grad is not None
