@@ -12,7 +12,8 @@ import yaml
 # section -> attribute names read from it (same grouping as config/config.yml)
 _SECTIONS = {
     "common": ("model", "cuda", "batch_size", "p_thresh", "graph_pairs_dir", "pair_list_dir"),
-    "arch": ("keep_node", "filters_1", "filters_2", "filters_3", "tensor_neurons", "bottle_neck_neurons", "K"),
+    "arch": ("keep_node", "filters_1", "filters_2", "filters_3", "tensor_neurons", "bottle_neck_neurons", "K",
+             "knn_ties"),      # knn_ties: not a reference key — "cuda" (default) / "cpu", see INTEGRATION.md
     "train": ("epochs", "train_sequences", "eval_sequences", "dropout", "learning_rate", "weight_decay", "gpu",
               "logdir", "node_num"),
     "eva_batch": ("sequences", "output_path", "show"),
@@ -24,6 +25,7 @@ _DEFAULTS = dict(
     keep_node=1, filters_1=64, filters_2=64, filters_3=32, tensor_neurons=16, bottle_neck_neurons=16, K=10,
     epochs=500, train_sequences=[], eval_sequences=[], dropout=0, learning_rate=1e-3, weight_decay=5e-4, gpu=0,
     logdir="./logs", node_num=100, sequences=[], output_path="./eva", show=False, pair_file="",
+    knn_ties="cuda",
 )
 
 
