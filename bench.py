@@ -150,7 +150,7 @@ def run_reference_arm(args, rank: int):
 # ------------------------------------------------------------------------------------------------------------------------
 # extra keys of the JSON line (VERDICT r01 task 2): the other BASELINE configs on the driver's clock
 # ------------------------------------------------------------------------------------------------------------------------
-def measure_scan(eng, dev, rank, world, dist, graphs_m=4000, steps=5, warmup=2):
+def measure_scan(eng, dev, rank, world, dist, graphs_m=4000, steps=5, warmup=2, exchange="nccl"):
     """BASELINE configs[3]: all ordered pairs of a 4000-graph sequence, row blocks sharded over the ranks (sg_pr_b200/scan.py),
     phases timed with CUDA events on every rank, max over ranks."""
     from sg_pr_b200 import scan
@@ -166,7 +166,7 @@ def measure_scan(eng, dev, rank, world, dist, graphs_m=4000, steps=5, warmup=2):
         def mark(name):
             ev[name] = torch.cuda.Event(enable_timing=True)
             ev[name].record()
-        mat, _ = sc.scan(graphs, K_NN, marks=mark, out=result)
+        mat, _ = sc.scan(graphs, K_NN, marks=mark, out=result, exchange=exchange)
         return mat, ev
     for _ in range(warmup):
         one()
@@ -193,13 +193,15 @@ def measure_scan(eng, dev, rank, world, dist, graphs_m=4000, steps=5, warmup=2):
     idx = synth.make_sequence_pairs(graphs_m, 512, seed=9).to(dev)
     fused, _, _ = eng.forward_pairs(graphs[idx[:, 0]], graphs[idx[:, 1]], K_NN)
     err = float((mat[idx[:, 0], idx[:, 1]] - fused).abs().max())
+    how = ("one in-place NCCL all-gather of the score rows" if exchange == "nccl" or world == 1 else
+           "exchange fused into the score kernel: every score stored into all ranks' matrices over NVLink peer memory")
     return {"workload": f"all ordered pairs of a {graphs_m}-graph synthetic sequence (BASELINE configs[3]), row blocks over "
-                        f"{world} GPU(s), one in-place NCCL all-gather of the score rows",
+                        f"{world} GPU(s), {how}", "exchange": exchange if world > 1 else "none",
             "value": graphs_m * graphs_m / (total_ms * 1e-3), "unit": "ordered graph-pairs/s", "graphs": graphs_m,
             "ms_per_scan": total_ms,
             "phases_ms": {"embed_row_block": embed_ms, "allgather_pooled": gp_ms, "score_row_block_tcgen05": score_ms,
-                          "allgather_scores": gs_ms},
-            "allgather_share": (gp_ms + gs_ms) / total_ms if total_ms > 0 else None,
+                          ("allgather_scores" if exchange == "nccl" or world == 1 else "completion_allreduce"): gs_ms},
+            "exchange_share": (gp_ms + gs_ms) / total_ms if total_ms > 0 else None,
             "score_matrix_bytes": graphs_m * graphs_m * 4, "max_abs_diff_vs_fused_pair_kernel": err,
             "timing": "CUDA events per phase, mean of %d scans after %d warm-ups, max over ranks" % (steps, warmup)}
 
@@ -397,7 +399,18 @@ def main():
 
     extras = {}
     if not args.no_extras:
-        extras["scan"] = measure_scan(eng, dev, rank, world, dist)
+        if world > 1:
+            # product path: the exchange fused into the score kernel's stores over NVLink peer memory; the plain
+            # "kernel, then NCCL all-gather" variant is measured beside it as the baseline
+            try:
+                extras["scan"] = measure_scan(eng, dev, rank, world, dist, exchange="peer")
+            except Exception as ex:          # peer mapping unavailable on this box
+                extras["scan"] = {"unavailable": repr(ex)[:300]}
+            extras["scan_nccl_allgather"] = measure_scan(eng, dev, rank, world, dist, exchange="nccl")
+            if "value" not in extras["scan"]:
+                extras["scan"] = extras["scan_nccl_allgather"]
+        else:
+            extras["scan"] = measure_scan(eng, dev, rank, world, dist)
         if rank == 0:
             extras["train"] = measure_train(state, dev)
             extras["sweep"] = measure_sweep(eng, dev)

@@ -159,6 +159,28 @@ int sgpr_score_pairs(sgpr_ctx* ctx, const float* pooled_dev, const int32_t* pair
 int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const float* pooled_cols_dev, int M,
                       float* scores_dev, int64_t ld_scores, void* stream);
 
+/*
+ * The same with the exchange step of the multi-GPU scan fused into the kernel: every score is stored into ALL n_out
+ * (1..8) destination matrices — this GPU's result and its peers' results mapped into this process (CUDA IPC) and
+ * reachable over NVLink after sgpr_enable_peer_access — instead of one local store followed by an all-gather.
+ * scores_dev_list[p] points at row 0 OF THIS ROW BLOCK inside destination p; same ld for all.  The stores are posted
+ * writes that overlap the tensor-core tiles; the caller orders them against the peers' reads with a stream-ordered
+ * collective afterwards (sg_pr_b200/scan.py uses a 1-element all-reduce).  tcgen05 kernel only.
+ */
+int sgpr_score_matrix_multi(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const float* pooled_cols_dev, int M,
+                            float* const* scores_dev_list, int n_out, int64_t ld_scores, void* stream);
+int sgpr_enable_peer_access(sgpr_ctx* ctx, int peer_device);
+/*
+ * Peer-visible buffers for it, one process per GPU: sgpr_peer_alloc = cudaMalloc on the context's device + a 64-byte
+ * CUDA IPC handle to hand to the other processes; sgpr_peer_open maps a peer's handle into this process WITH THIS
+ * CONTEXT'S DEVICE CURRENT (cudaIpcMemLazyEnablePeerAccess), which is what makes the returned pointer usable by this
+ * GPU's kernels over NVLink.  sgpr_peer_close / sgpr_peer_free undo them.
+ */
+int sgpr_peer_alloc(sgpr_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char* handle64);
+int sgpr_peer_open(sgpr_ctx* ctx, const unsigned char* handle64, void** dev_ptr);
+int sgpr_peer_close(sgpr_ctx* ctx, void* dev_ptr);
+int sgpr_peer_free(sgpr_ctx* ctx, void* dev_ptr);
+
 /* Debug/parity taps: k-NN index lists and per-layer EdgeConv outputs of sgpr_embed for the parity tests.
  *   knn_dev       : [M][6][N][k] uint8 | NULL   (layer order: xyz 1-3, sem 1-3 — sg_net.py:84-102)
  *   layer_out_dev : [M][6][N][64] float | NULL  (32-channel layers use the first 32 columns)            */

@@ -44,6 +44,13 @@ SYMBOLS = {
     "sgpr_score_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sgpr_score_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                     C.c_void_p]),
+    "sgpr_score_matrix_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                          C.c_int64, C.c_void_p]),
+    "sgpr_enable_peer_access": (C.c_int, [C.c_void_p, C.c_int]),
+    "sgpr_peer_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "sgpr_peer_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "sgpr_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgpr_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgpr_packed_size": (C.c_size_t, []),
     "sgpr_pack_weights_host": (C.c_int, [C.POINTER(SgprWeights), c_float_p, c_float_p, C.POINTER(C.c_size_t)]),
     "sgpr_launch_count": (C.c_int64, [C.c_void_p]),

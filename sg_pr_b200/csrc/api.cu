@@ -434,14 +434,14 @@ int sgpr_score_pairs(sgpr_ctx* ctx, const float* pooled_dev, const int32_t* pair
     return SGPR_OK;
 }
 
-int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const float* pooled_cols_dev, int M,
-                      float* scores_dev, int64_t ld_scores, void* stream) {
+static int score_matrix_impl(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const float* pooled_cols_dev, int M,
+                             float* scores_dev, int64_t ld_scores, void* stream, float* const* outs, int n_out) {
     if (!ctx) return fail(SGPR_E_INVALID, "sgpr_score_matrix: ctx is NULL");
     if (!ctx->has_weights) return fail(SGPR_E_NOWEIGHTS, "sgpr_score_matrix: call sgpr_set_weights first");
     if (R < 0 || M < 0) return fail(SGPR_E_INVALID, "sgpr_score_matrix: negative size");
     if (R == 0 || M == 0) return SGPR_OK;
     if (ld_scores < M) return fail(SGPR_E_INVALID, "sgpr_score_matrix: ld_scores %lld < M %d", (long long)ld_scores, M);
-    if (!pooled_rows_dev || !pooled_cols_dev || !scores_dev) return fail(SGPR_E_INVALID, "sgpr_score_matrix: NULL pointer");
+    if (!pooled_rows_dev || !pooled_cols_dev || (!scores_dev && n_out == 0)) return fail(SGPR_E_INVALID, "sgpr_score_matrix: NULL pointer");
     DeviceGuard guard(ctx->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #ifdef SGPR_EMU
@@ -449,6 +449,8 @@ int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const 
 #else
     const bool ffma = ctx->scoremat_ffma != 0;
 #endif
+    if (ffma && n_out > 0)
+        return fail(SGPR_E_INVALID, "sgpr_score_matrix_multi: the fused peer store exists in the tcgen05 kernel only (unset SGPR_SCOREMAT_FFMA)");
     if (ffma) {
         int rc = ensure(ctx->d_proj, ctx->proj_cap, static_cast<size_t>(R) * 512);
         if (rc) return rc;
@@ -471,12 +473,92 @@ int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const 
         int rc = ensure(ctx->d_proj, ctx->proj_cap, score_matrix_umma_scratch_floats(R, M));
         if (rc) return rc;
         score_matrix_umma_launch(ctx->sm_count, st, pooled_rows_dev, pooled_cols_dev, ctx->d_proj, scores_dev,
-                                 static_cast<long long>(ld_scores), R, M, ctx->pw, ctx->hp, ctx->d_fc1_planes, ctx->scoremat_version);
+                                 static_cast<long long>(ld_scores), R, M, ctx->pw, ctx->hp, ctx->d_fc1_planes, n_out > 0 ? 1 : ctx->scoremat_version, outs, n_out);
     }
 #endif
     ctx->launches += ffma ? 3 : 2;
     CUDA_TRY(cudaGetLastError());
     return SGPR_OK;
+}
+
+int sgpr_score_matrix(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const float* pooled_cols_dev, int M,
+                      float* scores_dev, int64_t ld_scores, void* stream) {
+    return score_matrix_impl(ctx, pooled_rows_dev, R, pooled_cols_dev, M, scores_dev, ld_scores, stream, nullptr, 0);
+}
+
+int sgpr_score_matrix_multi(sgpr_ctx* ctx, const float* pooled_rows_dev, int R, const float* pooled_cols_dev, int M,
+                            float* const* scores_dev_list, int n_out, int64_t ld_scores, void* stream) {
+    if (n_out < 1 || n_out > 8 || !scores_dev_list) return fail(SGPR_E_INVALID, "sgpr_score_matrix_multi: need 1..8 destination matrices");
+    for (int p = 0; p < n_out; ++p)
+        if (!scores_dev_list[p]) return fail(SGPR_E_INVALID, "sgpr_score_matrix_multi: destination %d is NULL", p);
+    return score_matrix_impl(ctx, pooled_rows_dev, R, pooled_cols_dev, M, scores_dev_list[0], ld_scores, stream, scores_dev_list, n_out);
+}
+
+// ---- peer-visible result buffers (CUDA IPC): cudaMalloc'ed here so that the handle names a whole allocation ----------
+int sgpr_peer_alloc(sgpr_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char* handle64) {
+    if (!ctx || !dev_ptr || !handle64 || bytes == 0) return fail(SGPR_E_INVALID, "sgpr_peer_alloc: bad argument");
+#ifdef SGPR_EMU
+    return fail(SGPR_E_INVALID, "sgpr_peer_alloc: no peers in the emulator build");
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    DeviceGuard guard(ctx->device);
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(SGPR_E_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+    std::memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return SGPR_OK;
+#endif
+}
+
+int sgpr_peer_open(sgpr_ctx* ctx, const unsigned char* handle64, void** dev_ptr) {
+    if (!ctx || !dev_ptr || !handle64) return fail(SGPR_E_INVALID, "sgpr_peer_open: bad argument");
+#ifdef SGPR_EMU
+    return fail(SGPR_E_INVALID, "sgpr_peer_open: no peers in the emulator build");
+#else
+    DeviceGuard guard(ctx->device);        // opened with THIS context's device current: the mapping is for its kernels
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SGPR_OK;
+#endif
+}
+
+int sgpr_peer_close(sgpr_ctx* ctx, void* dev_ptr) {
+    if (!ctx || !dev_ptr) return SGPR_OK;
+#ifndef SGPR_EMU
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+#endif
+    return SGPR_OK;
+}
+
+int sgpr_peer_free(sgpr_ctx* ctx, void* dev_ptr) {
+    if (!ctx || !dev_ptr) return SGPR_OK;
+#ifndef SGPR_EMU
+    DeviceGuard guard(ctx->device);
+    CUDA_TRY(cudaFree(dev_ptr));
+#endif
+    return SGPR_OK;
+}
+
+int sgpr_enable_peer_access(sgpr_ctx* ctx, int peer_device) {
+    if (!ctx) return fail(SGPR_E_INVALID, "sgpr_enable_peer_access: ctx is NULL");
+    if (peer_device == ctx->device) return SGPR_OK;
+#ifdef SGPR_EMU
+    return fail(SGPR_E_INVALID, "sgpr_enable_peer_access: no peers in the emulator build");
+#else
+    DeviceGuard guard(ctx->device);
+    int can = 0;
+    CUDA_TRY(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return fail(SGPR_E_CUDA, "sgpr_enable_peer_access: device %d cannot access device %d", ctx->device, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    if (e != cudaSuccess) return fail(SGPR_E_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", peer_device, cudaGetErrorString(e));
+    return SGPR_OK;
+#endif
 }
 
 int64_t sgpr_launch_count(const sgpr_ctx* ctx) { return ctx ? ctx->launches : 0; }

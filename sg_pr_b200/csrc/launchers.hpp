@@ -29,7 +29,7 @@ size_t score_matrix_umma_scratch_floats(int R, int M);     // operand planes + V
 void score_matrix_fc1_planes(const float* fc1_w, float* planes_1024);      // host: B operand of the FC1 UMMA
 void score_matrix_umma_launch(int sm_count, cudaStream_t st, const float* pooled_rows, const float* pooled_cols, float* scratch,
                               float* scores, long long ld, int R, int M, const PackedWeights& pw, const HeadParams& hp,
-                              const float* fc1_planes_dev, int version);
+                              const float* fc1_planes_dev, int version, float* const* outs, int n_out);
 
 namespace train {
 

@@ -46,7 +46,7 @@ size_t score_matrix_umma_scratch_floats(int R, int M) {
 
 void score_matrix_umma_launch(int sm_count, cudaStream_t st, const float* pooled_rows, const float* pooled_cols, float* scratch,
                               float* scores, long long ld, int R, int M, const PackedWeights& pw, const HeadParams& hp,
-                              const float* fc1_planes_dev, int version) {
+                              const float* fc1_planes_dev, int version, float* const* outs, int n_out) {
     const int r16 = (R + umma::kTileI - 1) / umma::kTileI * umma::kTileI;
     const int m128 = (M + umma::kTileJ - 1) / umma::kTileJ * umma::kTileJ;
     float* proj_big = scratch;
@@ -74,6 +74,8 @@ void score_matrix_umma_launch(int sm_count, cudaStream_t st, const float* pooled
     a.cols_big = cols_big; a.cols_small = cols_small; a.proj_big = proj_big; a.proj_small = proj_small;
     a.rowblk = rowblk;
     a.scores = scores; a.ld = ld; a.R = R; a.M = M;
+    a.n_out = n_out;
+    for (int p = 0; p < n_out && p < 8; ++p) a.outs[p] = outs[p];
     a.n_ib = r16 / umma::kTileI;
     a.n_tiles = (m128 / umma::kTileJ) * a.n_ib;
     const int grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;      // persistent: one CTA per SM, contiguous tile ranges

@@ -54,6 +54,11 @@ struct ScoreMatArgs {
     int R, M;
     int n_ib;               // row groups = ceil(R / 16)
     int n_tiles;            // column blocks * row groups
+    // Fused exchange (multi-GPU scan): every score is stored into n_out destination matrices — this GPU's and its peers'
+    // [M][M] results, mapped over NVLink (CUDA IPC + peer access) — instead of one local store followed by an all-gather.
+    // n_out == 0: store to `scores` only.
+    int n_out;
+    float* outs[8];
 };
 
 #ifndef SGPR_EMU
@@ -284,8 +289,18 @@ sgpr_score_matrix_umma_kernel(const ScoreMatArgs A, const HeadParams H) {
                         y = __ffma2_rn(h, make_float2(H.fc2_w[u], H.fc2_w[u]), y);
                     }
                     if (j < A.M) {
-                        A.scores[static_cast<size_t>(i) * A.ld + j] = 1.0f / (1.0f + expf(-__fadd_rn(y.x, H.fc2_b)));
-                        if (i + 1 < A.R) A.scores[static_cast<size_t>(i + 1) * A.ld + j] = 1.0f / (1.0f + expf(-__fadd_rn(y.y, H.fc2_b)));
+                        const float s0 = 1.0f / (1.0f + expf(-__fadd_rn(y.x, H.fc2_b)));
+                        const float s1 = 1.0f / (1.0f + expf(-__fadd_rn(y.y, H.fc2_b)));
+                        const size_t o = static_cast<size_t>(i) * A.ld + j;
+                        if (A.n_out == 0) {
+                            A.scores[o] = s0;
+                            if (i + 1 < A.R) A.scores[o + A.ld] = s1;
+                        } else {
+                            for (int p = 0; p < A.n_out; ++p) {        // posted stores: local HBM and NVLink peers alike
+                                A.outs[p][o] = s0;
+                                if (i + 1 < A.R) A.outs[p][o + A.ld] = s1;
+                            }
+                        }
                     }
                 }
             }

@@ -305,3 +305,31 @@ class Engine:
         check(self._lib.sgpr_score_matrix(self._ctx, rows.data_ptr(), r, cols.data_ptr(), m, out.data_ptr(),
                                           int(out.stride(0)) if r > 0 else m, self._stream()), "sgpr_score_matrix", self._lib)
         return out
+
+    def score_matrix_multi(self, pooled_rows: torch.Tensor, pooled_cols: torch.Tensor, out_ptrs, ld: int):
+        """score_matrix with every score stored at the same offsets behind EACH device address of `out_ptrs` (row 0 of this
+        row block inside this GPU's result and inside the peers' results mapped by peer_open — see scan.PeerResult): the
+        multi-GPU scan's exchange fused into the kernel's stores."""
+        rows, cols = self._dev(pooled_rows, "pooled_rows"), self._dev(pooled_cols, "pooled_cols")
+        r, m = int(rows.shape[0]), int(cols.shape[0])
+        ptrs = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+        check(self._lib.sgpr_score_matrix_multi(self._ctx, rows.data_ptr(), r, cols.data_ptr(), m, ptrs, len(out_ptrs), int(ld),
+                                                self._stream()), "sgpr_score_matrix_multi", self._lib)
+
+    # ---- peer-visible buffers (CUDA IPC) ---------------------------------------------------------------------------------
+    def peer_alloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of a fresh allocation on this engine's GPU."""
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        check(self._lib.sgpr_peer_alloc(self._ctx, int(nbytes), C.byref(ptr), handle), "sgpr_peer_alloc", self._lib)
+        return int(ptr.value), handle.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        check(self._lib.sgpr_peer_open(self._ctx, C.create_string_buffer(handle, 64), C.byref(ptr)), "sgpr_peer_open", self._lib)
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int):
+        self._lib.sgpr_peer_close(self._ctx, C.c_void_p(ptr))
+
+    def peer_free(self, ptr: int):
+        self._lib.sgpr_peer_free(self._ctx, C.c_void_p(ptr))

@@ -123,11 +123,49 @@ def scan_all_pairs(graphs: torch.Tensor, k: int,
     return full, (lo, hi)
 
 
+class _DevicePointer:
+    """Wraps a raw device allocation for torch.as_tensor (zero-copy, no ownership)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerResult:
+    """The [M, M] score matrix of every rank of one box, each reachable from THIS GPU's kernels: the local one is a
+    cudaMalloc'ed buffer (wrapped as a tensor), the peers' are CUDA-IPC mappings of their buffers opened with this GPU
+    current (handles exchanged once through the process group) — stores to them travel over NVLink / NVSwitch.  With it the
+    scan's exchange step is not a collective: the score kernel stores every value into all `world` matrices
+    (sgpr_score_matrix_multi), the stores overlap the tensor-core tiles, and a 1-element all-reduce afterwards orders
+    them against the readers."""
+
+    def __init__(self, m: int, engine, rank: int, world: int, group=None):
+        self.m, self.rank, self.world, self.engine = m, rank, world, engine
+        self._ptr, handle = engine.peer_alloc(m * m * 4)
+        self.local = torch.as_tensor(_DevicePointer(self._ptr, (m, m)), device=engine.device)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.ptrs = [self._ptr if r == rank else engine.peer_open(handles[r]) for r in range(world)]
+        self.flag = torch.zeros(1, dtype=torch.float32, device=engine.device)
+
+    def close(self):
+        """Unmap the peers' buffers and free the local one — collectively: every rank must have stopped scanning."""
+        if getattr(self, "ptrs", None):
+            for r, p in enumerate(self.ptrs):
+                if r != self.rank:
+                    self.engine.peer_close(p)
+            self.ptrs = None
+            torch.cuda.synchronize(self.engine.device)
+            dist.barrier()
+            self.local = None
+            self.engine.peer_free(self._ptr)
+
+
 class SequenceScanner:
     """`scan_all_pairs` bound to one device's Engine (the B200 path)."""
 
     def __init__(self, engine, rank: int = 0, world: int = 1, group=None):
         self.engine, self.rank, self.world, self.group = engine, rank, world, group
+        self._peers = None
 
     def _embed(self, block: torch.Tensor, k: int) -> torch.Tensor:
         if block.shape[0] == 0:
@@ -140,9 +178,46 @@ class SequenceScanner:
         return self.engine.score_matrix(rows, cols, out=out)
 
     def scan(self, graphs: torch.Tensor, k: int, gather_scores: bool = True, graphs_are_local: bool = False, marks=None,
-             out: Optional[torch.Tensor] = None):
+             out: Optional[torch.Tensor] = None, exchange: str = "peer"):
+        """exchange="peer" (default with more than one rank on a CUDA box): the exchange fused into the score kernel's
+        stores over NVLink peer memory (scan_peer_store; the result lives in a scanner-owned buffer, `out` is ignored).
+        exchange="nccl": the score kernel, then one in-place NCCL all-gather of the score rows (scan_all_pairs)."""
+        if (exchange == "peer" and self.world > 1 and gather_scores and not graphs_are_local
+                and self.engine.device.type == "cuda"):
+            return self.scan_peer_store(graphs, k, marks)
         return scan_all_pairs(graphs, k, self._embed, self._score, self.rank, self.world, self.group,
                               gather_scores, graphs_are_local, marks, out)
+
+    def scan_peer_store(self, graphs: torch.Tensor, k: int, marks=None):
+        """The multi-GPU scan with compute and exchange in ONE kernel: rank r embeds its row block, the pooled vectors are
+        all-gathered (512 KB; this collective also tells every rank that all peers have entered this scan, i.e. are done
+        reading the previous result), then the tcgen05 score kernel writes each score of the row block into every rank's
+        [M, M] matrix — its own HBM and, over NVLink, the peers' (PeerResult) — while the next tiles are on the tensor
+        cores; a stream-ordered 1-element all-reduce then publishes "my stores are complete" to the peers.
+        Returns (this rank's full matrix — owned by the scanner, overwritten by the next scan — , (lo, hi))."""
+        mark = marks or (lambda name: None)
+        m = graphs.shape[0]
+        lo, hi = row_block(m, self.rank, self.world)
+        if self._peers is None or self._peers.m != m:
+            if self._peers is not None:
+                self._peers.close()
+            self._peers = PeerResult(m, self.engine, self.rank, self.world, self.group)
+        pr = self._peers
+        pooled_rows = self._embed(graphs[lo:hi].contiguous(), k)
+        mark("embed")
+        pooled_all = _all_gather_rows(pooled_rows, m, self.world, self.group)
+        mark("gather_pooled")
+        if hi > lo:
+            self.engine.score_matrix_multi(pooled_rows, pooled_all, [p + lo * m * 4 for p in pr.ptrs], m)
+        mark("score")
+        dist.all_reduce(pr.flag, group=self.group)          # stream-ordered: completes once every rank's kernel has finished
+        mark("gather_scores")
+        return pr.local, (lo, hi)
+
+    def close(self):
+        if self._peers is not None:
+            self._peers.close()
+            self._peers = None
 
     def top_matches(self, graphs: torch.Tensor, k: int, per_row: int = 5, exclude_window: int = 50):
         """Loop-closure style query: for each row graph of this rank, the best-scoring earlier frames outside a

@@ -33,7 +33,7 @@ def test_scan_matches_pairwise_forward(kitti_state):
     eng.close()
 
 
-def _nccl_worker(rank, world, port, m, out_dir):
+def _nccl_worker(rank, world, port, m, out_dir, exchange="nccl"):
     import os
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -45,18 +45,24 @@ def _nccl_worker(rank, world, port, m, out_dir):
         eng = Engine(rank)
         eng.set_weights(orc.load_state_npz(os.path.join(root, "tests", "golden", "model_kitti.npz")))
         graphs = synth.make_graphs(m, 64, 20, seed=13).cuda()
-        full, (lo, hi) = scan.SequenceScanner(eng, rank, world).scan(graphs, 20)
+        sc = scan.SequenceScanner(eng, rank, world)
+        full, (lo, hi) = sc.scan(graphs, 20, exchange=exchange)
+        if exchange == "peer":                      # a second scan into the same peer-mapped buffers (reuse protocol)
+            full, (lo, hi) = sc.scan(graphs, 20, exchange=exchange)
         torch.cuda.synchronize()
         torch.save({"full": full.cpu(), "lo": lo, "hi": hi}, os.path.join(out_dir, f"r{rank}.pt"))
+        sc.close()
         eng.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("m", [256, 301])      # equal row blocks (one in-place all-gather) and unequal ones (pad path)
-def test_two_rank_nccl_scan_is_bit_equal_to_single_gpu(kitti_state, tmp_path, m):
+@pytest.mark.parametrize("m,exchange", [(256, "nccl"), (301, "nccl"), (256, "peer"), (301, "peer")])
+def test_two_rank_nccl_scan_is_bit_equal_to_single_gpu(kitti_state, tmp_path, m, exchange):
     """Config 4 on real ranks: two processes, one GPU each, NCCL — the sharded [M, M] matrix every rank ends up with is
-    bit-equal to the single-GPU scan (the row block a rank computes does not depend on how many ranks there are)."""
+    bit-equal to the single-GPU scan (the row block a rank computes does not depend on how many ranks there are).
+    m = 256 / 301: equal row blocks (one in-place all-gather) / unequal ones (pad path); exchange "peer": the score kernel
+    stores straight into both ranks' matrices over NVLink peer memory (CUDA IPC), no score collective."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import socket
@@ -70,7 +76,7 @@ def test_two_rank_nccl_scan_is_bit_equal_to_single_gpu(kitti_state, tmp_path, m)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_nccl_worker, args=(2, port, m, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, port, m, str(tmp_path), exchange), nprocs=2, join=True)
     for r in range(2):
         o = torch.load(tmp_path / f"r{r}.pt")
         assert o["full"].shape == (m, m)
