@@ -152,9 +152,16 @@ __device__ __forceinline__ float pick_uniform(const float (&v)[EPL], int jt) {
 // class's value pd[i][R-1], columns >= N carry -inf.  Only the NQ = ceil(R/32) column blocks that hold active nodes
 // are computed.
 // ------------------------------------------------------------------------------------------------------------
+// experiment switch (profiles/experiments/r02_embed_upper_bound.txt): -DSGPR_UB_EXPERIMENT=1 cuts the K loops of the
+// 64-channel Gram / GEMM tiles to one step — wrong results, the time of a kernel whose contractions cost nothing
+#ifndef SGPR_UB_EXPERIMENT
+#define SGPR_UB_EXPERIMENT 0
+#endif
+
 template <int NPL, int NQ, int NR>
 __device__ __forceinline__ void gram_rows(const float* __restrict__ sXt, const float* __restrict__ sXX,
                                           float* __restrict__ sY, int c4n, int R, int N, int r0, int lane) {
+    if (SGPR_UB_EXPERIMENT && c4n == 16) c4n = 1;
     float2 acc[NR][NQ];
 #pragma unroll
     for (int r = 0; r < NR; ++r)
@@ -451,6 +458,7 @@ template <int NR, int CPL, int EPI>
 __device__ __forceinline__ void gemm_rows(const float* __restrict__ sXin, const float* __restrict__ sW,
                                           float* __restrict__ sOut, int outStride, const float* __restrict__ ab,
                                           int cin4, int r0, int lane) {
+    if (SGPR_UB_EXPERIMENT && cin4 == 16 && EPI == 0) cin4 = 1;
     constexpr int CO = 32 * CPL;
     constexpr int ROW = 2 * CO;                  // floats per channel-pair row
     float2 acc[NR][CPL];
