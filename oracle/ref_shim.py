@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference (/root/reference) on a CPU-only box.  TEST INFRASTRUCTURE ONLY.
 
 Build-container use only (the GPU box has no /root/reference): `oracle/make_golden.py` uses this to run the
-reference's own `SG.forward` and record golden vectors; `tests/test_reference_live.py` uses it (skipping when
-the reference tree is absent) to compare oracle and reference live.  No reference source is copied — the
+reference's own `SG.forward` and record golden vectors (`oracle/make_golden_train.py` likewise for two optimiser
+steps); the reference's own scripts are executed separately by `tests/test_reference_scripts.py`, on top of the drop-in
+modules.  No reference source is copied — the
 reference modules are imported from where they lie, behind import-time stubs for what this image lacks
 (texttable / tensorboardX / matplotlib), a no-op `.cuda()`, a CPU `torch.device` for dgcnn.py:32, and a
 `Loader` for the PyYAML-6 `yaml.load` call at parser_sg.py:37.  Recipe: SURVEY.md §8(c).

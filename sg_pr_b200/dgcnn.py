@@ -1,6 +1,6 @@
 """`knn` / `get_graph_feature` with the reference's names and tensor contracts (/root/reference/dgcnn.py:14-49) as
-differentiable stock PyTorch ops on whatever device `x` lives on.  Used by the training path only; in eval mode both
-are fused into csrc/embed_kernel.cuh.  The DGCNN / PointNet classifier zoo of the reference file (dgcnn.py:52-149)
+differentiable stock PyTorch ops on whatever device `x` lives on.  Used by `torch_baseline.py` only (benchmark baseline,
+tie-rule reference); the product fuses both into csrc/embed_kernel.cuh (eval) and csrc/train_kernels.cuh (training).  The DGCNN / PointNet classifier zoo of the reference file (dgcnn.py:52-149)
 is dead code for SG_PR and is not provided."""
 import torch
 

@@ -2,8 +2,9 @@
 parameter names (`AttentionModule.weight_matrix`; `TenorNetworkModule` (sic) `.weight_matrix`,
 `.weight_matrix_block`, `.bias` — /root/reference/layers_batch.py:3-83) so checkpoints load unchanged.
 
-In eval mode the arithmetic of both modules runs inside the fused CUDA kernel (csrc/embed_kernel.cuh); the
-`forward` methods below are the differentiable device path used only by training (`SG.forward` in train mode).
+In eval AND in train mode the arithmetic of both modules runs in the CUDA library (csrc/embed_kernel.cuh,
+csrc/train_kernels.cuh); the `forward` methods below are stock PyTorch ops kept only for `torch_baseline.py` — the
+"unmodified module code on the same GPU" baseline of the benchmarks and the CUDA-reference of the tie-rule tests.
 """
 import torch
 
