@@ -372,8 +372,8 @@ sgpr_score_matrix_umma_kernel(const ScoreMatArgs A, const HeadParams H) {
 // operands of the tile in flight: row graph il owns columns 256 + 32 il .. +31 = [ Z_big(16) | Z_small(16) ].
 //   MMA2 pass 1: A = [Z_big | Z_small] (K = 32), B = rows [W1_big | W1_big]   ->  Z_big.W1_big + Z_small.W1_big
 //   MMA2 pass 2: A = Z_big (K = 16),            B = rows [W1_small | 0]      ->  + Z_big.W1_small
-// Warps 0-7 only PRODUCE Z (per row graph the four quadrant warps arrive on zfull[il], 128 arrivals), warps 8-15 only
-// CONSUME h (hfull[buffer][il], tcgen05.commit of the FC1 MMAs) — neither half ever idles through the MMA round trip of
+// Warps 0-7 only PRODUCE Z (per slice of four row graphs the four quadrant warps arrive on zfull[slice], 128 arrivals),
+// warps 8-15 only CONSUME h (hfull[buffer][slice], tcgen05.commit of the slice's FC1 MMAs) — neither half ever idles through the MMA round trip of
 // its own tile; the MMA thread issues the next tile's bilinear MMAs before it serves the current tile's FC1 MMAs.
 // =====================================================================================================================
 constexpr int kTileI2 = 8;                       // row graphs per tile
@@ -434,8 +434,8 @@ sgpr_score_matrix_umma2_kernel(const ScoreMat2Args A, const HeadParams H) {
     uint64_t* empty = bars + 2;       // [2]
     uint64_t* tfull = bars + 4;       // [2]
     uint64_t* tempty = bars + 6;      // [2]
-    uint64_t* zfull = bars + 8;       // [8]     Z of row graph il in TMEM (128 arrivals: the four quadrant warps)
-    uint64_t* hfull = bars + 16;      // [2][8]  FC1 accumulator of row graph il of the tile in D1 buffer a complete
+    uint64_t* zfull = bars + 8;       // [2]     Z of a slice (four row graphs) in TMEM (128 arrivals: its four quadrant warps)
+    uint64_t* hfull = bars + 16;      // [2][2]  FC1 accumulators of a slice of the tile in D1 buffer a complete
     uint64_t* wfull = bars + 32;      // W1 planes landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
 
@@ -450,7 +450,7 @@ sgpr_score_matrix_umma2_kernel(const ScoreMat2Args A, const HeadParams H) {
             mbar_init(tfull + s, 1);
             mbar_init(tempty + s, (kEpiWarps2 / 2) * 32);
         }
-        for (int i = 0; i < kTileI2; ++i) { mbar_init(zfull + i, 128); mbar_init(hfull + i, 1); mbar_init(hfull + kTileI2 + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(zfull + i, 128); mbar_init(hfull + i, 1); mbar_init(hfull + 2 + i, 1); }
         mbar_init(wfull, 1);
         fence_mbar_init();
     }
@@ -494,13 +494,13 @@ sgpr_score_matrix_umma2_kernel(const ScoreMat2Args A, const HeadParams H) {
                         zs[4 * t4 + c] = __fsub_rn(z, zb[4 * t4 + c]);
                     }
                 }
-                // Z slot of this row graph: free once the FC1 MMA of the previous tile has read it
-                if (it > 0) { mbar_wait_wd(hfull + ((it - 1) & 1) * kTileI2 + il, ((it - 1) >> 1) & 1); tc_fence_after(); }
+                // Z slots of this slice: free once the FC1 MMAs of the previous tile have read them
+                if (u == 0 && it > 0) { mbar_wait_wd(hfull + ((it - 1) & 1) * 2 + slice, ((it - 1) >> 1) & 1); tc_fence_after(); }
                 tc_st32(tmem_base + lane_base + static_cast<uint32_t>(2 * kN1 + il * 32), zb, zs);
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(zfull + il);
             }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(zfull + slice);                              // one hand-over per slice of four row graphs
         }
     } else if (warp < kEpiWarps2) {
         // ===================== epilogue, second half: h <- TMEM, bias, relu, FC2, sigmoid, store ========================
@@ -517,8 +517,7 @@ sgpr_score_matrix_umma2_kernel(const ScoreMat2Args A, const HeadParams H) {
                 const int il = (kTileI2 / 2) * slice + u;
                 const int i = ib * kTileI2 + il;
                 float h[kT];
-                mbar_wait_wd(hfull + a * kTileI2 + il, aph);
-                tc_fence_after();
+                if (u == 0) { mbar_wait_wd(hfull + a * 2 + slice, aph); tc_fence_after(); }
                 tc_ld16(d1 + il * kT, h);
                 tc_wait_ld();
                 float y = 0.0f;
@@ -580,15 +579,17 @@ sgpr_score_matrix_umma2_kernel(const ScoreMat2Args A, const HeadParams H) {
         for (int it = 0; it < n_it; ++it) {
             if (it + 1 < n_it) issue_bilinear(it + 1);              // next tile's bilinear MMAs run under this tile's epilogue
             const uint32_t d1 = tmem_base + static_cast<uint32_t>((it & 1) * kN1);
-            for (int il = 0; il < kTileI2; ++il) {
-                mbar_wait_wd(zfull + il, it & 1);
+            for (int sl = 0; sl < 2; ++sl) {
+                mbar_wait_wd(zfull + sl, it & 1);
                 tc_fence_after();
-                const uint32_t d2 = d1 + il * kT, az = tmem_base + static_cast<uint32_t>(2 * kN1 + il * 32);
+                for (int il = sl * (kTileI2 / 2); il < (sl + 1) * (kTileI2 / 2); ++il) {
+                    const uint32_t d2 = d1 + il * kT, az = tmem_base + static_cast<uint32_t>(2 * kN1 + il * 32);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d2, az + 8 * k, wb + 2 * k, kIdesc2, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d2, az + 8 * k, wb + 2 * k, kIdesc2, k > 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) tc_mma_tf32_ts(d2, az + 8 * k, ws + 2 * k, kIdesc2, 1u);
-                tc_commit(hfull + (it & 1) * kTileI2 + il);
+                    for (int k = 0; k < 2; ++k) tc_mma_tf32_ts(d2, az + 8 * k, ws + 2 * k, kIdesc2, 1u);
+                }
+                tc_commit(hfull + (it & 1) * 2 + sl);
             }
         }
     }
