@@ -113,7 +113,8 @@ def emu_engine(kitti_state):
 def test_emulated_cpu_rule_reproduces_dense_golden(emu_engine):
     """Graphs WITHOUT pads (the tie-rule regime): `knn_ties="cpu"` is the reference on CPU to 1e-5, same k-NN sets."""
     with np.load(os.path.join(GOLDEN, "ref_synth_n64_k20_dense.npz")) as z:
-        f1, f2 = torch.from_numpy(z["features_1"]), torch.from_numpy(z["features_2"])
+        nb = 2                                              # two of the four golden pairs keep the CPU suite short
+        f1, f2 = torch.from_numpy(z["features_1"])[:nb], torch.from_numpy(z["features_2"])[:nb]
         emu_engine.set_knn_ties("cpu")
         try:
             assert emu_engine.knn_ties() == "cpu"
@@ -121,12 +122,12 @@ def test_emulated_cpu_rule_reproduces_dense_golden(emu_engine):
             got = emu_engine.embed(f1, 20, trace=True, want_emb=True)
         finally:
             emu_engine.set_knn_ties("cuda")
-        assert float(np.abs(score.numpy() - z["score"]).max()) <= 1e-5
-        assert float(np.abs(a1.numpy() - z["att_1"]).max()) <= 1e-5
-        assert float(np.abs(a2.numpy() - z["att_2"]).max()) <= 1e-5
-        np.testing.assert_allclose(got["emb"].numpy(), z["emb_1"], atol=2e-5, rtol=1e-5)
+        assert float(np.abs(score.numpy() - z["score"][:nb]).max()) <= 1e-5
+        assert float(np.abs(a1.numpy() - z["att_1"][:nb]).max()) <= 1e-5
+        assert float(np.abs(a2.numpy() - z["att_2"][:nb]).max()) <= 1e-5
+        np.testing.assert_allclose(got["emb"].numpy(), z["emb_1"][:nb], atol=2e-5, rtol=1e-5)
         for layer in range(6):
-            want = np.sort(z[f"knn_idx_1_{layer}"], axis=-1)
+            want = np.sort(z[f"knn_idx_1_{layer}"][:nb], axis=-1)
             assert np.array_equal(np.sort(got["knn"][:, layer].numpy().astype(np.int64), axis=-1), want), layer
 
 
@@ -134,9 +135,9 @@ def test_emulated_default_rule_differs_from_cpu_reference_only_by_exact_ties(emu
     """The default (ATen-CUDA) rule on the same dense batch: far from the CPU golden in score (that is the point), but the
     FIRST k-NN divergence of every graph branch is a swap among exactly tied distances — never a different distance."""
     with np.load(os.path.join(GOLDEN, "ref_synth_n64_k20_dense.npz")) as z:
-        f1 = torch.from_numpy(z["features_1"])
-        want_score = z["score"]
-        f2 = torch.from_numpy(z["features_2"])
+        f1 = torch.from_numpy(z["features_1"])[:2]
+        want_score = z["score"][:2]
+        f2 = torch.from_numpy(z["features_2"])[:2]
     assert emu_engine.knn_ties() == "cuda"
     score, _, _ = emu_engine.forward_pairs(f1, f2, 20)
     assert float(np.abs(score.numpy() - want_score).max()) > 1e-3
