@@ -56,7 +56,9 @@ void score_matrix_umma_launch(int sm_count, cudaStream_t st, const float* pooled
     float* rowblk = cols_small + static_cast<size_t>(m128) * 32;
     // one launch prepares both sides: CTAs [0, gr) split the row side (64 KB of shared memory: the transposed NTN tensor),
     // CTAs [gr, gr + gc) the column side
-    const int gr = min((r16 + 3) / 4, sm_count * 2), gc = min((m128 + 3) / 4, sm_count * 2);
+    // (8 graphs per CTA step; one CTA per SM on the row side amortises its 66 KB table load over more steps, the column
+    // side — no table — gets half an SM count: the whole preparation is a single wave)
+    const int gr = min((r16 + 7) / 8, sm_count), gc = min((m128 + 7) / 8, sm_count / 2);
     umma::sgpr_ntn_split_kernel<<<gr + gc, kThreads, umma::kSplitSmem, st>>>(pooled_rows, R, r16, proj_big, proj_small, rowblk,
                                                                           pooled_cols, M, m128, cols_big, cols_small, nullptr, gr, pw);
     if (version == 2) {
