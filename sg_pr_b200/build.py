@@ -20,7 +20,7 @@ OBJ_DIR = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libsgpr_b200.so")
 HEADERS = [os.path.join(ROOT, "include", h) for h in ("sgpr_b200.h", "sgpr_b200_train.h")]
 COMMON = ["common.cuh", "launchers.hpp"]
-EMBED_DEPS = COMMON + ["embed_kernel.cuh", "topk_nth.cuh", "sortnet32.inc", "sortnet16.inc", "sortnet8.inc"]
+EMBED_DEPS = COMMON + ["embed_kernel.cuh", "embed_tc_kernel.cuh", "tc_ops.cuh", "topk_nth.cuh", "sortnet32.inc", "sortnet16.inc", "sortnet8.inc"]
 TRAIN_DEPS = EMBED_DEPS + ["train_kernels.cuh"]
 # object name -> (source, extra defines, dependencies)
 UNITS = {

@@ -98,6 +98,7 @@ struct sgpr_ctx {
     float* d_fc1_planes = nullptr;   // [2][16][32] FC1 weights as UMMA B operand (tcgen05 score matrix, version 2)
     int scoremat_version = 1;    // tcgen05 score-matrix kernel: 1 = FFMA2 epilogue (default, faster), 2 = FC1 on the tensor cores
                                  // too, A operand in TMEM (SGPR_SCOREMAT_V2=1; see scoremat_umma.cuh for the measurements)
+    int embed_tc = 0;            // N <= 64: the tensor-core variant of the fused kernel (SGPR_EMBED_TC=1)
     int scoremat_ffma = 0;       // score matrix on fp32 FMA instead of tcgen05 (SGPR_SCOREMAT_FFMA=1; always in tests/emu)
     int knn_ties = SGPR_TIES_CUDA;   // k-NN tie rule (sgpr_set_knn_ties); SGPR_KNN_TIES=cpu|cuda sets the initial value
 };
@@ -133,6 +134,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
     if (const char* nz = getenv("SGPR_NO_ZEROCOPY")) ctx->zerocopy = (nz[0] == '1') ? 0 : 1;
     if (const char* nb = getenv("SGPR_NO_BALANCE")) ctx->balance = (nb[0] == '1') ? 0 : 1;
     if (const char* v2 = getenv("SGPR_SCOREMAT_V2")) ctx->scoremat_version = (v2[0] == '1') ? 2 : 1;
+    if (const char* et = getenv("SGPR_EMBED_TC")) ctx->embed_tc = (et[0] == '1') ? 1 : 0;
     if (const char* sf = getenv("SGPR_SCOREMAT_FFMA")) ctx->scoremat_ffma = (sf[0] == '1') ? 1 : 0;
     if (const char* kt = getenv("SGPR_KNN_TIES")) ctx->knn_ties = (strcmp(kt, "cpu") == 0) ? SGPR_TIES_CPU : SGPR_TIES_CUDA;
     // opt in to the full shared-memory carve-out (the per-NPL objects subtract each kernel's static __shared__ bytes)
@@ -140,6 +142,7 @@ int sgpr_create(sgpr_ctx** out, int device) {
     e = embed_optin<1>(optin);
     if (e == cudaSuccess) e = embed_optin<2>(optin);
     if (e == cudaSuccess) e = embed_optin<4>(optin);
+    if (e == cudaSuccess) e = embed_tc_optin(optin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sgpr_score_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
 #ifndef SGPR_EMU
     if (e == cudaSuccess) e = score_matrix_umma_optin();
@@ -205,7 +208,8 @@ int sgpr_set_weights(sgpr_ctx* ctx, const sgpr_weights* w) {
     const PackOffsets& o = ctx->off;
     ctx->pw = PackedWeights{b + o.s1,    b + o.w_s2,  b + o.w_s3,  b + o.w_f1,  b + o.w_f2,  b + o.w_f3,
                             b + o.w_end, b + o.ab_s2, b + o.ab_s3, b + o.ab_f1, b + o.ab_f2, b + o.ab_f3,
-                            b + o.ab_end, b + o.att_w, b + o.ntn_w, b + o.ntn_v, b + o.ntn_b};
+                            b + o.ab_end, b + o.att_w, b + o.ntn_w, b + o.ntn_v, b + o.ntn_b,
+                            b + o.wtc_s2, b + o.wtc_s3, b + o.wtc_f2, b + o.wtc_f3};
 #ifndef SGPR_EMU
     {
         float planes[1024];
@@ -272,6 +276,13 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
         ctx->launches += 1;
         a.order = ctx->d_order + a.G;
         if (!resident) a.work_ctr = ctx->d_ctrs + 1;
+    }
+    if (ctx->embed_tc && npl == 2 && ctx->knn_ties == SGPR_TIES_CUDA && !a.trace_knn && !a.trace_layers) {
+        embed_tc_launch(grid, st, a, ctx->pw, ctx->hp);
+        ctx->launches += 1;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(SGPR_E_CUDA, "embed (tensor-core) kernel launch failed: %s", cudaGetErrorString(e));
+        return SGPR_OK;
     }
     switch (npl) {
         case 1: embed_launch<1>(ctx->knn_ties, grid, L.total, st, a, ctx->pw, ctx->hp); break;

@@ -52,6 +52,11 @@ struct PackedWeights {
     const float* ntn_w;     // [32][512]  tensor_network.weight_matrix.view(32, 32*16): col = b*16 + t
     const float* ntn_v;     // [16][64]
     const float* ntn_b;     // [16]
+    // tensor-core operand planes of the four 64-channel EdgeConv layers: [big, small][128][64] (pack.hpp::pack_edgeconv_tc)
+    const float* wtc_s2;
+    const float* wtc_s3;
+    const float* wtc_f2;
+    const float* wtc_f3;
 };
 
 // FC head, small enough to travel as a kernel parameter (constant bank, uniform access).

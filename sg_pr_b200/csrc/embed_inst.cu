@@ -1,6 +1,9 @@
 // One object per NPL (-DSGPR_INST_NPL=1|2|4): the instantiations of the fused eval kernel and their launch wrappers.
 #include "../../include/sgpr_b200.h"
 #include "embed_kernel.cuh"
+#if SGPR_INST_NPL == 2
+#include "embed_tc_kernel.cuh"
+#endif
 #include "launchers.hpp"
 
 #ifndef SGPR_INST_NPL
@@ -40,5 +43,27 @@ void embed_launch<SGPR_INST_NPL>(int ties, int grid, int smem, cudaStream_t st, 
         SGPR_LAUNCH(kern, grid, kThreads, smem, st, a, pw, hp);
     }
 }
+
+#if SGPR_INST_NPL == 2
+// the tensor-core variant of the fused kernel (N <= 64, default tie rule, no debug taps)
+cudaError_t embed_tc_optin(int optin_bytes) {
+#ifdef SGPR_EMU
+    (void)optin_bytes;
+    return cudaSuccess;
+#else
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, sgpr_embed_tc_kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(sgpr_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                optin_bytes - static_cast<int>(fa.sharedSizeBytes));
+#endif
+}
+
+int embed_tc_smem(int ks) { return make_tc_layout(ks).total; }
+
+void embed_tc_launch(int grid, cudaStream_t st, const EmbedArgs& a, const PackedWeights& pw, const HeadParams& hp) {
+    SGPR_LAUNCH(sgpr_embed_tc_kernel, grid, kThreads, make_tc_layout(a.KS).total, st, a, pw, hp);
+}
+#endif
 
 }  // namespace sgpr

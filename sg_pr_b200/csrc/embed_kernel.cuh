@@ -526,6 +526,7 @@ __device__ __forceinline__ void gemm_rows(const float* __restrict__ sXin, const 
 #pragma unroll
         for (int j = 0; j < CPL; ++j) { al[j] = __ldg(ab + lane * CPL + j); be[j] = __ldg(ab + CO + lane * CPL + j); }
     }
+    if constexpr (EPI == 1) __syncwarp();          // conv_end may run in place (output rows = input rows): reads first
 #pragma unroll
     for (int n = 0; n < NR; ++n) {
         float y[CPL];
@@ -570,10 +571,39 @@ __device__ __forceinline__ void norms_rows(const float* __restrict__ sT, float* 
 // (j*YS) of the neighbour rows; 4*GW of them are fetched per step (GW 8-byte list words, then 4*GW independent row
 // loads) to keep the shared-memory pipe busy.
 // ------------------------------------------------------------------------------------------------------------
-template <int COUT>
+// Output of a layer as tensor-core operand planes (embed_tc_kernel.cuh): z = big + small, big = z rounded to TF32, both in
+// the K-major 128-byte-swizzled image of tc_ops.cuh (two atoms of 32 channels), plus the row's squared norm.
+struct PlaneOut {
+    float* big;       // [2 atoms][64 rows][32]
+    float* small;
+    float* xx;        // [64] squared norms of the rows (dgcnn.py:16 term of the next layer)
+};
+#ifdef SGPR_EMU
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+#else
+__device__ __forceinline__ float tf32_round(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+#endif
+// a lane's channel pair (2*lane, 2*lane+1) of row i -> planes, and the row norm (all lanes call; lane 0 stores it)
+__device__ __forceinline__ void store_planes(const PlaneOut& P, int i, int lane, float z0, float z1) {
+    const int c = 2 * lane;
+    const uint32_t off = static_cast<uint32_t>(c >> 5) * 2048u + static_cast<uint32_t>(i) * 32u +
+                         (((((c & 31) >> 2) ^ (i & 7)) << 2) | (c & 3));
+    const float b0 = tf32_round(z0), b1 = tf32_round(z1);
+    *reinterpret_cast<float2*>(P.big + off) = make_float2(b0, b1);
+    *reinterpret_cast<float2*>(P.small + off) = make_float2(__fsub_rn(z0, b0), __fsub_rn(z1, b1));
+    const float s = warp_sum(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)));
+    if (lane == 0) P.xx[i] = s;
+}
+
+template <int COUT, int PLANES = 0>
 __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const uint16_t* __restrict__ sIdx,
                                             const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ ab,
-                                            float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane) {
+                                            float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane,
+                                            const PlaneOut* planes = nullptr) {
     constexpr int CPL = COUT / 32;
     constexpr int GW = SGPR_GATHER_W;
     float al[CPL], be[CPL];
@@ -614,12 +644,18 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
                     m[p] = fmaxf(m[p], fmaxf(fmaxf(v[4 * q][p], v[4 * q + 1][p]), fmaxf(v[4 * q + 2][p], v[4 * q + 3][p])));
             }
         }
+        float zz[CPL];
 #pragma unroll
         for (int p = 0; p < CPL; ++p) {
             const float y = __fadd_rn(__fsub_rn(m[p], ai[p]), bi[p]);
             const float z = lrelu(fmaf(y, al[p], be[p]));
-            sDst[i * XS + lane * CPL + p] = z;
+            zz[p] = z;
+            if constexpr (!PLANES) sDst[i * XS + lane * CPL + p] = z;
             if (trace) trace[i * 64 + lane * CPL + p] = z;
+        }
+        if constexpr (PLANES) {
+            static_assert(!PLANES || CPL == 2, "operand planes are 64 channels wide");
+            store_planes(*planes, i, lane, zz[0], zz[CPL - 1]);
         }
     }
 }
@@ -631,9 +667,11 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
 // A lane owns output channels 2*lane, 2*lane+1; neighbour coordinates come from the layer-0 node tile (list entries
 // are word offsets j*XS into it).
 // ------------------------------------------------------------------------------------------------------------
+template <int PLANES = 0>
 __device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uint16_t* __restrict__ sIdx,
                                          const uint8_t* __restrict__ sCnt, int KS, const float* __restrict__ s1,
-                                         float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane) {
+                                         float* __restrict__ sDst, float* __restrict__ trace, int r0, int r1, int lane,
+                                         const PlaneOut* planes = nullptr) {
     // sT: the (x, y, z, 0) node tile of layer 0 (stride XS).  p0 = {wa0,wa1,wa2,wb0}, p1 = {wb1,wb2,alpha,beta} of
     // channel 2*lane; q0/q1 the same for channel 2*lane+1
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(s1) + (2 * lane) * 2);
@@ -665,7 +703,8 @@ __device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uin
         float y1 = fmaf(q0.w, xi.x, m1); y1 = fmaf(q1.x, xi.y, y1); y1 = fmaf(q1.y, xi.z, y1);
         const float z0 = lrelu(fmaf(y0, p1.z, p1.w));
         const float z1 = lrelu(fmaf(y1, q1.z, q1.w));
-        *reinterpret_cast<float2*>(sDst + i * XS + 2 * lane) = make_float2(z0, z1);
+        if constexpr (PLANES) store_planes(*planes, i, lane, z0, z1);
+        else *reinterpret_cast<float2*>(sDst + i * XS + 2 * lane) = make_float2(z0, z1);
         if (trace) { trace[i * 64 + 2 * lane] = z0; trace[i * 64 + 2 * lane + 1] = z1; }
     }
 }
@@ -730,6 +769,116 @@ __device__ __forceinline__ void pair_head_cta(const float* __restrict__ e1, cons
         float z = (tid < kBn) ? P[tid] : 0.0f;                                                                          // sg_net.py:136
         z = group16_sum(z);
         if (tid == 0) *score_out = sigmoidf_acc(__fadd_rn(z, H.fc2_b));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Everything after the EdgeConv stack for one graph (shared by the FFMA kernel below and the tensor-core kernel of
+// embed_tc_kernel.cuh): replicate the collapsed pad rows, attention pooling over all N nodes (layers_batch.py:28-39),
+// pooled vector out, and — in pairs mode — the pair head in whichever CTA of the pair finishes second.
+// sE: node embeddings [n][XS] (first 32 columns), complete for rows < R behind a CTA barrier; sScratch: >= 576 floats.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finish_graph(const EmbedArgs& A, const PackedWeights& W, const HeadParams& H, float* sE,
+                                             float* sRed, float* sScratch, int* sFlag, int g, int N, int R, int tid,
+                                             int warp, int lane) {
+    // every trailing pad is a copy of row R-1
+    for (int e = tid; e < (N - R) * kF3; e += kThreads) sE[(R + (e >> 5)) * XS + (e & 31)] = sE[(R - 1) * XS + (e & 31)];
+    __syncthreads();
+    if (A.emb) {
+        float* eo = A.emb + static_cast<size_t>(g) * N * kF3;
+        for (int e = tid; e < N * kF3; e += kThreads) eo[e] = sE[(e >> 5) * XS + (e & 31)];
+    }
+
+    // ================= attention pooling over all N nodes (layers_batch.py:28-39) =================
+    // warp w handles nodes w, w+8, ...; lane = feature index
+    float* sCtx = sRed + kWarps * 32;        // [32]
+    float* sPool = sRed + kWarps * 32 + 32;  // [32]
+    {   // ctx[b] = tanh(mean_n sum_a E[n][a] Watt[a][b])
+        float wcol[kF3];
+#pragma unroll
+        for (int a = 0; a < kF3; ++a) wcol[a] = __ldg(W.att_w + a * kF3 + lane);
+        float colsum = 0.0f;
+#pragma unroll 2
+        for (int n = warp; n < N; n += kWarps) {
+            float t = 0.0f;
+#pragma unroll
+            for (int a4 = 0; a4 < kF3 / 4; ++a4) {
+                const float4 e = *reinterpret_cast<const float4*>(sE + n * XS + 4 * a4);
+                t = fmaf(e.x, wcol[4 * a4 + 0], t);
+                t = fmaf(e.y, wcol[4 * a4 + 1], t);
+                t = fmaf(e.z, wcol[4 * a4 + 2], t);
+                t = fmaf(e.w, wcol[4 * a4 + 3], t);
+            }
+            colsum = __fadd_rn(colsum, t);
+        }
+        sRed[warp * 32 + lane] = colsum;
+    }
+    __syncthreads();
+    if (tid < kF3) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s = __fadd_rn(s, sRed[w * 32 + tid]);
+        sCtx[tid] = tanhf(s / static_cast<float>(N));
+    }
+    __syncthreads();
+    {   // att[n] = sigmoid(E[n] . ctx); pooled[a] = sum_n E[n][a] att[n]   (per-warp partials, then 8-way sum)
+        const float cb = sCtx[lane];
+        float* ao = A.pairs ? ((g & 1) ? A.att1 : A.att0) : A.att0;
+        if (ao) ao += static_cast<size_t>(A.pairs ? (g >> 1) : g) * N;
+        float pool = 0.0f;
+        for (int n0 = warp; n0 < N; n0 += 8 * kWarps) {          // up to 8 nodes of this warp at a time
+            float e[8], d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int n = n0 + u * kWarps;
+                e[u] = (n < N) ? sE[n * XS + lane] : 0.0f;
+                d[u] = __fmul_rn(e[u], cb);
+            }
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d[u] = __fadd_rn(d[u], __shfl_xor_sync(0xffffffffu, d[u], sft));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int n = n0 + u * kWarps;
+                if (n < N) {
+                    const float a = sigmoidf_acc(d[u]);
+                    if (ao && lane == 0) ao[n] = a;
+                    pool = fmaf(e[u], a, pool);
+                }
+            }
+        }
+        sRed[warp * 32 + lane] = pool;
+    }
+    __syncthreads();
+    if (tid < kF3) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s = __fadd_rn(s, sRed[w * 32 + tid]);
+        sPool[tid] = s;
+        A.pooled[static_cast<size_t>(g) * kF3 + tid] = s;
+    }
+
+    SGPR_TL(60);
+    // ================= pair head, run by whichever CTA of the pair finishes last =================
+    if (A.pairs) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *sFlag = atomicAdd(A.counters + (g >> 1), 1);
+        __syncthreads();
+        if (*sFlag == 1) {
+            __threadfence();
+            float* e1 = sRed;        // side 0 pooled
+            float* e2 = sRed + 32;   // side 1 pooled
+            if (tid < 64) {
+                const int side = tid >> 5, a = tid & 31;
+                const float v = __ldcg(A.pooled + (static_cast<size_t>(g & ~1) + side) * kF3 + a);
+                (side ? e2 : e1)[a] = v;
+            }
+            if (tid == 0) A.counters[g >> 1] = 0;
+            __syncthreads();
+            pair_head_cta(e1, e2, W, H, sScratch, A.score + (g >> 1), tid);
+        }
     }
 }
 
@@ -969,106 +1118,7 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         }
 
         SGPR_TL(58);
-        float* sE = sX;   // node embeddings, stride XS (first 32 columns)
-        // every trailing pad is a copy of row R-1
-        for (int e = tid; e < (N - R) * kF3; e += kThreads) sE[(R + (e >> 5)) * XS + (e & 31)] = sE[(R - 1) * XS + (e & 31)];
-        __syncthreads();
-        if (A.emb) {
-            float* eo = A.emb + static_cast<size_t>(g) * N * kF3;
-            for (int e = tid; e < N * kF3; e += kThreads) eo[e] = sE[(e >> 5) * XS + (e & 31)];
-        }
-
-        // ================= attention pooling over all N nodes (layers_batch.py:28-39) =================
-        // warp w handles nodes w, w+8, ...; lane = feature index
-        float* sCtx = sRed + kWarps * 32;        // [32]
-        float* sPool = sRed + kWarps * 32 + 32;  // [32]
-        {   // ctx[b] = tanh(mean_n sum_a E[n][a] Watt[a][b])
-            float wcol[kF3];
-#pragma unroll
-            for (int a = 0; a < kF3; ++a) wcol[a] = __ldg(W.att_w + a * kF3 + lane);
-            float colsum = 0.0f;
-#pragma unroll 2
-            for (int n = warp; n < N; n += kWarps) {
-                float t = 0.0f;
-#pragma unroll
-                for (int a4 = 0; a4 < kF3 / 4; ++a4) {
-                    const float4 e = *reinterpret_cast<const float4*>(sE + n * XS + 4 * a4);
-                    t = fmaf(e.x, wcol[4 * a4 + 0], t);
-                    t = fmaf(e.y, wcol[4 * a4 + 1], t);
-                    t = fmaf(e.z, wcol[4 * a4 + 2], t);
-                    t = fmaf(e.w, wcol[4 * a4 + 3], t);
-                }
-                colsum = __fadd_rn(colsum, t);
-            }
-            sRed[warp * 32 + lane] = colsum;
-        }
-        __syncthreads();
-        if (tid < kF3) {
-            float s = 0.0f;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) s = __fadd_rn(s, sRed[w * 32 + tid]);
-            sCtx[tid] = tanhf(s / static_cast<float>(N));
-        }
-        __syncthreads();
-        {   // att[n] = sigmoid(E[n] . ctx); pooled[a] = sum_n E[n][a] att[n]   (per-warp partials, then 8-way sum)
-            const float cb = sCtx[lane];
-            float* ao = A.pairs ? ((g & 1) ? A.att1 : A.att0) : A.att0;
-            if (ao) ao += static_cast<size_t>(A.pairs ? (g >> 1) : g) * N;
-            float pool = 0.0f;
-            for (int n0 = warp; n0 < N; n0 += 8 * kWarps) {          // up to 8 nodes of this warp at a time
-                float e[8], d[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int n = n0 + u * kWarps;
-                    e[u] = (n < N) ? sE[n * XS + lane] : 0.0f;
-                    d[u] = __fmul_rn(e[u], cb);
-                }
-#pragma unroll
-                for (int sft = 16; sft >= 1; sft >>= 1)
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) d[u] = __fadd_rn(d[u], __shfl_xor_sync(0xffffffffu, d[u], sft));
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int n = n0 + u * kWarps;
-                    if (n < N) {
-                        const float a = sigmoidf_acc(d[u]);
-                        if (ao && lane == 0) ao[n] = a;
-                        pool = fmaf(e[u], a, pool);
-                    }
-                }
-            }
-            sRed[warp * 32 + lane] = pool;
-        }
-        __syncthreads();
-        if (tid < kF3) {
-            float s = 0.0f;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) s = __fadd_rn(s, sRed[w * 32 + tid]);
-            sPool[tid] = s;
-            A.pooled[static_cast<size_t>(g) * kF3 + tid] = s;
-        }
-
-        SGPR_TL(60);
-        // ================= pair head, run by whichever CTA of the pair finishes last =================
-        if (A.pairs) {
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) sFlag = atomicAdd(A.counters + (g >> 1), 1);
-            __syncthreads();
-            if (sFlag == 1) {
-                __threadfence();
-                float* e1 = sRed;        // side 0 pooled
-                float* e2 = sRed + 32;   // side 1 pooled
-                if (tid < 64) {
-                    const int side = tid >> 5, a = tid & 31;
-                    const float v = __ldcg(A.pooled + (static_cast<size_t>(g & ~1) + side) * kF3 + a);
-                    (side ? e2 : e1)[a] = v;
-                }
-                if (tid == 0) A.counters[g >> 1] = 0;
-                __syncthreads();
-                pair_head_cta(e1, e2, W, H, sY, A.score + (g >> 1), tid);
-            }
-        }
+        finish_graph(A, W, H, sX, sRed, sY, &sFlag, g, N, R, tid, warp, lane);
         __syncthreads();
         SGPR_TL(62);
     }

@@ -23,6 +23,11 @@ SGPR_DECL_EMBED(2)
 SGPR_DECL_EMBED(4)
 #undef SGPR_DECL_EMBED
 
+// embed_inst.cu (NPL = 2 object): the tensor-core variant of the fused kernel (embed_tc_kernel.cuh)
+cudaError_t embed_tc_optin(int optin_bytes);
+int embed_tc_smem(int ks);
+void embed_tc_launch(int grid, cudaStream_t st, const EmbedArgs& a, const PackedWeights& pw, const HeadParams& hp);
+
 // scoremat_umma.cu: the tcgen05 score-matrix kernel (not part of the tests/emu build: inline tcgen05 PTX)
 cudaError_t score_matrix_umma_optin();
 size_t score_matrix_umma_scratch_floats(int R, int M);     // operand planes + V-block terms

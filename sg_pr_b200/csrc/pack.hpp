@@ -17,6 +17,7 @@ struct PackOffsets {          // offsets in floats into the blob; every section 
     size_t s1, w_s2, w_s3, w_f1, w_f2, w_f3, w_end;
     size_t ab_s2, ab_s3, ab_f1, ab_f2, ab_f3, ab_end;
     size_t att_w, ntn_w, ntn_v, ntn_b;
+    size_t wtc_s2, wtc_s3, wtc_f2, wtc_f3;   // tensor-core operand planes of the 64-channel EdgeConv layers (embed_tc_kernel.cuh)
     size_t total;
 };
 
@@ -43,6 +44,10 @@ inline PackOffsets make_offsets() {
     o.ntn_w = take(32 * 512);
     o.ntn_v = take(16 * 64);
     o.ntn_b = take(16);
+    o.wtc_s2 = take(2 * 128 * 64);
+    o.wtc_s3 = take(2 * 128 * 64);
+    o.wtc_f2 = take(2 * 128 * 64);
+    o.wtc_f3 = take(2 * 128 * 64);
     o.total = p;
     return o;
 }
@@ -80,6 +85,33 @@ inline void pack_edgeconv(const float* w, const sgpr_bn& bn, int cin, int cout, 
     }
 }
 
+// The same sign-folded [cin = 64][2*cout] matrix as pack_edgeconv builds, as the TMEM-resident A operand of the
+// tensor-core GEMM D[m][node] = sum_k W[m][k] x_node[k]: row m < cout is the (x_j - x_i) half, cout <= m < 2*cout the x_i
+// half, rows beyond 2*cout are zero; split x = big + small with big = x rounded to TF32 (ties away, cvt.rna.tf32.f32).
+// Layout [plane: big, small][m = 128][k = 64] row-major — a thread (TMEM lane = m) reads its 64 values contiguously.
+inline void pack_edgeconv_tc(const float* w, const sgpr_bn& bn, int cout, float eps, float* planes) {
+    const int cin = 64;
+    for (int i = 0; i < 2 * 128 * 64; ++i) planes[i] = 0.0f;
+    for (int c = 0; c < cout; ++c) {
+        float alpha, beta;
+        bn_terms(bn, c, eps, alpha, beta);
+        const float sign = (alpha < 0.0f) ? -1.0f : 1.0f;
+        for (int half = 0; half < 2; ++half) {
+            const int m = half * cout + c;
+            for (int ci = 0; ci < cin; ++ci) {
+                const float x = sign * w[static_cast<size_t>(c) * 2 * cin + half * cin + ci];
+                uint32_t bits;
+                std::memcpy(&bits, &x, 4);
+                bits = (bits + 0x1000u) & 0xFFFFE000u;
+                float big;
+                std::memcpy(&big, &bits, 4);
+                planes[m * 64 + ci] = big;
+                planes[128 * 64 + m * 64 + ci] = x - big;
+            }
+        }
+    }
+}
+
 inline int pack_weights(const sgpr_weights& hw, std::vector<float>& blob, HeadParams& hp, const PackOffsets& o) {
     blob.assign(o.total, 0.0f);
     const float eps = hw.bn_eps;
@@ -98,6 +130,10 @@ inline int pack_weights(const sgpr_weights& hw, std::vector<float>& blob, HeadPa
     pack_edgeconv(hw.f_conv_w[0], hw.f_bn[0], 12, 64, eps, blob.data() + o.w_f1, blob.data() + o.ab_f1);
     pack_edgeconv(hw.f_conv_w[1], hw.f_bn[1], 64, 64, eps, blob.data() + o.w_f2, blob.data() + o.ab_f2);
     pack_edgeconv(hw.f_conv_w[2], hw.f_bn[2], 64, 32, eps, blob.data() + o.w_f3, blob.data() + o.ab_f3);
+    pack_edgeconv_tc(hw.s_conv_w[1], hw.s_bn[1], 64, eps, blob.data() + o.wtc_s2);
+    pack_edgeconv_tc(hw.s_conv_w[2], hw.s_bn[2], 32, eps, blob.data() + o.wtc_s3);
+    pack_edgeconv_tc(hw.f_conv_w[1], hw.f_bn[1], 64, eps, blob.data() + o.wtc_f2);
+    pack_edgeconv_tc(hw.f_conv_w[2], hw.f_bn[2], 32, eps, blob.data() + o.wtc_f3);
     // conv_end [32][64] -> pair layout of [64][32]; BN sign kept (no max follows)
     for (int c = 0; c < 32; ++c) {
         float alpha, beta;

@@ -18,7 +18,7 @@ CSRC = os.path.join(ROOT, "sg_pr_b200", "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsgpr_emu.so")
 DEPS = [os.path.join(CSRC, f) for f in ("api.cu", "train.cu", "embed_inst.cu", "train_inst.cu", "train_kernels.cuh",
-                                        "embed_kernel.cuh", "head_kernels.cuh", "common.cuh", "pack.hpp", "topk_nth.cuh",
+                                        "embed_kernel.cuh", "head_kernels.cuh", "common.cuh", "pack.hpp", "topk_nth.cuh", "embed_tc_kernel.cuh", "tc_ops.cuh",
                                         "launchers.hpp")] + \
        [os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "sgpr_b200_train.h"),
         os.path.join(ROOT, "include", "sgpr_b200.h"), os.path.abspath(__file__)]

@@ -107,3 +107,27 @@ def test_emulated_host_entry_point_matches_device_entry(emu_engine):
     assert torch.equal(h_score, d_score) and torch.equal(h_a1, d_a1) and torch.equal(h_a2, d_a2)
     empty, _, _ = emu_engine.forward_pairs(f1[:0], f2[:0], 10)
     assert empty.shape == (0,)
+
+
+def test_emulated_tensor_core_variant_of_the_fused_kernel(kitti_state, monkeypatch):
+    """csrc/embed_tc_kernel.cuh (SGPR_EMBED_TC=1): Gram / GEMM of the 64-channel layers as 3xTF32 UMMAs — here with the
+    emulator's model of tcgen05 / TMEM (tests/emu + csrc/tc_ops.cuh), which checks the operand-plane swizzle, the TMEM
+    column map and the lane / row assignments.  Same scores as the FFMA kernel and the oracle."""
+    from tests.emu import build_emu
+    lib = _lib.bind(C.CDLL(build_emu.build()), _lib.SYMBOLS)
+    monkeypatch.setenv("SGPR_EMBED_TC", "1")
+    tc = Engine(lib=lib)
+    monkeypatch.delenv("SGPR_EMBED_TC")
+    ff = Engine(lib=lib)
+    tc.set_weights(kitti_state)
+    ff.set_weights(kitti_state)
+    for n, k in ((40, 10), (64, 20)):
+        f1, f2 = synth.make_pair_batch(2, n, k, seed=5)
+        a, b = tc.forward_pairs(f1, f2, k), ff.forward_pairs(f1, f2, k)
+        want = orc.forward_pairs(f1, f2, k, kitti_state)
+        assert float((a[0] - b[0]).abs().max()) <= 5e-6 and float((a[0] - want["score"]).abs().max()) <= 1e-5
+        assert float((a[1] - want["att_1"]).abs().max()) <= 1e-5
+    e = tc.embed(f1, 20, want_emb=True)
+    assert float((e["emb"] - want["emb_1"]).abs().max()) <= 2e-5
+    tc.close()
+    ff.close()

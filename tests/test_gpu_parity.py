@@ -280,6 +280,34 @@ def test_score_matrix_kernel_variants_agree(kitti_state, monkeypatch, env):
     e.close()
 
 
+def test_tensor_core_variant_of_the_fused_kernel(kitti_state, golden_dir, monkeypatch):
+    """csrc/embed_tc_kernel.cuh (opt-in, SGPR_EMBED_TC=1): the 64-channel Gram / GEMM tiles as 3xTF32 tcgen05 UMMAs with the
+    weights as a TMEM-resident A operand.  Same parity bar as the default kernel: golden batch, live oracle with near ties
+    explained, compact input, persistent launch."""
+    from sg_pr_b200.engine import Engine, compact_graphs
+    from tests.helpers import assert_scores_match_or_near_tie
+    monkeypatch.setenv("SGPR_EMBED_TC", "1")
+    tc = Engine(0)
+    monkeypatch.delenv("SGPR_EMBED_TC")
+    tc.set_weights(kitti_state)
+    with np.load(os.path.join(golden_dir, "ref_synth_n64_k20.npz")) as z:
+        f1, f2 = torch.from_numpy(z["features_1"]), torch.from_numpy(z["features_2"])
+        score, a1, _ = tc.forward_pairs(_cuda(f1), _cuda(f2), 20)
+        assert np.abs(score.cpu().numpy() - z["score"]).max() <= SCORE_TOL
+        assert np.abs(a1.cpu().numpy() - z["att_1"]).max() <= SCORE_TOL
+    for n, k, b in ((64, 20, 128), (40, 10, 64), (33, 8, 40)):
+        f1, f2 = synth.make_pair_batch(b, n, k, seed=70 + n)
+        want = orc.forward_pairs(f1, f2, k, kitti_state)
+        score, _, _ = tc.forward_pairs(_cuda(f1), _cuda(f2), k)
+        assert_scores_match_or_near_tie(tc, kitti_state, f1, f2, k, score, want["score"], SCORE_TOL)
+        again, _, _ = tc.forward_pairs_compact(_cuda(compact_graphs(f1)), _cuda(compact_graphs(f2)), n, k)
+        assert torch.equal(again, score)
+    g = _cuda(synth.make_graphs(700, 64, 20, seed=3))          # persistent launch, heaviest-first order
+    full = tc.embed(g, 20)["pooled"]
+    assert torch.equal(tc.embed(g[17:18].contiguous(), 20)["pooled"][0], full[17])
+    tc.close()
+
+
 def test_host_entry_point_matches_device(eng):
     f1, f2 = synth.make_pair_batch(64, 64, 20, seed=21)
     d_score, d_a1, d_a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)
