@@ -400,6 +400,74 @@ class SGTrainer(object):
             exit(-1)
         return feats[0], feats[1], target
 
+    def _training_batch(self, batch):
+        """The mirrored TRAINING batch of `batch` listed pairs in one pass: float32 `[2*len(batch), 15, node_num]` (rows
+        a0, b0, a1, b1, ...) and float32 targets `[2*len(batch)]` — the same bits as stacking `_training_features(pair)` of
+        every pair (hence as transfer_to_torch(process_pair(pair), True), sg_net.py:241-310) and the same consumption of
+        numpy's / random's global streams: the draws are taken pair by pair, cloud by cloud in the reference's call order
+        (subsample choices, flip, then per cloud angle / jitter / scale / perturbation / shift, utils.py:91-178), and only the
+        arithmetic is batched — elementwise numpy ops and stacked `np.matmul`s, which run the same BLAS routine on the same
+        [node_num, 3] x [3, 3] shapes as the per-cloud `np.dot`s (tests/test_host_logic.py checks bits and stream
+        positions).  uniform(lo, hi) is taken as lo + (hi - lo) * random_sample(), numpy's own definition."""
+        store = self._store()
+        want = int(self.args.node_num)
+        clouds = 2 * len(batch)
+        sample, normal = np.random.random_sample, np.random.standard_normal
+        xyz = np.zeros((clouds, want, 3))
+        labels = np.full((clouds, want), -1, dtype=np.int64)
+        flipped = np.zeros(clouds, dtype=bool)
+        u_angle, u_scale = np.empty(clouds), np.empty(clouds)
+        jitter = np.empty((clouds, want * 3))
+        perturb, u_shift = np.empty((clouds, 3)), np.empty((clouds, 3))
+        targets = np.empty(clouds, dtype=np.float32)
+        for p, graph_pair in enumerate(batch):
+            for side, path in enumerate(graph_pair):                  # _fit_node_count, graph 1 then graph 2
+                nodes, centers, _ = store._load(path)
+                have = len(nodes)
+                if have > want:
+                    keep = np.random.choice(have, want, replace=False)
+                    keep.sort()
+                    nodes, centers, have = nodes[keep], centers[keep], want
+                xyz[2 * p + side, :have] = centers
+                labels[2 * p + side, :have] = nodes
+            flipped[2 * p] = flipped[2 * p + 1] = random.random() > 0.5      # sg_net.py:288
+            for i in (2 * p, 2 * p + 1):                                      # augment_data(xyz_1), augment_data(xyz_2)
+                u_angle[i] = sample()
+                jitter[i] = normal(want * 3)
+                u_scale[i] = sample()
+                perturb[i] = normal(3)
+                u_shift[i] = sample(3)
+            d = store.distance(graph_pair[0], graph_pair[1])
+            if d <= self.args.p_thresh:
+                targets[2 * p] = targets[2 * p + 1] = 1.0
+            elif d >= 20:
+                targets[2 * p] = targets[2 * p + 1] = 0.0
+            else:
+                print("distance error: ", d)
+                exit(-1)
+        xyz[flipped, :, 0] = -xyz[flipped, :, 0]                              # pads become -0.0 exactly as in the reference
+        angle = u_angle * 2 * np.pi
+        c, s = np.cos(angle), np.sin(angle)
+        rot = np.zeros((clouds, 3, 3))
+        rot[:, 0, 0], rot[:, 0, 1], rot[:, 1, 0], rot[:, 1, 1], rot[:, 2, 2] = c, -s, s, c, 1.0
+        rotated = np.matmul(xyz, rot).astype(np.float32)
+        cloud = np.clip(0.01 * jitter.reshape(clouds, want, 3), -0.05, 0.05)
+        cloud += rotated
+        cloud *= (0.8 + (1.25 - 0.8) * u_scale)[:, None, None]
+        ang = np.clip(0.015 * perturb, -0.045, 0.045)
+        ca, sa = np.cos(ang), np.sin(ang)
+        rx, ry, rz = np.zeros((clouds, 3, 3)), np.zeros((clouds, 3, 3)), np.zeros((clouds, 3, 3))
+        rx[:, 0, 0], rx[:, 1, 1], rx[:, 1, 2], rx[:, 2, 1], rx[:, 2, 2] = 1.0, ca[:, 0], -sa[:, 0], sa[:, 0], ca[:, 0]
+        ry[:, 0, 0], ry[:, 0, 2], ry[:, 1, 1], ry[:, 2, 0], ry[:, 2, 2] = ca[:, 1], sa[:, 1], 1.0, -sa[:, 1], ca[:, 1]
+        rz[:, 0, 0], rz[:, 0, 1], rz[:, 1, 0], rz[:, 1, 1], rz[:, 2, 2] = ca[:, 2], -sa[:, 2], sa[:, 2], ca[:, 2], 1.0
+        out = np.matmul(cloud, np.matmul(rz, np.matmul(ry, rx))).astype(np.float32)
+        out += (-0.3 + (0.3 - -0.3) * u_shift)[:, None, :]
+        feats = np.zeros((clouds, 3 + self.number_of_labels, want), dtype=np.float32)
+        feats[:, :3, :] = out.transpose(0, 2, 1)
+        which, node = np.nonzero(labels >= 0)
+        feats[which, 3 + labels[which, node], node] = 1.0
+        return feats, targets
+
     def pc_normalize(self, pc):
         pc = pc - np.mean(pc, axis=0)
         return pc / np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
@@ -548,30 +616,26 @@ class SGTrainer(object):
             done = self._process_batch_on_device(batch)
             if done is not None:
                 return done
-        f1, targets = [], []
-        if getattr(self, "_json_cache", None) is None:
-            self._json_cache = {}
-        for graph_pair in batch:
-            if training:
-                a, b, t = self._training_features(graph_pair)
-                f1 += [a, b]
-                targets += [t, t]
-                continue
-            data = self.transfer_to_torch(process_pair(graph_pair, self._json_cache), training)
-            f1 += [data["features_1"], data["features_2"]]
-            targets += [data["target"], data["target"]]
         if training:
             # the batch holds every listed pair in both orders (features_2[p] == features_1[p ^ 1] by construction), so
             # both sides are the same BatchNorm batch: one EdgeConv pass per graph serves both (mirrored step) and
             # features_2 is never materialised
+            f1, targets = self._training_batch(batch)
             eng = self._device_trainer()
             dev = eng.device
-            feats = torch.from_numpy(np.asarray(f1, dtype=np.float32))
-            target = torch.from_numpy(np.asarray(targets, dtype=np.float32))
+            feats = torch.from_numpy(f1)
+            target = torch.from_numpy(targets)
             loss, prediction = eng.step(feats.to(dev, non_blocking=True), None, target.to(dev, non_blocking=True),
                                         int(self.args.K), apply=True, mirrored=True)
             self._unsynced_steps += 1
             return (loss.item(), prediction.cpu().numpy().reshape(-1), target.numpy().reshape(-1))
+        f1, targets = [], []
+        if getattr(self, "_json_cache", None) is None:
+            self._json_cache = {}
+        for graph_pair in batch:
+            data = self.transfer_to_torch(process_pair(graph_pair, self._json_cache), training)
+            f1 += [data["features_1"], data["features_2"]]
+            targets += [data["target"], data["target"]]
         f2 = [f1[i ^ 1] for i in range(len(f1))]
         data = self._stack(f1, f2, targets)
         self.sync_model_from_device()

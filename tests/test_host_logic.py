@@ -214,3 +214,14 @@ def test_fast_training_features_are_bit_identical_to_the_reference_shaped_path(t
             for w, (a, b, t) in zip(want, got):
                 assert a.dtype == w["features_1"].dtype == np.float64 and a.shape == (15, node_num)
                 assert np.array_equal(a, w["features_1"]) and np.array_equal(b, w["features_2"]) and t == w["target"]
+            # the batched form process_batch uses: draws in the same order, arithmetic over the whole batch at once
+            np.random.seed(seed); random.seed(seed)
+            feats, targets = trainer._training_batch(pairs)
+            assert (np.random.rand(), random.random()) == tail_w
+            assert feats.dtype == np.float32 and feats.shape == (2 * len(pairs), 15, node_num) and targets.dtype == np.float32
+            for i, w in enumerate(want):
+                for side, key in enumerate(("features_1", "features_2")):
+                    ref = w[key].astype(np.float32)
+                    assert np.array_equal(feats[2 * i + side], ref)
+                    assert np.array_equal(np.signbit(feats[2 * i + side]), np.signbit(ref))     # flipped pads are -0.0
+                assert targets[2 * i] == targets[2 * i + 1] == w["target"]

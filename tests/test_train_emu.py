@@ -160,7 +160,8 @@ def test_emulated_train_forward_in_cpu_tie_mode_matches_oracle_on_dense_graphs(e
     a, b = synth.make_pair_batch(3, 32, 10, seed=8, dense=True)
     f1 = torch.stack([a, b], dim=1).reshape(6, 15, 32).contiguous()
     f2 = torch.stack([b, a], dim=1).reshape(6, 15, 32).contiguous()
-    want = ort.forward_train(kitti_state, f1, f2, 10)[0].detach()
+    state = {name: value.clone() for name, value in kitti_state.items()}    # forward_train updates BN buffers in place
+    want = ort.forward_train(state, f1, f2, 10)[0].detach()
     eng = TrainEngine(lib=emu_lib)
     eng.set_state(kitti_state)
     eng.set_knn_ties("cpu")
