@@ -262,9 +262,11 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     a.order = nullptr;
     a.work_ctr = nullptr;
     // persistent launches (more graphs than resident CTAs): pop the graphs heaviest-first (LPT) so that the tail of the
-    // launch is short; results are unchanged.  Not worth its ~3 us pre-pass while every graph has its own resident CTA
-    // (the hardware's CTA->SM placement cannot be steered, profiles/r01_variants_timeline.txt), and skipped when the
-    // graphs sit in pinned host memory (the pre-pass would pull them over PCIe a second time).
+    // launch is short; results are unchanged.  Not worth its pre-pass while every graph has its own resident CTA: the
+    // hardware's CTA->SM placement cannot be steered (profiles/r01_variants_timeline.txt), and claiming graphs by the SM a
+    // CTA lands on so that heavy graphs share an SM with light ones balances the row sums but not the launch time
+    // (profiles/experiments/r02_embed_sm_pairing.txt).  Skipped when the graphs sit in pinned host memory (the pre-pass
+    // would pull them over PCIe a second time).
     if (ctx->balance && !a.compact && a.G > capacity && is_device_memory(a.g0)) {
         int rc = ensure(ctx->d_order, ctx->order_cap, static_cast<size_t>(2) * a.G);
         if (rc) return rc;
@@ -600,17 +602,10 @@ int sgpr_topk_cpu_rule_host(const float* rows, int num_rows, int n, int k, int d
 }
 
 #ifdef SGPR_TIMELINE
-// debug builds only (not declared in the public header): copy CTA 0's clock stamps, [8 warps][128 slots]
-int sgpr_debug_timeline(long long* out) {
-    return cudaMemcpyFromSymbol(out, g_timeline, sizeof(long long) * kWarps * 128) == cudaSuccess ? 0 : -2;
-}
-int sgpr_debug_ctas(int* smid1024, long long* t2048) {
-    if (cudaMemcpyFromSymbol(smid1024, g_smid, sizeof(int) * 1024) != cudaSuccess) return -2;
-    return cudaMemcpyFromSymbol(t2048, g_cta_t, sizeof(long long) * 2048) == cudaSuccess ? 0 : -2;
-}
-int sgpr_debug_cta_graphs(int* g1024) {
-    return cudaMemcpyFromSymbol(g1024, g_cta_g, sizeof(int) * 1024) == cudaSuccess ? 0 : -2;
-}
+// debug builds only (not declared in the public header): clock stamps of the N <= 64 fused kernel (embed_inst.cu)
+int sgpr_debug_timeline(long long* out) { return sgpr::debug_read_timeline(out); }
+int sgpr_debug_ctas(int* smid1024, long long* t2048) { return sgpr::debug_read_ctas(smid1024, t2048, nullptr); }
+int sgpr_debug_cta_graphs(int* g1024) { return sgpr::debug_read_ctas(nullptr, nullptr, g1024); }
 #endif
 
 size_t sgpr_packed_size(void) { return make_offsets().total; }

@@ -64,6 +64,19 @@ int embed_tc_smem(int ks) { return make_tc_layout(ks).total; }
 void embed_tc_launch(int grid, cudaStream_t st, const EmbedArgs& a, const PackedWeights& pw, const HeadParams& hp) {
     SGPR_LAUNCH(sgpr_embed_tc_kernel, grid, kThreads, make_tc_layout(a.KS).total, st, a, pw, hp);
 }
+
+#ifdef SGPR_TIMELINE
+// debug builds: the stamp arrays are per translation unit; the N <= 64 kernels of THIS object are the ones profiled
+int debug_read_timeline(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_timeline, sizeof(long long) * kWarps * 128) == cudaSuccess ? 0 : -2;
+}
+int debug_read_ctas(int* smid1024, long long* t2048, int* g1024) {
+    if (smid1024 && cudaMemcpyFromSymbol(smid1024, g_smid, sizeof(int) * 1024) != cudaSuccess) return -2;
+    if (t2048 && cudaMemcpyFromSymbol(t2048, g_cta_t, sizeof(long long) * 2048) != cudaSuccess) return -2;
+    if (g1024 && cudaMemcpyFromSymbol(g1024, g_cta_g, sizeof(int) * 1024) != cudaSuccess) return -2;
+    return 0;
+}
+#endif
 #endif
 
 }  // namespace sgpr

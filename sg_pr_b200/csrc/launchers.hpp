@@ -28,6 +28,12 @@ cudaError_t embed_tc_optin(int optin_bytes);
 int embed_tc_smem(int ks);
 void embed_tc_launch(int grid, cudaStream_t st, const EmbedArgs& a, const PackedWeights& pw, const HeadParams& hp);
 
+#ifdef SGPR_TIMELINE
+// debug builds (embed_inst.cu, NPL = 2 object): clock stamps written by the N <= 64 fused kernel
+int debug_read_timeline(long long* out);
+int debug_read_ctas(int* smid1024, long long* t2048, int* g1024);
+#endif
+
 // scoremat_umma.cu: the tcgen05 score-matrix kernel (not part of the tests/emu build: inline tcgen05 PTX)
 cudaError_t score_matrix_umma_optin();
 size_t score_matrix_umma_scratch_floats(int R, int M);     // operand planes + V-block terms

@@ -1,5 +1,6 @@
 """CTA -> SM placement, per-CTA wall time and graph weight of the fused kernel (needs a -DSGPR_TIMELINE build:
-SGPR_B200_LIB=tools/variants/lib_tl.so).  Run with SGPR_NO_PLACED=1 for the hardware's own placement."""
+SGPR_EXTRA_NVCC_FLAGS=-DSGPR_TIMELINE SGPR_BUILD_TAG=tl python -m sg_pr_b200.build, then
+SGPR_B200_LIB=tools/variants/libsgpr_b200_tl.so python tools/cta_map.py 128)."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,7 +27,7 @@ assert sorted(graph.tolist()) == list(range(G)), "every graph exactly once"
 t0 = t[:, 0].min()
 dur = (t[:, 1] - t[:, 0]) / 1e3
 end = (t[:, 1] - t0) / 1e3
-print("placed mode:", os.environ.get("SGPR_NO_PLACED", "0") != "1")
+print("smid range", int(smid.min()), int(smid.max()), "distinct", len(set(smid.tolist())))
 print("kernel span us: %.1f   CTA start spread us: %.1f" % ((t[:, 1].max() - t0) / 1e3, (t[:, 0].max() - t0) / 1e3))
 per = defaultdict(list)
 for b in range(G): per[int(smid[b])].append(b)

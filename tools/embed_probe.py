@@ -12,7 +12,7 @@ sd = orc.load_state_npz(os.path.join(os.path.dirname(__file__), "..", "tests", "
 eng = Engine(0); eng.set_weights(sd)
 out = {"lib": os.environ.get("SGPR_B200_LIB", "default")}
 ref = None
-for B in (16, 64, 74, 128, 148, 256, 512):
+for B in (16, 64, 74, 80, 96, 112, 128, 148, 256, 512):
     sets = max(2, min(64, 140_000_000 // (2 * B * 15 * 64 * 4)))
     data = [tuple(t.cuda() for t in synth.make_pair_batch(B, 64, 20, seed=s)) for s in range(sets)]
     for i in range(10): eng.forward_pairs(*data[i % sets], 20)
