@@ -258,6 +258,39 @@ def measure_sweep(eng, dev, batch=512, iters=30, warmup=5):
     return {"workload": "node-count sweep, batch 512 (BASELINE configs[4]); inputs in HBM (L2-resident across iterations)", "rows": rows}
 
 
+def measure_small_batches(eng, model, dev, iters=200, warmup=10):
+    """Latency of small calls (eval_pair.py is a batch of ONE pair): the fused kernel with inputs in HBM at B = 1 / 16 / 37
+    pairs (2B graphs <= 74: every work unit of a branch-split launch has an SM to itself) and one pair end to end through
+    SG.forward(data) with pinned CPU tensors + prediction.cpu()."""
+    out = {"workload": "pair batches of 1 / 16 / 37 (N = 64, k = 20), CUDA events over %d launches, rotating inputs" % iters}
+    for b in (1, 16, 37):
+        sets = [tuple(t.to(dev) for t in synth.make_pair_batch(b, NODES, K_NN, seed=400 + s)) for s in range(32)]
+        for i in range(warmup):
+            eng.forward_pairs(*sets[i % 32], K_NN, want_att=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            eng.forward_pairs(*sets[i % 32], K_NN, want_att=True)
+        e1.record()
+        torch.cuda.synchronize()
+        out["B%d_kernel_us" % b] = e0.elapsed_time(e1) / iters * 1e3
+    pins = [tuple(t.pin_memory() for t in synth.make_pair_batch(1, NODES, K_NN, seed=500 + s)) for s in range(32)]
+    def one(i):
+        with torch.no_grad():
+            prediction, _, _ = model({"features_1": pins[i % 32][0], "features_2": pins[i % 32][1]})
+        return prediction.cpu()
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(iters):
+        one(i)
+    torch.cuda.synchronize()
+    out["one_pair_e2e_us"] = (time.perf_counter() - t0) / iters * 1e6
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -414,6 +447,7 @@ def main():
         if rank == 0:
             extras["train"] = measure_train(state, dev)
             extras["sweep"] = measure_sweep(eng, dev)
+            extras["small_batch"] = measure_small_batches(eng, model, dev)
         barrier()
 
     if rank == 0:

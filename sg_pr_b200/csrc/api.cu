@@ -91,6 +91,10 @@ struct sgpr_ctx {
     cudaStream_t stream = nullptr;                      // host-path stream
     long long launches = 0;
     int* d_order = nullptr;      size_t order_cap = 0;   // rows[G] | order[G]
+    float* d_halves = nullptr;   size_t halves_cap = 0;  // branch-split launches: [G][2][N][32]
+    int* d_gctr = nullptr;       size_t gctr_cap = 0;    //   and their per-graph arrival counters (zero between launches)
+    int split_max = -1;          // largest G launched branch-split (-1: two thirds of the resident CTA slots)
+    int split = 1;               // branch-split launches while the graphs fit the resident CTAs; SGPR_NO_SPLIT=1 disables it
     int* d_ctrs = nullptr;                               // {done counter, work counter}
     int zerocopy = 1;            // host entry point: read pinned buffers in place; SGPR_NO_ZEROCOPY=1 forces staged copies
     int balance = 1;             // order graphs by active rows before the fused kernel; SGPR_NO_BALANCE=1 disables it
@@ -133,6 +137,8 @@ int sgpr_create(sgpr_ctx** out, int device) {
     if (const char* nd = getenv("SGPR_NO_DEDUP")) ctx->dedup = (nd[0] == '1') ? 0 : 1;
     if (const char* nz = getenv("SGPR_NO_ZEROCOPY")) ctx->zerocopy = (nz[0] == '1') ? 0 : 1;
     if (const char* nb = getenv("SGPR_NO_BALANCE")) ctx->balance = (nb[0] == '1') ? 0 : 1;
+    if (const char* ns = getenv("SGPR_NO_SPLIT")) ctx->split = (ns[0] == '1') ? 0 : 1;
+    if (const char* sm = getenv("SGPR_SPLIT_MAX")) ctx->split_max = atoi(sm);
     if (const char* v2 = getenv("SGPR_SCOREMAT_V2")) ctx->scoremat_version = (v2[0] == '1') ? 2 : 1;
     if (const char* et = getenv("SGPR_EMBED_TC")) ctx->embed_tc = (et[0] == '1') ? 1 : 0;
     if (const char* sf = getenv("SGPR_SCOREMAT_FFMA")) ctx->scoremat_ffma = (sf[0] == '1') ? 1 : 0;
@@ -172,6 +178,8 @@ int sgpr_destroy(sgpr_ctx* ctx) {
     cudaFree(ctx->d_proj);
     cudaFree(ctx->d_blk);
     cudaFree(ctx->d_order);
+    cudaFree(ctx->d_halves);
+    cudaFree(ctx->d_gctr);
     cudaFree(ctx->d_ctrs);
     cudaFree(ctx->d_fc1_planes);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -261,6 +269,28 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     if (grid < 1) return SGPR_OK;
     a.order = nullptr;
     a.work_ctr = nullptr;
+    a.split = 0;
+    a.halves = nullptr;
+    a.gctr = nullptr;
+    // Small launches run one BRANCH of a graph per work unit: the xyz and the semantic EdgeConv stacks are independent
+    // until conv_end, so a graph's critical path halves (embed_kernel.cuh, EmbedArgs::split).  It pays while the 2G units
+    // stay within ~4/3 of the resident CTA slots (B200, N = 64: 37 vs 57 us at 32 graphs, 79 vs 86 at 192, 94 vs 86 at
+    // 224 — profiles/experiments/r02_embed_branch_split.txt).  Bit-identical; the debug taps keep the whole-graph form.
+    const int split_max = ctx->split_max >= 0 ? ctx->split_max : (2 * capacity) / 3;
+    if (ctx->split && a.G <= split_max && !a.trace_knn && !a.trace_layers && !(ctx->embed_tc && npl == 2)) {
+        int rc = ensure(ctx->d_halves, ctx->halves_cap, static_cast<size_t>(a.G) * 2 * N * kF3);
+        if (rc) return rc;
+        if (static_cast<size_t>(a.G) > ctx->gctr_cap) {
+            rc = ensure(ctx->d_gctr, ctx->gctr_cap, static_cast<size_t>(a.G));
+            if (rc) return rc;
+            cudaError_t e = cudaMemsetAsync(ctx->d_gctr, 0, ctx->gctr_cap * sizeof(int), st);
+            if (e != cudaSuccess) return fail(SGPR_E_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+        }
+        a.split = 1;
+        a.halves = ctx->d_halves;
+        a.gctr = ctx->d_gctr;
+        grid = 2 * a.G < capacity ? 2 * a.G : capacity;
+    }
     // persistent launches (more graphs than resident CTAs): pop the graphs heaviest-first (LPT) so that the tail of the
     // launch is short; results are unchanged.  Not worth its pre-pass while every graph has its own resident CTA: the
     // hardware's CTA->SM placement cannot be steered (profiles/r01_variants_timeline.txt), and claiming graphs by the SM a

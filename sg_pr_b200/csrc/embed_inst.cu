@@ -19,8 +19,10 @@ cudaError_t embed_optin<SGPR_INST_NPL>(int optin_bytes) {
     return cudaSuccess;
 #else
     // the dynamic limit excludes each kernel's static __shared__ bytes
-    const void* fns[2] = {reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 0>),
-                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 1>)};
+    const void* fns[4] = {reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 0, 0>),
+                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 1, 0>),
+                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 0, 1>),
+                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 1, 1>)};
     for (const void* fn : fns) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, fn);
@@ -35,13 +37,9 @@ cudaError_t embed_optin<SGPR_INST_NPL>(int optin_bytes) {
 template <>
 void embed_launch<SGPR_INST_NPL>(int ties, int grid, int smem, cudaStream_t st, const EmbedArgs& a, const PackedWeights& pw,
                                  const HeadParams& hp) {
-    if (ties == SGPR_TIES_CPU) {
-        const auto kern = &sgpr_embed_kernel<SGPR_INST_NPL, 1>;
-        SGPR_LAUNCH(kern, grid, kThreads, smem, st, a, pw, hp);
-    } else {
-        const auto kern = &sgpr_embed_kernel<SGPR_INST_NPL, 0>;
-        SGPR_LAUNCH(kern, grid, kThreads, smem, st, a, pw, hp);
-    }
+    const auto kern = (ties == SGPR_TIES_CPU) ? (a.split ? &sgpr_embed_kernel<SGPR_INST_NPL, 1, 1> : &sgpr_embed_kernel<SGPR_INST_NPL, 1, 0>)
+                                              : (a.split ? &sgpr_embed_kernel<SGPR_INST_NPL, 0, 1> : &sgpr_embed_kernel<SGPR_INST_NPL, 0, 0>);
+    SGPR_LAUNCH(kern, grid, kThreads, smem, st, a, pw, hp);
 }
 
 #if SGPR_INST_NPL == 2

@@ -80,6 +80,11 @@ struct EmbedArgs {
     float* trace_layers;    // [G][6][N][64] or null
     const int* order;       // [G] slot -> graph (heavy graphs placed so that co-resident CTAs balance), or null = identity
     int* work_ctr;          // non-null: CTAs pop slots from this counter (persistent launches, heaviest graph first)
+    int split;              // 1: a work unit is one BRANCH of a graph (unit u = 2*slot + branch: xyz layers 1-3 | semantic layers
+                            //    1-3, independent until conv_end, sg_net.py:84-104); the unit that finishes second merges.  Halves
+                            //    the critical path of a graph when the launch has fewer graphs than CTA slots.  Same results.
+    float* halves;          // split: [G][2][N][32] branch outputs handed to the merging unit
+    int* gctr;              // split: [G] arrival counters, zero on entry, zero on exit
 };
 
 struct SmemLayout {
@@ -947,7 +952,9 @@ __device__ __forceinline__ void conv_end_dispatch(const float* sCat, const float
 #ifndef SGPR_MINBLOCKS_SMALL
 #define SGPR_MINBLOCKS_SMALL 2
 #endif
-template <int NPL, int TIES = 0>       // TIES: 0 = lowest index first (ATen CUDA topk), 1 = ATen CPU nth_element order
+// TIES: 0 = lowest index first (ATen CUDA topk), 1 = ATen CPU nth_element order.  SPLIT: 1 = one branch of a graph per
+// work unit (EmbedArgs::split) — its own instantiation so that the whole-graph kernel's register allocation is untouched.
+template <int NPL, int TIES = 0, int SPLIT = 0>
 __global__ void __launch_bounds__(kThreads, (NPL <= 2) ? SGPR_MINBLOCKS_SMALL : 1)
 sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) {
     constexpr int NMAX = 32 * NPL;
@@ -999,7 +1006,9 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             slot = sSlot;
             __syncthreads();
         }
-        if (slot >= A.G) break;
+        if (slot >= (SPLIT ? 2 * A.G : A.G)) break;
+        const int br = SPLIT ? (slot & 1) : -1;         // -1: the whole graph; 0: xyz branch; 1: semantic branch
+        if (SPLIT) slot >>= 1;
         const int g = A.order ? __ldg(A.order + slot) : slot;
         const float* gin = reinterpret_cast<const float*>(
             reinterpret_cast<const unsigned char*>((A.pairs && (g & 1)) ? A.g1 : A.g0) + static_cast<size_t>(A.pairs ? (g >> 1) : g) * inBytes);
@@ -1011,8 +1020,8 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         // ---- stage the input block and the first GEMM's weights (TMA bulk copies, mbarrier completion) ----
         if (tid == 0) {
             if (bulk_ok) { mbar_expect_tx(barIn, inBytes); bulk_g2s(sIn, gin, inBytes, barIn); }
-            mbar_expect_tx(barW, 64 * 128 * 4);
-            bulk_g2s(sW, W.w_s2, 64 * 128 * 4, barW);
+            if (br == 1) { mbar_expect_tx(barW, 12 * 128 * 4); bulk_g2s(sW, W.w_f1, 12 * 128 * 4, barW); }
+            else         { mbar_expect_tx(barW, 64 * 128 * 4); bulk_g2s(sW, W.w_s2, 64 * 128 * 4, barW); }
         }
         if (bulk_ok) { mbar_wait(barIn, phIn); phIn ^= 1; }
         else { for (int e = tid; e < static_cast<int>(inBytes / 4); e += kThreads) sIn[e] = __ldg(gin + e); __syncthreads(); }
@@ -1058,13 +1067,21 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
         const int w0 = min(R, warp * rpw), w1 = min(R, w0 + rpw);
 
         // ================= the six EdgeConv layers: xyz 1,2,3 then sem 1,2,3 (sg_net.py:84-102) =================
+        // the semantic branch's input: rows [n][0..11] from input rows 3..14 (sg_net.py:82,94), own rows
+        auto stage_semantic = [&]() {
+            for (int i = w0; i < w1; ++i)
+                if (lane < 16) sX[i * XS + lane] = (lane < kLabels) ? sIn[(3 + lane) * N + i] : 0.0f;
+            __syncwarp();
+            norms_rows(sX, sXX, 3, w0, w1, lane);
+        };
+        if (br == 1) { stage_semantic(); __syncthreads(); }
 #pragma unroll 1
-        for (int l = 0; l < 6; ++l) {
+        for (int l = (br == 1) ? 3 : 0; l < ((br == 0) ? 3 : 6); ++l) {
             LayerDesc D;
             switch (l) {
                 case 0:  D = LayerDesc{nullptr, nullptr, 0, 1, 64}; break;
                 case 1:  D = LayerDesc{W.ab_s2, W.w_s3, 64 * 64 * 4, 16, 64}; break;
-                case 2:  D = LayerDesc{W.ab_s3, W.w_f1, 12 * 128 * 4, 16, 32}; break;
+                case 2:  D = LayerDesc{W.ab_s3, (br == 0) ? nullptr : W.w_f1, 12 * 128 * 4, 16, 32}; break;
                 case 3:  D = LayerDesc{W.ab_f1, W.w_f2, 64 * 128 * 4, 3, 64}; break;
                 case 4:  D = LayerDesc{W.ab_f2, W.w_f3, (64 * 64 + 64 * 32) * 4, 16, 64}; break;   // w_f3 + w_end (adjacent)
                 default: D = LayerDesc{W.ab_f3, nullptr, 0, 16, 32}; break;
@@ -1088,7 +1105,13 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             } else {
                 __syncthreads();                               // barrier B: every A|B row is in place, sW is consumed
                 SGPR_TL(8 + l * 8 + 4);
-                if (tid == 0 && D.next_w) { mbar_expect_tx(barW, D.next_bytes); bulk_g2s(sW, D.next_w, D.next_bytes, barW); }
+                if (tid == 0 && D.next_w) {
+                    // an xyz-branch unit may be the one that merges: conv_end's matrix rides along with layer 3's
+                    const int extra = (br == 0 && l == 1) ? 64 * 32 * 4 : 0;
+                    mbar_expect_tx(barW, D.next_bytes + extra);
+                    bulk_g2s(sW, D.next_w, D.next_bytes, barW);
+                    if (extra) bulk_g2s(sW + 64 * 64, W.w_end, extra, barW);
+                }
                 // ---- back: gather-max for own rows ----
                 if (D.cout == 64) {
                     gather_rows<64>(sY, sIdx, sCnt, KS, D.ab, sX, tr, w0, w1, lane);
@@ -1096,12 +1119,9 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
                     norms_rows(sX, sXX, 16, w0, w1, lane);
                 } else {
                     gather_rows<32>(sY, sIdx, sCnt, KS, D.ab, (l == 2) ? sCat : sCat + 32, tr, w0, w1, lane);
-                    if (l == 2) {   // stage the semantic branch input: rows [n][0..11] from input rows 3..14 (sg_net.py:82,94)
-                        for (int i = w0; i < w1; ++i)
-                            if (lane < 16) sX[i * XS + lane] = (lane < kLabels) ? sIn[(3 + lane) * N + i] : 0.0f;
-                        __syncwarp();
-                        norms_rows(sX, sXX, 3, w0, w1, lane);
-                    } else {        // l == 5: conv_end on own rows (sg_net.py:104-109): cat(xyz3, sem3) [.,64] -> [.,32]
+                    if (l == 2) {
+                        if (br < 0) stage_semantic();
+                    } else if (br < 0) {   // l == 5: conv_end on own rows (sg_net.py:104-109): cat(xyz3, sem3) [.,64] -> [.,32]
                         __syncwarp();
                         for (int r0 = w0; r0 < w1; r0 += 8)
                             conv_end_dispatch(sCat, sW + 64 * 64, sX, W.ab_end, r0, min(8, w1 - r0), lane);
@@ -1117,6 +1137,23 @@ sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) 
             }
         }
 
+        if constexpr (SPLIT != 0) {
+            // ---- branch unit: hand the 32 channels over; whichever unit of the graph arrives second merges ----
+            float* mine = A.halves + (static_cast<size_t>(g) * 2 + br) * N * kF3;
+            for (int e = tid; e < R * kF3; e += kThreads) mine[e] = sCat[(e >> 5) * XS + br * 32 + (e & 31)];
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) sFlag = atomicAdd(A.gctr + g, 1);
+            __syncthreads();
+            if (sFlag == 0) { __syncthreads(); continue; }
+            __threadfence();
+            const float* other = A.halves + (static_cast<size_t>(g) * 2 + (br ^ 1)) * N * kF3;
+            for (int e = tid; e < R * kF3; e += kThreads) sCat[(e >> 5) * XS + (br ^ 1) * 32 + (e & 31)] = __ldcg(other + e);
+            if (tid == 0) A.gctr[g] = 0;
+            __syncthreads();
+            for (int r0 = w0; r0 < w1; r0 += 8) conv_end_dispatch(sCat, sW + 64 * 64, sX, W.ab_end, r0, min(8, w1 - r0), lane);
+            __syncthreads();
+        }
         SGPR_TL(58);
         finish_graph(A, W, H, sX, sRed, sY, &sFlag, g, N, R, tid, warp, lane);
         __syncthreads();

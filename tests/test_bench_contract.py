@@ -55,3 +55,6 @@ def test_our_arm_line_carries_every_key():
     assert set(scan["phases_ms"]) >= {"embed_row_block", "allgather_pooled", "score_row_block_tcgen05"}
     assert line["train"]["launches_per_step"] == 10 and line["train"]["ms_per_step"] > 0
     assert {(r["node_num"], r["k"]) for r in line["sweep"]["rows"]} == {(16, 10), (32, 10), (32, 20), (64, 10), (64, 20), (128, 10), (128, 20)}
+    small = line["small_batch"]
+    assert 0 < small["B1_kernel_us"] <= small["B37_kernel_us"] * 1.1 and small["B37_kernel_us"] < line["ms_per_step"] * 1e3
+    assert small["one_pair_e2e_us"] > small["B1_kernel_us"]

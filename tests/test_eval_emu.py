@@ -131,3 +131,35 @@ def test_emulated_tensor_core_variant_of_the_fused_kernel(kitti_state, monkeypat
     assert float((e["emb"] - want["emb_1"]).abs().max()) <= 2e-5
     tc.close()
     ff.close()
+
+
+def test_emulated_branch_split_launch_is_bit_identical(kitti_state, monkeypatch):
+    """EmbedArgs::split (small launches: one EdgeConv branch of a graph per work unit, the second arriver merges) against
+    whole-graph units (SGPR_NO_SPLIT=1): every output bit for bit, pairs / embed / compact records, both tie rules.  The
+    emulated device has 8 resident CTA slots, so G <= 5 graphs launch split and larger batches do not."""
+    from sg_pr_b200.engine import compact_graphs
+    from tests.emu import build_emu
+    lib = _lib.bind(C.CDLL(build_emu.build()), _lib.SYMBOLS)
+    split = Engine(lib=lib)
+    monkeypatch.setenv("SGPR_NO_SPLIT", "1")
+    whole = Engine(lib=lib)
+    monkeypatch.delenv("SGPR_NO_SPLIT")
+    for e in (split, whole):
+        e.set_weights(kitti_state)
+    for b, n, k in ((1, 40, 10), (2, 64, 20), (2, 100, 10)):
+        f1, f2 = synth.make_pair_batch(b, n, k, seed=20 + b)
+        got, ref = split.forward_pairs(f1, f2, k), whole.forward_pairs(f1, f2, k)
+        assert all(torch.equal(x, y) for x, y in zip(got, ref))
+        want = orc.forward_pairs(f1, f2, k, kitti_state)
+        assert float((got[0] - want["score"]).abs().max()) <= 1e-5
+        again = split.forward_pairs_compact(compact_graphs(f1), compact_graphs(f2), n, k)
+        assert torch.equal(again[0], ref[0])
+    g = synth.make_graphs(5, 64, 20, seed=3)
+    a, b = split.embed(g, 20, want_att=True, want_emb=True), whole.embed(g, 20, want_att=True, want_emb=True)
+    assert all(torch.equal(a[key], b[key]) for key in ("pooled", "att", "emb"))
+    for e in (split, whole):
+        e.set_knn_ties("cpu")
+    f1, f2 = synth.make_pair_batch(2, 32, 10, seed=9, dense=True)
+    assert torch.equal(split.forward_pairs(f1, f2, 10)[0], whole.forward_pairs(f1, f2, 10)[0])
+    split.close()
+    whole.close()

@@ -308,6 +308,35 @@ def test_tensor_core_variant_of_the_fused_kernel(kitti_state, golden_dir, monkey
     tc.close()
 
 
+def test_branch_split_launch_is_bit_identical(kitti_state, monkeypatch):
+    """Small launches run one EdgeConv branch of a graph per work unit (EmbedArgs::split; api.cu splits while G <= 2/3 of the
+    resident CTA slots, 197 on a B200).  Against whole-graph units (SGPR_NO_SPLIT=1): every output bit for bit — across the
+    threshold, for the three row-tiling widths, compact records, the embed entry and the CPU tie rule."""
+    from sg_pr_b200.engine import Engine, compact_graphs
+    split = Engine(0)
+    monkeypatch.setenv("SGPR_NO_SPLIT", "1")
+    whole = Engine(0)
+    monkeypatch.delenv("SGPR_NO_SPLIT")
+    for e in (split, whole):
+        e.set_weights(kitti_state)
+    for b, n, k in ((1, 64, 20), (16, 64, 20), (37, 64, 20), (64, 64, 20), (98, 64, 20), (99, 64, 20), (24, 32, 10), (12, 128, 20)):
+        f1, f2 = (_cuda(t) for t in synth.make_pair_batch(b, n, k, seed=300 + b))
+        for _ in range(2):                                   # twice: the arrival counters must be back at zero
+            got, ref = split.forward_pairs(f1, f2, k), whole.forward_pairs(f1, f2, k)
+            assert all(torch.equal(x, y) for x, y in zip(got, ref)), (b, n, k)
+        again = split.forward_pairs_compact(_cuda(compact_graphs(f1.cpu())), _cuda(compact_graphs(f2.cpu())), n, k)
+        assert torch.equal(again[0], ref[0])
+    g = _cuda(synth.make_graphs(150, 64, 20, seed=5))
+    a, b = split.embed(g, 20, want_att=True, want_emb=True), whole.embed(g, 20, want_att=True, want_emb=True)
+    assert all(torch.equal(a[key], b[key]) for key in ("pooled", "att", "emb"))
+    for e in (split, whole):
+        e.set_knn_ties("cpu")
+    f1, f2 = (_cuda(t) for t in synth.make_pair_batch(8, 64, 20, seed=9, dense=True))
+    assert torch.equal(split.forward_pairs(f1, f2, 20)[0], whole.forward_pairs(f1, f2, 20)[0])
+    split.close()
+    whole.close()
+
+
 def test_host_entry_point_matches_device(eng):
     f1, f2 = synth.make_pair_batch(64, 64, 20, seed=21)
     d_score, d_a1, d_a2 = eng.forward_pairs(_cuda(f1), _cuda(f2), 20)
