@@ -12,4 +12,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:sgpr
 timeout 300 python tools/embed_probe.py > gpurun_out/embed_probe.json 2>&1
 SGPR_SCOREMAT_V2=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:umma_kernel -s 1 -c 1 -f -o gpurun_out/prof_scoremat python tools/scoremat_profile.py 3 > gpurun_out/ncu_scoremat.log 2>&1
 timeout 120 python tools/scoremat_check.py > gpurun_out/scoremat_check.jsonl 2>&1
-tail -4 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; head -c 1200 gpurun_out/bench.json; echo; tail -2 gpurun_out/bench.err; head -c 600 gpurun_out/bench_reference.json; echo; tail -3 gpurun_out/sanitizer.log; cat gpurun_out/embed_probe.json
+timeout 300 python tools/train_e2e_bench.py > gpurun_out/train_e2e.jsonl 2> gpurun_out/train_e2e.err
+tail -4 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; head -c 1200 gpurun_out/bench.json; echo; tail -2 gpurun_out/bench.err; head -c 600 gpurun_out/bench_reference.json; echo; tail -3 gpurun_out/sanitizer.log; cat gpurun_out/embed_probe.json; cat gpurun_out/train_e2e.jsonl
