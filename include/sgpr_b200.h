@@ -127,6 +127,12 @@ int sgpr_forward_pairs_host(sgpr_ctx* ctx, const float* f1_host, const float* f2
  * expanded input.  4.6x fewer input bytes per pair (1,664 instead of 7,680 at N = 64).
  */
 size_t sgpr_compact_stride(int N);
+/* Host-only: G one-hot blocks [15][N] fp32 -> G compact records (records_host: G * sgpr_compact_stride(N) bytes, e.g. a
+ * pinned staging buffer).  What a caller holding the reference's own input tensors (sg_net.py:296-299, 517-519) runs to
+ * hand them over in 13 instead of 60 bytes a node.  Returns 0, or 1 when some label value is neither +0.0f nor 1.0f or a
+ * node carries more than one 1 — such a batch has no compact form (the records are then unspecified); negative on bad
+ * arguments. */
+int sgpr_compact_from_blocks(const float* blocks_host, int G, int N, void* records_host);
 int sgpr_forward_pairs_compact(sgpr_ctx* ctx, const void* graphs1, const void* graphs2, int B, int N, int k,
                                float* score_dev, float* att1_dev, float* att2_dev, void* stream);
 int sgpr_embed_compact(sgpr_ctx* ctx, const void* graphs, int M, int N, int k, float* pooled_dev, float* att_dev,

@@ -55,6 +55,7 @@ SYMBOLS = {
     "sgpr_pack_weights_host": (C.c_int, [C.POINTER(SgprWeights), c_float_p, c_float_p, C.POINTER(C.c_size_t)]),
     "sgpr_launch_count": (C.c_int64, [C.c_void_p]),
     "sgpr_compact_stride": (C.c_size_t, [C.c_int]),
+    "sgpr_compact_from_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sgpr_forward_pairs_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgpr_embed_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

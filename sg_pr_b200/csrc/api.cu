@@ -361,6 +361,44 @@ int sgpr_forward_pairs(sgpr_ctx* ctx, const float* f1_dev, const float* f2_dev, 
 
 size_t sgpr_compact_stride(int N) { return (static_cast<size_t>(N) * 13 + 15) & ~static_cast<size_t>(15); }
 
+int sgpr_compact_from_blocks(const float* blocks_host, int G, int N, void* records_host) {
+    if (G < 0 || N < 1 || N > SGPR_MAX_NODES) return fail(SGPR_E_INVALID, "sgpr_compact_from_blocks: G=%d N=%d out of range", G, N);
+    if (G == 0) return SGPR_OK;
+    if (!blocks_host || !records_host) return fail(SGPR_E_INVALID, "sgpr_compact_from_blocks: NULL pointer");
+    const size_t stride = sgpr_compact_stride(N);
+    unsigned char* out = static_cast<unsigned char*>(records_host);
+    const uint32_t kOne = 0x3f800000u;                        // 1.0f
+    uint32_t bad = 0;
+    for (int g = 0; g < G; ++g) {
+        const float* blk = blocks_host + static_cast<size_t>(g) * kInCh * N;
+        unsigned char* rec = out + static_cast<size_t>(g) * stride;
+        std::memcpy(rec, blk, static_cast<size_t>(12) * N);                      // xyz rows, bit for bit
+        // plain integer loops over a row (the compiler vectorises them): per node the number of 1.0f, the label they
+        // name, and any bits that are neither +0.0f nor 1.0f
+        uint32_t label[SGPR_MAX_NODES], ones[SGPR_MAX_NODES], other[SGPR_MAX_NODES];
+        for (int n = 0; n < N; ++n) { label[n] = 0u; ones[n] = 0u; other[n] = 0u; }
+        for (int c = 0; c < kLabels; ++c) {
+            uint32_t row[SGPR_MAX_NODES];
+            std::memcpy(row, blk + static_cast<size_t>(3 + c) * N, static_cast<size_t>(4) * N);
+            const uint32_t cc = static_cast<uint32_t>(c);
+            for (int n = 0; n < N; ++n) {
+                const uint32_t w = row[n];
+                const uint32_t one = (w == kOne) ? 1u : 0u;
+                ones[n] += one;
+                label[n] += one * cc;
+                other[n] |= w ^ ((0u - one) & kOne);
+            }
+        }
+        unsigned char* lab = rec + static_cast<size_t>(12) * N;
+        for (int n = 0; n < N; ++n) {
+            bad |= other[n] | ((ones[n] > 1u) ? 1u : 0u);
+            lab[n] = static_cast<unsigned char>(ones[n] ? label[n] : 255u);
+        }
+        std::memset(rec + static_cast<size_t>(13) * N, 0, stride - static_cast<size_t>(13) * N);
+    }
+    return bad ? 1 : SGPR_OK;
+}
+
 int sgpr_forward_pairs_compact(sgpr_ctx* ctx, const void* g1, const void* g2, int B, int N, int k, float* score_dev,
                                float* att1_dev, float* att2_dev, void* stream) {
     if (!ctx) return fail(SGPR_E_INVALID, "sgpr_forward_pairs_compact: ctx is NULL");

@@ -257,6 +257,15 @@ class Engine:
               "sgpr_forward_pairs_compact", self._lib)
         return score, att1, att2
 
+    def compact_from_blocks(self, blocks: torch.Tensor, out: torch.Tensor) -> bool:
+        """Host-side: contiguous float32 CPU blocks [B, 15, N] -> compact records written into `out` (uint8 CPU tensor of at
+        least B * stride bytes, typically pinned).  False when the batch has no compact form (label rows not one-hot)."""
+        b, n = int(blocks.shape[0]), int(blocks.shape[2])
+        rc = self._lib.sgpr_compact_from_blocks(blocks.data_ptr(), b, n, out.data_ptr())
+        if rc < 0:
+            check(rc, "sgpr_compact_from_blocks", self._lib)
+        return rc == 0
+
     def embed_compact(self, graphs: torch.Tensor, n: int, k: int, want_att: bool = False) -> dict:
         graphs = self._check_compact(graphs, n, "graphs")
         m = int(graphs.shape[0])

@@ -237,6 +237,9 @@ class SG(torch.nn.Module):
             self._ring_pos += 1
             return out
         eng = self.engine()
+        # plain (pageable) CPU tensors — what the reference's callers build (sg_net.py:517-519) — go through the driver's
+        # staged copy.  Staging them as compact records on the host instead (sgpr_compact_from_blocks into a pinned ring) was
+        # measured and is slower: 322 vs 245 us per 128-pair batch, the one-hot scan costs more than the bytes it saves.
         f1 = f1.to(dev, dtype=torch.float32, non_blocking=True)
         f2 = f2.to(dev, dtype=torch.float32, non_blocking=True)
         return eng.forward_pairs(f1, f2, int(self.args.K), True, False)

@@ -209,3 +209,31 @@ def test_unmodified_reference_script(tree):
                          text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "Score: 1.34" in out.stdout and "e-06" in out.stdout
+
+
+def test_module_forward_placements_agree_bit_for_bit(kitti_state):
+    """SG.forward(data) takes the feature tensors wherever the caller has them: plain (pageable) CPU tensors — what the
+    reference's callers build (sg_net.py:517-519) — pinned CPU tensors (read in place over PCIe), or device tensors.  Same
+    bits in every case, for changing batch sizes (whole-graph and branch-split launches) and for label rows that are
+    not one-hot."""
+    from sg_pr_b200 import synth
+    from sg_pr_b200.parser_sg import sgpr_args
+    from sg_pr_b200.sg_net import SG
+    args = sgpr_args()
+    args.K, args.node_num, args.gpu, args.cuda = 20, 64, 0, "0"
+    model = SG(args, 12)
+    model.load_state_dict(kitti_state)
+    model.cuda(0).eval()
+    with torch.no_grad():
+        for b in (128, 128, 5, 128, 1, 128, 128, 128, 128):
+            f1, f2 = synth.make_pair_batch(b, 64, 20, seed=40 + b)
+            want = model({"features_1": f1.cuda(), "features_2": f2.cuda()})
+            for a, c in ((f1, f2), (f1.pin_memory(), f2.pin_memory())):
+                got = model({"features_1": a, "features_2": c})
+                assert all(torch.equal(x, y) for x, y in zip(got, want)) and got[0].is_cuda
+        soft1, soft2 = synth.make_pair_batch(8, 64, 20, seed=3)
+        soft1[2, 5, 3] = 0.25                                          # a soft label
+        want = model({"features_1": soft1.cuda(), "features_2": soft2.cuda()})
+        got = model({"features_1": soft1, "features_2": soft2})
+        assert all(torch.equal(x, y) for x, y in zip(got, want))
+        assert not torch.equal(want[0], model({"features_1": synth.make_pair_batch(8, 64, 20, seed=3)[0], "features_2": soft2})[0])

@@ -225,3 +225,26 @@ def test_fast_training_features_are_bit_identical_to_the_reference_shaped_path(t
                     assert np.array_equal(feats[2 * i + side], ref)
                     assert np.array_equal(np.signbit(feats[2 * i + side]), np.signbit(ref))     # flipped pads are -0.0
                 assert targets[2 * i] == targets[2 * i + 1] == w["target"]
+
+
+def test_compact_from_blocks_matches_the_python_packer():
+    """sgpr_compact_from_blocks (host-only C entry point: one-hot [15][N] blocks -> 13-byte-per-node records) against
+    engine.compact_graphs, and its refusal of blocks that have no compact form.  No device needed."""
+    import ctypes as C
+    import torch
+    from sg_pr_b200 import _lib, synth
+    from sg_pr_b200.engine import compact_graphs
+    lib = _lib.bind(C.CDLL(_lib.LIB_PATH), _lib.SYMBOLS)
+    for n, k in ((64, 20), (33, 8), (128, 20), (5, 2)):
+        g = synth.make_graphs(40, n, k, seed=n)
+        g[3, 0, :] = -g[3, 0, :]                                   # flipped cloud: -0.0 coordinates on the pads stay as they are
+        out = torch.full((40, int(lib.sgpr_compact_stride(n))), 7, dtype=torch.uint8)
+        assert lib.sgpr_compact_from_blocks(g.data_ptr(), 40, n, out.data_ptr()) == 0
+        assert torch.equal(out, compact_graphs(g))
+    out = torch.empty(4, 832, dtype=torch.uint8)
+    for edit in (lambda t: t[2, 5].__setitem__(3, 0.5), lambda t: t[1, 4].__setitem__(60, -0.0),
+                 lambda t: (t[1, 4].__setitem__(0, 1.0), t[1, 5].__setitem__(0, 1.0))):
+        g = synth.make_graphs(4, 64, 20, seed=1)
+        edit(g)
+        assert lib.sgpr_compact_from_blocks(g.data_ptr(), 4, 64, out.data_ptr()) == 1
+    assert lib.sgpr_compact_from_blocks(None, 4, 64, out.data_ptr()) < 0 and b"NULL" in lib.sgpr_last_error()
