@@ -113,6 +113,17 @@ __device__ __forceinline__ void cmpx(float& a, float& b) {
     const float lo = fminf(a, b), hi = fmaxf(a, b);
     a = lo; b = hi;
 }
+// max of three in ONE instruction (sm_100 FMNMX3): the neighbour-max of the gather is bound by the half-rate min/max
+// pipe, and max is exact and order-independent, so regrouping changes no bit
+__device__ __forceinline__ float max3(float a, float b, float c) {
+#ifdef SGPR_EMU
+    return fmaxf(fmaxf(a, b), c);
+#else
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+#endif
+}
 __device__ __forceinline__ float warp_sum(float s) {
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, d));
@@ -645,8 +656,8 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ sY, const 
 #pragma unroll
             for (int p = 0; p < CPL; ++p) {
 #pragma unroll
-                for (int q = 0; q < GW; ++q)
-                    m[p] = fmaxf(m[p], fmaxf(fmaxf(v[4 * q][p], v[4 * q + 1][p]), fmaxf(v[4 * q + 2][p], v[4 * q + 3][p])));
+                for (int q = 0; q < GW; ++q)      // 4 neighbours + the running max: two 3-input max
+                    m[p] = max3(m[p], max3(v[4 * q][p], v[4 * q + 1][p], v[4 * q + 2][p]), v[4 * q + 3][p]);
             }
         }
         float zz[CPL];
@@ -701,8 +712,8 @@ __device__ __forceinline__ void xyz_rows(const float* __restrict__ sT, const uin
                 e0[u] = fmaf(p0.z, d2, fmaf(p0.y, d1, __fmul_rn(p0.x, d0)));
                 e1[u] = fmaf(q0.z, d2, fmaf(q0.y, d1, __fmul_rn(q0.x, d0)));
             }
-            m0 = fmaxf(fmaxf(m0, fmaxf(e0[0], e0[1])), fmaxf(e0[2], e0[3]));
-            m1 = fmaxf(fmaxf(m1, fmaxf(e1[0], e1[1])), fmaxf(e1[2], e1[3]));
+            m0 = max3(m0, max3(e0[0], e0[1], e0[2]), e0[3]);
+            m1 = max3(m1, max3(e1[0], e1[1], e1[2]), e1[3]);
         }
         float y0 = fmaf(p0.w, xi.x, m0); y0 = fmaf(p1.x, xi.y, y0); y0 = fmaf(p1.y, xi.z, y0);
         float y1 = fmaf(q0.w, xi.x, m1); y1 = fmaf(q1.x, xi.y, y1); y1 = fmaf(q1.y, xi.z, y1);
