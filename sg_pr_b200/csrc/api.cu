@@ -270,6 +270,7 @@ int launch_embed(sgpr_ctx* ctx, EmbedArgs a, cudaStream_t st) {
     a.order = nullptr;
     a.work_ctr = nullptr;
     a.split = 0;
+    a.sm_count = ctx->sm_count;
     a.halves = nullptr;
     a.gctr = nullptr;
     // Small launches run one BRANCH of a graph per work unit: the xyz and the semantic EdgeConv stacks are independent

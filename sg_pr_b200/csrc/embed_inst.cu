@@ -19,10 +19,12 @@ cudaError_t embed_optin<SGPR_INST_NPL>(int optin_bytes) {
     return cudaSuccess;
 #else
     // the dynamic limit excludes each kernel's static __shared__ bytes
-    const void* fns[4] = {reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 0, 0>),
+    const void* fns[6] = {reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 0, 0>),
                           reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 1, 0>),
                           reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 0, 1>),
-                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 1, 1>)};
+                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 1, 1>),
+                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 0, 1, 1>),
+                          reinterpret_cast<const void*>(&sgpr_embed_kernel<SGPR_INST_NPL, 1, 1, 1>)};
     for (const void* fn : fns) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, fn);
@@ -37,8 +39,11 @@ cudaError_t embed_optin<SGPR_INST_NPL>(int optin_bytes) {
 template <>
 void embed_launch<SGPR_INST_NPL>(int ties, int grid, int smem, cudaStream_t st, const EmbedArgs& a, const PackedWeights& pw,
                                  const HeadParams& hp) {
-    const auto kern = (ties == SGPR_TIES_CPU) ? (a.split ? &sgpr_embed_kernel<SGPR_INST_NPL, 1, 1> : &sgpr_embed_kernel<SGPR_INST_NPL, 1, 0>)
-                                              : (a.split ? &sgpr_embed_kernel<SGPR_INST_NPL, 0, 1> : &sgpr_embed_kernel<SGPR_INST_NPL, 0, 0>);
+    // a split launch whose units all get an SM of their own (`sole`) runs the one-CTA-per-SM compilation
+    const bool sole = a.split && 2 * a.G <= a.sm_count;
+    const auto kern = (ties == SGPR_TIES_CPU)
+        ? (sole ? &sgpr_embed_kernel<SGPR_INST_NPL, 1, 1, 1> : a.split ? &sgpr_embed_kernel<SGPR_INST_NPL, 1, 1> : &sgpr_embed_kernel<SGPR_INST_NPL, 1, 0>)
+        : (sole ? &sgpr_embed_kernel<SGPR_INST_NPL, 0, 1, 1> : a.split ? &sgpr_embed_kernel<SGPR_INST_NPL, 0, 1> : &sgpr_embed_kernel<SGPR_INST_NPL, 0, 0>);
     SGPR_LAUNCH(kern, grid, kThreads, smem, st, a, pw, hp);
 }
 

@@ -85,6 +85,7 @@ struct EmbedArgs {
                             //    the critical path of a graph when the launch has fewer graphs than CTA slots.  Same results.
     float* halves;          // split: [G][2][N][32] branch outputs handed to the merging unit
     int* gctr;              // split: [G] arrival counters, zero on entry, zero on exit
+    int sm_count;           // SMs of the device (launch-side choice between the compilations of the kernel)
 };
 
 struct SmemLayout {
@@ -965,8 +966,10 @@ __device__ __forceinline__ void conv_end_dispatch(const float* sCat, const float
 #endif
 // TIES: 0 = lowest index first (ATen CUDA topk), 1 = ATen CPU nth_element order.  SPLIT: 1 = one branch of a graph per
 // work unit (EmbedArgs::split) — its own instantiation so that the whole-graph kernel's register allocation is untouched.
-template <int NPL, int TIES = 0, int SPLIT = 0>
-__global__ void __launch_bounds__(kThreads, (NPL <= 2) ? SGPR_MINBLOCKS_SMALL : 1)
+// RICH: 1 = compiled for ONE CTA per SM (up to 255 registers, no spills) — launches whose work units all have an SM to
+// themselves anyway (5 % off the small-batch latency floor).
+template <int NPL, int TIES = 0, int SPLIT = 0, int RICH = 0>
+__global__ void __launch_bounds__(kThreads, (NPL <= 2 && !RICH) ? SGPR_MINBLOCKS_SMALL : 1)
 sgpr_embed_kernel(const EmbedArgs A, const PackedWeights W, const HeadParams H) {
     constexpr int NMAX = 32 * NPL;
     SGPR_DYN_SMEM(smem);
