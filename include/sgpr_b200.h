@@ -17,6 +17,10 @@
  *   - Return value: SGPR_OK (0) or a negative SGPR_E_* code; sgpr_last_error() gives the text for the calling
  *     thread.  The reference signals the same conditions with Python exceptions (e.g. topk raising when k > N,
  *     dgcnn.py:19; load_state_dict(strict) raising on a shape mismatch, sg_net.py:174).
+ *   - A context is not re-entrant: it owns device workspace (arrival counters, the branch hand-over buffer, the
+ *     ordering pre-pass) that consecutive launches share, so calls on ONE context must be issued from one thread at
+ *     a time and onto one stream (or onto streams the caller orders against each other).  The reference has the same
+ *     shape: a single Python thread, one CUDA stream.  Use one context per concurrent stream.
  *   - There is no CPU implementation behind this ABI: without a CUDA device sgpr_create fails.
  */
 #ifndef SGPR_B200_H
