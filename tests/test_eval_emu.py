@@ -163,3 +163,32 @@ def test_emulated_branch_split_launch_is_bit_identical(kitti_state, monkeypatch)
     assert torch.equal(split.forward_pairs(f1, f2, 10)[0], whole.forward_pairs(f1, f2, 10)[0])
     split.close()
     whole.close()
+
+
+def test_emulated_random_shapes_vs_oracle(kitti_state):
+    """A seeded random walk over (node_num, k, batch, density): odd node counts on both sides of the 32 / 64 row-tiling
+    boundaries, k from 1 up, dense batches under the CPU tie rule — every score and attention value within 1e-5 of the
+    oracle, compact records bit-identical to the one-hot blocks.  Small batches launch branch-split, larger ones do not."""
+    import random
+    from sg_pr_b200.engine import compact_graphs
+    from tests.emu import build_emu
+    eng = Engine(lib=_lib.bind(C.CDLL(build_emu.build()), _lib.SYMBOLS))
+    eng.set_weights(kitti_state)
+    rnd = random.Random(11)
+    for it in range(12):
+        n = rnd.choice([2, 3, 5, 17, 31, 33, 47, 63, 65, 96])
+        k = rnd.randint(1, max(1, min(n - 1, 24)))
+        b = rnd.choice([1, 2, 3, 5])
+        dense = rnd.random() < 0.25
+        try:
+            f1, f2 = synth.make_pair_batch(b, n, k, seed=it, dense=dense)
+        except ValueError:                                   # no room for k pads: only a dense graph has this (n, k)
+            f1, f2 = synth.make_pair_batch(b, n, k, seed=it, dense=True)
+            dense = True
+        eng.set_knn_ties("cpu" if dense else "cuda")         # the oracle is the reference on the CPU
+        got = eng.forward_pairs(f1, f2, k)
+        want = orc.forward_pairs(f1, f2, k, kitti_state)
+        assert float((got[0] - want["score"]).abs().max()) <= 1e-5, (n, k, b, dense)
+        assert float((got[1] - want["att_1"]).abs().max()) <= 1e-5 and float((got[2] - want["att_2"]).abs().max()) <= 1e-5
+        assert torch.equal(eng.forward_pairs_compact(compact_graphs(f1), compact_graphs(f2), n, k)[0], got[0])
+    eng.close()
