@@ -487,7 +487,7 @@ def main():
                     "c_abi_host_call": {"value": total_pairs / (cabi_ms * 1e-3), "ms_per_step": cabi_ms / args.steps},
                     "pageable_inputs": {"value": total_pairs / (page_ms * 1e-3), "ms_per_step": page_ms / args.steps,
                                         "api": "the same call with plain (pageable) torch.FloatTensor inputs, as the reference's "
-                                               "callers build them (sg_net.py:517-519): two staged H2D copies, then the kernel"},
+                                               "callers build them (sg_net.py:517-519): one host copy into the module's pinned staging ring, read in place by the kernel"},
                     "compact_inputs": {"value": total_pairs / (compact_ms * 1e-3), "ms_per_step": compact_ms / args.steps,
                                        "h2d_bytes_per_step": int(2 * BATCH * c1_pin.shape[-1]),
                                        "api": "Engine.forward_pairs_compact on pinned 13-byte-per-node records + score.cpu()"}},
