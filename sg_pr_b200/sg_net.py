@@ -120,7 +120,7 @@ class SG(torch.nn.Module):
         self._packed_version = None
         self._pinned_in_flight = []
         self._ring_pos = 0
-        self._staging = None
+        self._staging = {}
 
     def calculate_bottleneck_features(self):
         self.feature_count = self.args.tensor_neurons
@@ -246,11 +246,13 @@ class SG(torch.nn.Module):
                 and f2.dtype == torch.float32 and f1.dim() == 3 and f1.shape[1] == 15 and f2.shape == f1.shape
                 and f1.shape[0] > 0 and os.environ.get("SGPR_NO_STAGING") != "1"):
             key = (int(f1.shape[0]), int(f1.shape[2]))
-            ring = self._staging
-            if ring is None or ring["key"] != key:
-                if ring is not None:
-                    torch.cuda.synchronize(dev)          # a queued kernel may still be reading the old buffers
-                ring = self._staging = {"key": key, "pos": 0, "slots": [
+            rings = self._staging                        # one ring per batch shape (full batches and the tail batch alternate)
+            ring = rings.get(key)
+            if ring is None:
+                if len(rings) >= 4:                      # an unusual caller with many shapes: drop the oldest ring
+                    torch.cuda.synchronize(dev)          # a queued kernel may still be reading its buffers
+                    rings.pop(next(iter(rings)))
+                ring = rings[key] = {"pos": 0, "slots": [
                     [torch.empty((2,) + tuple(f1.shape), dtype=torch.float32, pin_memory=True), torch.cuda.Event(), False]
                     for _ in range(4)]}
             slot = ring["slots"][ring["pos"] % 4]

@@ -225,7 +225,7 @@ def test_module_forward_placements_agree_bit_for_bit(kitti_state):
     model.load_state_dict(kitti_state)
     model.cuda(0).eval()
     with torch.no_grad():
-        for b in (128, 128, 5, 128, 1, 128, 128, 128, 128):
+        for b in (128, 128, 5, 128, 1, 128, 2, 3, 7, 128, 128, 5, 128):      # more shapes than staging rings are kept
             f1, f2 = synth.make_pair_batch(b, 64, 20, seed=40 + b)
             want = model({"features_1": f1.cuda(), "features_2": f2.cuda()})
             for a, c in ((f1, f2), (f1.pin_memory(), f2.pin_memory())):
