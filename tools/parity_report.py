@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Parity at scale (SURVEY §4 test-pyramid item 4): >= 10^4 KITTI-shape pairs through the fused kernel vs the oracle, with
 every k-NN row mismatch classified (exact tie / near tie / real), plus the shape sweep at smaller counts.
-Writes one JSON document to stdout (committed as profiles/r01_parity_report.json)."""
+Writes one JSON document to stdout (committed as profiles/r01_parity_report.json, profiles/r02_parity_report*.json)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,10 +11,14 @@ from sg_pr_b200.engine import Engine
 
 sd = orc.load_state_npz(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "model_kitti.npz"))
 eng = Engine(0); eng.set_weights(sd)
+SD64 = {name: (v.double() if v.dtype.is_floating_point else v) for name, v in sd.items()}
 NEAR = orc.NEAR_TIE   # near tie: swapped columns differ by <= NEAR * (xx_i + max_j xx_j) in reference distance — the
                       # rounding scale of pd = 2 x_i.x_j - xx_j - xx_i (dgcnn.py:15-17)
 
-def run(n, k, pairs, seed0, chunk=256):
+CHUNK = int(os.environ.get("SGPR_PARITY_CHUNK", "256"))   # pairs per launch: 256 = persistent launches, <= 98 = branch-split ones
+
+
+def run(n, k, pairs, seed0, chunk=CHUNK):
     rep = {"N": n, "k": k, "pairs": 0, "rows_checked": 0, "rows_equivalent": 0, "rows_exact_tie_swap": 0, "rows_near_tie": 0,
            "rows_real_mismatch": 0, "mismatch_rows": [],
            "pairs_within_1e-5": 0, "pairs_off_explained_by_near_tie": 0, "pairs_off_unexplained": 0,
@@ -24,6 +28,17 @@ def run(n, k, pairs, seed0, chunk=256):
         f1, f2 = synth.make_pair_batch(b, n, k, seed=seed0 + c0)
         want = orc.forward_pairs(f1, f2, k, sd, want_trace=True)
         score, a1, a2 = eng.forward_pairs(f1.cuda(), f2.cuda(), k)
+        if c0 == 0:
+            # who is closer to the exact value?  the same path in float64 on the first chunk: the kernel and the fp32
+            # reference are two fp32 roundings of it (different summation orders), and the 1e-5 bar compares them
+            # (a near-tie k-NN row that float64 decides differently moves a score by 1e-3 and more: those pairs are counted
+            # apart, the maxima are over the pairs where all three agree on the neighbours)
+            w64 = orc.forward_pairs(f1.double(), f2.double(), k, SD64)["score"].float()
+            dk, dr = (score.cpu() - w64).abs(), (want["score"] - w64).abs()
+            same = (dk <= 1e-4) & (dr <= 1e-4)
+            rep["fp64_check"] = {"pairs": b, "pairs_with_a_knn_flip_against_fp64": int((~same).sum()),
+                                 "max_abs_kernel_vs_fp64": float(dk[same].max()),
+                                 "max_abs_reference_fp32_vs_fp64": float(dr[same].max())}
         got1 = eng.embed(f1.cuda(), k, trace=True)["knn"].cpu().long()
         got2 = eng.embed(f2.cuda(), k, trace=True)["knn"].cpu().long()
         first_bad = torch.zeros(b, dtype=torch.bool)          # pair has a first divergence that is a real mismatch
@@ -93,5 +108,6 @@ except Exception as ex:  # pragma: no cover
     out["reference_modules_on_gpu_vs_cpu"] = repr(ex)
 for n, k, p in ((16, 10, 512), (32, 10, 512), (64, 10, 512), (100, 10, 512), (128, 10, 256), (128, 20, 256)):
     out["configs"].append(run(n, k, p, 20_000 + n * 7 + k))
+out["pairs_per_launch"] = CHUNK
 out["seconds"] = round(time.time() - t0, 1)
 print(json.dumps(out, indent=1))
