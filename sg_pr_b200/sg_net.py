@@ -648,7 +648,12 @@ class SGTrainer(object):
             # the batch holds every listed pair in both orders (features_2[p] == features_1[p ^ 1] by construction), so
             # both sides are the same BatchNorm batch: one EdgeConv pass per graph serves both (mirrored step) and
             # features_2 is never materialised
-            f1, targets = self._training_batch(batch)
+            ahead = getattr(self, "_prefetched", None)
+            self._prefetched = None
+            if ahead is not None and ahead[0] is batch:
+                f1, targets = ahead[1], ahead[2]              # built while the previous step ran on the device (fit())
+            else:
+                f1, targets = self._training_batch(batch)
             eng = self._device_trainer()
             dev = eng.device
             feats = torch.from_numpy(f1)
@@ -656,6 +661,12 @@ class SGTrainer(object):
             loss, prediction = eng.step(feats.to(dev, non_blocking=True), None, target.to(dev, non_blocking=True),
                                         int(self.args.K), apply=True, mirrored=True)
             self._unsynced_steps += 1
+            upcoming = getattr(self, "_upcoming_batch", None)
+            self._upcoming_batch = None
+            if upcoming is not None and len(upcoming) > 0:
+                # fit() named the batch that follows: build it now, while this step runs on the device — the same draws
+                # in the same order as building it at the top of the next call (nothing else touches the streams between)
+                self._prefetched = (upcoming,) + self._training_batch(upcoming)
             return (loss.item(), prediction.cpu().numpy().reshape(-1), target.numpy().reshape(-1))
         f1, targets = [], []
         if getattr(self, "_json_cache", None) is None:
@@ -690,6 +701,8 @@ class SGTrainer(object):
             self.model.train()
             self.loss_sum, main_index = 0, 0
             for index, batch in tqdm(enumerate(batches), total=len(batches), desc="Batches"):
+                if not self.device_augment and index + 1 < len(batches):
+                    self._upcoming_batch = batches[index + 1]   # host prep of the next batch overlaps this batch's device step
                 loss_score, _, _ = self.process_batch(batch)
                 main_index += len(batch)
                 self.loss_sum += loss_score * len(batch)

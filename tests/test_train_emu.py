@@ -148,6 +148,27 @@ def test_emulated_process_batch_glue(emu_lib, golden_dir, tmp_path):
         ref = work[name]
         assert float((synced[name] - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), name
     assert not torch.equal(synced["attention.weight_matrix"], state0["attention.weight_matrix"])
+
+    # fit()'s pipelining: naming the batch that follows makes process_batch build it while the current step runs on the
+    # device — the same draws in the same order, hence the same batches, losses and stream positions as without it
+    batches = [trainer.training_graphs, list(reversed(trainer.training_graphs)), trainer.training_graphs[:1]]
+
+    def epoch(prefetch):
+        eng.set_state(state0, reset_optimizer=True)
+        random.seed(9); np.random.seed(9)
+        out = []
+        for i, b in enumerate(batches):
+            if prefetch and i + 1 < len(batches):
+                trainer._upcoming_batch = batches[i + 1]
+            out.append(trainer.process_batch(b, True))
+        assert getattr(trainer, "_prefetched", None) is None and getattr(trainer, "_upcoming_batch", None) is None
+        return out, (np.random.rand(), random.random())
+
+    plain, tail_plain = epoch(False)
+    piped, tail_piped = epoch(True)
+    assert tail_plain == tail_piped
+    for x, y in zip(plain, piped):
+        assert x[0] == y[0] and np.array_equal(x[1], y[1]) and np.array_equal(x[2], y[2])
     eng.close()
 
 

@@ -64,13 +64,17 @@ def make_trainer(**kw):
     return t
 
 
-def run(label, trainer, fn, warm=False):
+def run(label, trainer, fn, warm=False, pipelined=False):
     fn(batches[0])                                     # warm-up: context, workspace, first upload
     if warm:                                           # epoch 2 onwards: every file parsed / every graph uploaded already
         for b in batches:
             fn(b)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    losses = [fn(b)[0] for b in batches]
+    losses = []
+    for i, b in enumerate(batches):
+        if pipelined and i + 1 < len(batches):         # what fit() does: the next batch is built while this step runs
+            trainer._upcoming_batch = batches[i + 1]
+        losses.append(fn(b)[0])
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(json.dumps({"arm": label, "listed_pairs": len(pairs), "batch": args.batch, "seconds": round(dt, 4),
                       "listed_pairs_per_s": round(len(pairs) / dt, 1), "ms_per_batch": round(dt / len(batches) * 1e3, 3),
@@ -109,6 +113,8 @@ run("reference-shaped host prep (re-read JSON, python one-hot, both sides) + dev
 t2 = make_trainer()
 run("default, first epoch: cached parse + vectorised one-hot + mirrored device step (reference RNG order)", t2, lambda b: t2.process_batch(b, True))
 run("default, later epochs", t2, lambda b: t2.process_batch(b, True), warm=True)
+run("default, later epochs, as fit() drives it (next batch's host prep overlaps the device step)", t2,
+    lambda b: t2.process_batch(b, True), warm=True, pipelined=True)
 
 t3 = make_trainer(device_augment=True, augment_seed=1)
 run("device_augment, first epoch (parses + uploads every graph once): sgpr_train_assemble + mirrored device step", t3, lambda b: t3.process_batch(b, True))
