@@ -58,3 +58,14 @@ def test_our_arm_line_carries_every_key():
     small = line["small_batch"]
     assert 0 < small["B1_kernel_us"] <= small["B37_kernel_us"] * 1.1 and small["B37_kernel_us"] < line["ms_per_step"] * 1e3
     assert small["one_pair_e2e_us"] > small["B1_kernel_us"]
+
+
+def test_profiles_index_names_existing_files():
+    """profiles/current.json (read by bench.py for the roofline's measured DRAM traffic) names captures that are committed."""
+    with open(os.path.join(ROOT, "profiles", "current.json")) as f:
+        index = json.load(f)
+    names = [n for v in index.values() for n in (v if isinstance(v, list) else [v])]
+    missing = [n for n in names if not os.path.exists(os.path.join(ROOT, "profiles", n))]
+    assert not missing, missing
+    with open(os.path.join(ROOT, "profiles", index["embed_ncu_summary"])) as f:
+        assert json.load(f)["dram_bytes_per_launch"] > 0
