@@ -47,8 +47,9 @@ def _worker(rank, world, port, m, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("m", [9, 12])      # unequal blocks (pad path) and equal blocks (direct, one collective)
-def test_two_rank_scan_matches_single_rank(tmp_path, m):
+# unequal blocks (pad path) and equal blocks (direct, one collective) on two ranks; three ranks with a ragged last block
+@pytest.mark.parametrize("world,m", [(2, 9), (2, 12), (3, 10)])
+def test_sharded_scan_matches_single_rank(tmp_path, world, m):
     from oracle import sgpr_oracle as orc
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sd = orc.load_state_npz(os.path.join(root, "tests", "golden", "model_kitti.npz"))
@@ -58,10 +59,10 @@ def test_two_rank_scan_matches_single_rank(tmp_path, m):
     single, _ = scan.scan_all_pairs(graphs, 10, lambda g, k: orc.embed_graphs(g, k, sd)["pooled"].squeeze(-1),
                                     lambda r, c, out=None: orc.score_matrix(r, c, sd))
     assert torch.equal(single, want)
-    mp.spawn(_worker, args=(2, _free_port(), m, str(tmp_path)), nprocs=2, join=True)
-    outs = [torch.load(tmp_path / f"r{r}.pt") for r in range(2)]
+    mp.spawn(_worker, args=(world, _free_port(), m, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
     for r, o in enumerate(outs):
         assert o["full"].shape == (m, m)
         assert torch.allclose(o["full"], want, atol=1e-6), r       # every rank ends up with the whole matrix
         assert torch.allclose(o["local"], want[o["lo"]:o["hi"]], atol=1e-6)
-    assert (outs[0]["lo"], outs[1]["hi"]) == (0, m) and outs[0]["hi"] == outs[1]["lo"]
+    assert (outs[0]["lo"], outs[-1]["hi"]) == (0, m) and all(outs[r]["hi"] == outs[r + 1]["lo"] for r in range(world - 1))
